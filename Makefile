@@ -1,0 +1,36 @@
+# xmp_b200 build: host C library, sm_100a CUDA library (C ABI), the fastdnamp_b200 CLI, and the
+# test-only oracle.  Everything is built in-tree so that the .so files travel with the snapshot.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --use_fast_math
+CFLAGS    := -O2 -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
+
+CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu
+CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh include/xmp_cuda.h
+HOST_SRCS := host/phylip.c host/prep.c host/trees.c
+
+.PHONY: all host cuda cli oracle ref clean
+all: host cuda cli oracle
+
+host: host/libxmp_host.so
+host/libxmp_host.so: $(HOST_SRCS) host/xmp_host.h
+	$(CC) $(CFLAGS) -shared -o $@ $(HOST_SRCS)
+
+cuda: xmp_b200/libxmp_b200.so
+xmp_b200/libxmp_b200.so: $(CUDA_SRCS) $(CUDA_HDRS)
+	$(NVCC) $(NVFLAGS) -shared -cudart static -o $@ $(CUDA_SRCS) 2> xmp_b200/csrc/ptxas.log || (cat xmp_b200/csrc/ptxas.log; exit 1)
+
+cli: fastdnamp_b200
+fastdnamp_b200: host/fastdnamp.c host/libxmp_host.so xmp_b200/libxmp_b200.so
+	$(CC) $(CFLAGS) -fPIE -o $@ host/fastdnamp.c -Ihost -Iinclude -Lhost -Lxmp_b200 -lxmp_host -lxmp_b200 \
+	  -Wl,-rpath,'$$ORIGIN/host' -Wl,-rpath,'$$ORIGIN/xmp_b200' -lpthread
+
+oracle:
+	$(MAKE) -C oracle oracle
+ref:
+	$(MAKE) -C oracle ref
+
+clean:
+	rm -f host/libxmp_host.so xmp_b200/libxmp_b200.so fastdnamp_b200 xmp_b200/csrc/ptxas.log
+	$(MAKE) -C oracle clean

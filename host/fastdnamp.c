@@ -1,0 +1,491 @@
+/* fastdnamp_b200 -- the fastdnamp command line over the B200 search library.
+ *
+ * Same command line, same PHYLIP input handling, same result files as the reference's fastdnamp
+ * (reference src/fastdnamp.c:22-161, option parsing src/common.c:73-250, settings report :252-369,
+ * timing report :456-481).  What differs is only what `north_star` says must differ: the branch and
+ * bound itself runs on the GPU(s) through include/xmp_cuda.h, and the MPI boss/worker pair
+ * (src/mpiboss.c, src/mpiworker.c) is replaced by one host thread per GPU that shares the upper bound
+ * and hands subtree jobs to idle GPUs.  Two options are new: --gpus=<n> and --membudget=<MiB>.
+ *
+ * Not built in (the reference computes them on the CPU before the search; see DESIGN.md "Out of
+ * scope"): the -Bi/-Bk/-BK/-Bh/-Bp lower bounds (load their restBound.txt with -Bf <file>) and the TBR
+ * heuristic (--tbr is accepted and ignored: a greedy beam dive on the device seeds the bound instead).
+ */
+#include <limits.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include "xmp_cuda.h"
+#include "xmp_host.h"
+
+#define PROGNAME "fastDNAmp"
+#define PROGLONGNAME "fastDNAmp: Exact Maximum Parsimony Phylogenetic Tree Search v1.1"
+
+typedef struct {
+	xmph_settings s;
+	unsigned update_secs, seed, n_gpus;
+	size_t mem_budget;
+	int rand1, rand2, rand3;
+	const char *in_name, *out_name;
+	FILE *in, *out;
+} cli;
+
+static double now_seconds(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+static void die(const char *msg) {
+	fprintf(stderr, "%s\n", msg);
+	exit(1);
+}
+
+static void usage(void) {
+	fprintf(stderr,
+	        "Syntax: " PROGNAME " [<options>] <phylipfile>\n"
+	        "  -o <fname>   File to write results to, instead of standard output\n"
+	        "  -b <nn>      Specify an initial upper bound (or 0 for no bound)\n"
+	        "  -m <nn>      Maximum number of trees to save (or 0 for no limit)\n"
+	        "  -r           Output trees in raw (Newick) format (default: NEXUS format)\n"
+	        "  -d           Discard sites containing gaps/ambiguous states\n"
+	        "                 (default: like GAPMODE=MISSING in PAUP*)\n"
+	        "  -q           Quiet mode: only the final set of trees is output\n"
+	        "  -B<letters>  Lower bounds: d = distinct bases (default), m = MST, f <fname> = load restBound[]\n"
+	        "  --startcol=<nn>           Starting site number (first site is site 1)\n"
+	        "  --endcol=<nn>             Ending site number\n"
+	        "  --displaynewbounds={Y|N}  Control printing of updated bounds while running\n"
+	        "  --displaynewtrees={Y|N}   Control printing of best trees while running\n"
+	        "  --updatesecs=<nn>         Update progress every <nn> seconds (use 0 to\n"
+	        "                              turn off periodic progress updates)\n"
+	        "  --seed=<nn>               Use <nn> as the random number generation seed --\n"
+	        "                              0 (the default) means 'pick a random seed'\n"
+	        "  --gpus=<nn>               Number of GPUs to search on (default 1)\n"
+	        "  --membudget=<MiB>         Device memory the search frontier may use per GPU\n");
+}
+
+/* "--name", "--name=Y|N": returns 1 if arg names this option. */
+static int bool_option(const char *arg, const char *name, unsigned *flags, unsigned mask) {
+	size_t n = strlen(name);
+	if (strncmp(arg, name, n) != 0 || (arg[n] != 0 && arg[n] != '=')) return 0;
+	const char *v = arg[n] ? arg + n + 1 : "";
+	if (*v == 0 || *v == 'Y' || *v == 'y' || *v == '1' || *v == 'T' || *v == 't') *flags |= mask; else *flags &= ~mask;
+	return 1;
+}
+
+static int unsigned_option(const char *arg, const char *name, unsigned *out) {
+	size_t n = strlen(name);
+	if (strncmp(arg, name, n) != 0 || arg[n] != '=' || arg[n + 1] == 0) return 0;
+	*out = (unsigned) strtoul(arg + n + 1, NULL, 10);
+	return 1;
+}
+
+static int parse_args(int argc, char **argv, cli *c) {
+	unsigned ignored = 0, mb = 0;
+	if (argc < 2) { usage(); return 0; }
+	for (int i = 1; i < argc; ++i) {
+		const char *a = argv[i];
+		if (a[0] != '-') {
+			c->in_name = a;
+			if (!(c->in = fopen(a, "r"))) {
+				fprintf(stderr, "File '%s' could not be opened for input, aborting.\n", a);
+				exit(1);
+			}
+			continue;
+		}
+		switch (a[1]) {
+		case 'b':
+			if (++i >= argc) die("Option -b needs a value, aborting.");
+			c->s.bound = (unsigned) atoi(argv[i]);
+			if (c->s.bound == 0) c->s.bound = XMPH_NO_LIMIT;
+			break;
+		case 'o':
+			if (++i >= argc) die("Option -o needs a value, aborting.");
+			if (!(c->out = fopen(argv[i], "w"))) {
+				fprintf(stderr, "File '%s' could not be opened for output, aborting.\n", argv[i]);
+				exit(1);
+			}
+			c->out_name = argv[i];
+			break;
+		case 'm':
+			if (++i >= argc) die("Option -m needs a value, aborting.");
+			c->s.max_trees = (unsigned) atoi(argv[i]);
+			if (c->s.max_trees == 0) c->s.max_trees = XMPH_NO_LIMIT;
+			break;
+		case 'r': c->s.options &= ~XMPH_OPT_NEXUSFMT; break;
+		case 'd': c->s.options |= XMPH_OPT_DISCARDMISSAMBIG; break;
+		case 'q':
+			c->s.options |= XMPH_OPT_QUIET;
+			c->s.options &= ~(XMPH_OPT_DISPLAYNEWBOUNDS | XMPH_OPT_DISPLAYNEWTREES);
+			c->update_secs = 0;
+			break;
+		case 'B':
+			c->s.options &= ~(XMPH_OPT_USELOADRESTBOUND | XMPH_OPT_USEDISTBASESBOUNDREST | XMPH_OPT_USEINCOMPATBOUNDREST |
+			                  XMPH_OPT_USEMSTBOUNDREST | XMPH_OPT_USEKICKASSBOUNDREST | XMPH_OPT_USEKA2BOUNDREST |
+			                  XMPH_OPT_USEGREEDYHITTINGSETBOUND | XMPH_OPT_USEPARTBOUND);
+			for (const char *p = a + 2; *p; ++p) {
+				switch (*p) {
+				case 'd': c->s.options |= XMPH_OPT_USEDISTBASESBOUNDREST; break;
+				case 'i': c->s.options |= XMPH_OPT_USEINCOMPATBOUNDREST; break;
+				case 'm': c->s.options |= XMPH_OPT_USEMSTBOUNDREST; break;
+				case 'k': c->s.options |= XMPH_OPT_USEKICKASSBOUNDREST; break;
+				case 'K': c->s.options |= XMPH_OPT_USEKA2BOUNDREST; break;
+				case 'h': c->s.options |= XMPH_OPT_USEGREEDYHITTINGSETBOUND; break;
+				case 'p': c->s.options |= XMPH_OPT_USEPARTBOUND; break;
+				case 'C': case 'L':
+					if (!(c->s.options & XMPH_OPT_USEPARTBOUND)) {
+						fprintf(stderr, "To specify the '%c' option, you must have previously specified -Bp.\n", *p);
+						exit(1);
+					}
+					break;
+				case 'f':
+					if (i + 1 >= argc) die("Option -Bf needs a file name, aborting.");
+					c->s.options |= XMPH_OPT_USELOADRESTBOUND;
+					c->s.rest_bound_file = argv[i + 1];
+					break;
+				default:
+					fprintf(stderr, "Unknown bound type '%c'.\n", *p);
+					exit(1);
+				}
+			}
+			if (c->s.options & XMPH_OPT_USELOADRESTBOUND) ++i;
+			break;
+		case '-': {
+			const char *x = a + 2;
+			unsigned v;
+			if (bool_option(x, "displaynewbounds", &c->s.options, XMPH_OPT_DISPLAYNEWBOUNDS)) break;
+			if (bool_option(x, "displaynewtrees", &c->s.options, XMPH_OPT_DISPLAYNEWTREES)) break;
+			if (unsigned_option(x, "updatesecs", &c->update_secs)) break;
+			if (unsigned_option(x, "startcol", &v)) { c->s.start_col = v - 1; break; }
+			if (unsigned_option(x, "endcol", &v)) { c->s.end_col = v - 1; break; }
+			if (bool_option(x, "improveinitupperbound", &c->s.options, XMPH_OPT_IMPROVEINITUPPERBOUND)) break;
+			if (unsigned_option(x, "seed", &c->seed)) break;
+			if (bool_option(x, "onlycomputelowerbound", &c->s.options, XMPH_OPT_ONLYCOMPUTELOWERBOUND)) break;
+			if (bool_option(x, "keeptempfiles", &c->s.options, XMPH_OPT_KEEPTEMPFILES)) break;
+			if (unsigned_option(x, "pbmaxiters", &ignored)) break;
+			if (bool_option(x, "savereordereddataset", &c->s.options, XMPH_OPT_SAVEREORDEREDDATASET)) break;
+			if (bool_option(x, "tbr", &c->s.options, XMPH_OPT_TBR)) break;
+			if (unsigned_option(x, "gpus", &c->n_gpus)) break;
+			if (unsigned_option(x, "membudget", &mb)) { c->mem_budget = (size_t) mb << 20; break; }
+			fprintf(stderr, "Unrecognised option '%s', aborting.\n", a);
+			exit(1);
+		}
+		case '?': case 'h': usage(); return 0;
+		case 0: c->in = stdin; break;
+		default:
+			fprintf(stderr, "Unrecognised option '-%c', aborting.\n", a[1]);
+			exit(1);
+		}
+	}
+	if (!c->seed) c->seed = (unsigned) time(NULL) * (unsigned) (getpid() + 1);
+	srand(c->seed);
+	c->rand1 = rand();
+	c->rand2 = rand();
+	c->rand3 = rand();
+	if (!c->in) die("Must specify PHYLIP-format file to open on the command line (or '-' to read data from standard input).");
+	return 1;
+}
+
+static void report_settings(const cli *c) {
+	const unsigned o = c->s.options;
+	if (o & XMPH_OPT_QUIET) return;
+	fprintf(stderr, "%s\n\n", PROGLONGNAME);
+	fprintf(stderr, "B200 (CUDA) version searching on %u GPU%s.\n", c->n_gpus, c->n_gpus == 1 ? "" : "s");
+	if (c->in == stdin) fprintf(stderr, "Reading data from standard input.\n");
+	else fprintf(stderr, "Reading data from file '%s'.\n", c->in_name);
+	if (c->out == stdout) fprintf(stderr, "Writing result trees to standard output.\n");
+	else fprintf(stderr, "Writing result trees to file '%s'.\n", c->out_name);
+	if (c->s.bound == XMPH_NO_LIMIT) fprintf(stderr, "No initial bound specified.\n");
+	else fprintf(stderr, "Initial bound = %u.\n", c->s.bound);
+	if (c->s.max_trees == XMPH_NO_LIMIT) fprintf(stderr, "All optimal trees will be saved.\n");
+	else fprintf(stderr, "Up to %u optimal trees will be saved.\n", c->s.max_trees);
+	if (c->s.start_col == 0 && c->s.end_col == XMPH_NO_LIMIT) fprintf(stderr, "All sites will be processed.\n");
+	else fprintf(stderr, "Sites %u-%u will be processed.\n", c->s.start_col + 1, c->s.end_col + 1);
+	fprintf(stderr, "Sites containing gaps or ambiguous characters will be %s.\n", (o & XMPH_OPT_DISCARDMISSAMBIG) ? "discarded" : "retained");
+	fprintf(stderr, "Trees will be output in %s format.\n", (o & XMPH_OPT_NEXUSFMT) ? "NEXUS" : "raw (Newick)");
+	if (!(o & XMPH_OPT_DISPLAYNEWBOUNDS)) fprintf(stderr, "New bounds will not be reported as they occur.\n");
+	if (!(o & XMPH_OPT_DISPLAYNEWTREES)) fprintf(stderr, "New trees will not be reported as they occur.\n");
+	if (o & XMPH_OPT_USELOADRESTBOUND) fprintf(stderr, "The restBound[] array will be loaded from the file '%s'.\n", c->s.rest_bound_file);
+	if (o & XMPH_OPT_USEDISTBASESBOUNDREST) fprintf(stderr, "The distinct-bases-per-site bound will be used.\n");
+	if (o & XMPH_OPT_USEMSTBOUNDREST) fprintf(stderr, "The minimum spanning tree bound will be used.\n");
+	if (o & XMPH_OPT_ONLYCOMPUTELOWERBOUND) fprintf(stderr, "The program will exit after computing lower bounds.\n");
+	if (o & XMPH_OPT_SAVEREORDEREDDATASET) fprintf(stderr, "The dataset produced by reordering taxa and stripping constant and non-PI sites will be saved.\n");
+	if (o & XMPH_OPT_KEEPTEMPFILES) fprintf(stderr, "Temporary intermediate files will be kept.\n");
+	fprintf(stderr, "Using random number seed %u.  First 3 random numbers: %d, %d, %d.\n", c->seed, c->rand1, c->rand2, c->rand3);
+}
+
+/* reordered.phy: the reduced alignment as a legitimate PHYLIP file, weighted columns replicated
+ * (reference src/common.c:1190-1202,1233-1286 with options = 0). */
+static void save_reordered(const xmph_problem *p) {
+	static const char names[16] = { '0', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N' };
+	FILE *f = fopen("reordered.phy", "w");
+	unsigned total = 0;
+	if (!f) { perror("Could not open 'reordered.phy' for output"); exit(1); }
+	for (unsigned i = 0; i < p->num_sites; ++i) total += p->site_weights[i];
+	fprintf(f, "%d %d\n", (int) p->num_taxa, (int) total);
+	for (unsigned t = 0; t < p->num_taxa; ++t) {
+		fprintf(f, "T%-9d", (int) p->taxon_map[t] + 1);
+		for (unsigned i = 0; i < p->num_sites; ++i) {
+			for (unsigned k = 0; k < p->site_weights[i]; ++k) fputc(names[p->sites[(size_t) t * p->num_sites + i] & 15], f);
+		}
+		fputc('\n', f);
+	}
+	fclose(f);
+}
+
+/* ---- the search across GPUs -------------------------------------------------------------------- */
+/* Replaces Boss()/Worker() (reference src/mpiboss.c:30-429, src/mpiworker.c:214-380).  There is no
+ * boss: every GPU searches.  Shards start from a hashed deal of the frontier at a shallow tree size
+ * (the library's shard_index/shard_count), then
+ *   - the upper bound is a shared word: after every slice of batches a worker folds its own bound in
+ *     and adopts the minimum (the reference relays MSG_NEWBOUND through the boss, src/mpiboss.c:162-171);
+ *   - a worker that runs dry asks for work; busy workers then detach open subtrees from their shallowest
+ *     level as job descriptors into a mailbox (the reference's "steal the last edge at the shallowest
+ *     level", src/mpiworker.c:169-181), and the idle worker replays them (src/yanbader.c:136-143);
+ *   - the search ends when every worker is idle and the mailbox is empty. */
+typedef struct {
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	unsigned bound;
+	unsigned n_workers, n_idle;
+	int finished, failed;
+	unsigned char *mail;       /* job descriptors, num_taxa bytes each */
+	unsigned n_mail, cap_mail;
+	char err[512];
+	int display_bounds;
+} shared_state;
+
+typedef struct {
+	shared_state *sh;
+	const xmph_problem *p;
+	const cli *c;
+	unsigned index;
+	xmp_ctx *ctx;
+	unsigned char *paths;
+	unsigned long long n_trees;
+	unsigned score;
+	xmp_search_stats stats;
+} worker;
+
+#define SLICE_BATCHES 64
+#define STEAL_NODES 256
+
+static void worker_fail(worker *w, const char *what) {
+	shared_state *sh = w->sh;
+	pthread_mutex_lock(&sh->mu);
+	if (!sh->failed) snprintf(sh->err, sizeof sh->err, "GPU %u: %s: %s", w->index, what, xmp_cuda_last_error());
+	sh->failed = sh->finished = 1;
+	pthread_cond_broadcast(&sh->cv);
+	pthread_mutex_unlock(&sh->mu);
+}
+
+static void *worker_main(void *arg) {
+	worker *w = (worker *) arg;
+	shared_state *sh = w->sh;
+	const xmph_problem *p = w->p;
+	xmp_search_params prm;
+	unsigned char *jobs = (unsigned char *) malloc((size_t) STEAL_NODES * p->num_taxa);
+	int done = 0;
+
+	if (xmp_cuda_init((int) w->index, &w->ctx)) { worker_fail(w, "initialising"); return NULL; }
+	if (xmp_cuda_load(w->ctx, p->rows, p->weights, p->num_taxa, p->n_blocks, p->rest_bound, p->constant_weight)) { worker_fail(w, "uploading the problem"); return NULL; }
+	memset(&prm, 0, sizeof prm);
+	prm.bound = p->bound;
+	prm.max_trees = w->c->s.max_trees;
+	prm.mem_budget = w->c->mem_budget;
+	prm.shard_index = w->index;
+	prm.shard_count = sh->n_workers;
+	if (xmp_cuda_search_begin(w->ctx, &prm)) { worker_fail(w, "starting the search"); return NULL; }
+
+	for (;;) {
+		unsigned mine = 0, global;
+		if (!done && xmp_cuda_search_run(w->ctx, sh->n_workers > 1 ? SLICE_BATCHES : 0, &done)) { worker_fail(w, "searching"); break; }
+		if (xmp_cuda_search_get_bound(w->ctx, &mine)) { worker_fail(w, "reading the bound"); break; }
+
+		pthread_mutex_lock(&sh->mu);
+		if (mine < sh->bound) {
+			sh->bound = mine;
+			if (sh->display_bounds) fprintf(stderr, "New bound = %u\n", mine);
+		}
+		global = sh->bound;
+		int give = !done && sh->n_idle > 0 && sh->n_mail == 0;
+		int stop = sh->finished;
+		pthread_mutex_unlock(&sh->mu);
+		if (stop) break;
+		if (global < mine && xmp_cuda_search_set_bound(w->ctx, global)) { worker_fail(w, "lowering the bound"); break; }
+
+		if (give) {
+			unsigned n = 0;
+			if (xmp_cuda_search_export_jobs(w->ctx, STEAL_NODES, jobs, &n)) { worker_fail(w, "exporting jobs"); break; }
+			if (n) {
+				pthread_mutex_lock(&sh->mu);
+				if (sh->n_mail + n > sh->cap_mail) {
+					sh->cap_mail = (sh->n_mail + n) * 2;
+					sh->mail = (unsigned char *) realloc(sh->mail, (size_t) sh->cap_mail * p->num_taxa);
+				}
+				memcpy(sh->mail + (size_t) sh->n_mail * p->num_taxa, jobs, (size_t) n * p->num_taxa);
+				sh->n_mail += n;
+				pthread_cond_broadcast(&sh->cv);
+				pthread_mutex_unlock(&sh->mu);
+			}
+		}
+		if (!done) continue;
+
+		/* Out of work: wait for jobs or for everybody to be idle. */
+		unsigned n = 0;
+		pthread_mutex_lock(&sh->mu);
+		++sh->n_idle;
+		while (!sh->finished && sh->n_mail == 0) {
+			if (sh->n_idle == sh->n_workers) {
+				sh->finished = 1;
+				pthread_cond_broadcast(&sh->cv);
+				break;
+			}
+			pthread_cond_wait(&sh->cv, &sh->mu);
+		}
+		if (!sh->finished && sh->n_mail) {
+			/* Take a fair share of the mailbox. */
+			n = (sh->n_mail + sh->n_idle - 1) / sh->n_idle;
+			if (n > STEAL_NODES) n = STEAL_NODES;
+			memcpy(jobs, sh->mail + (size_t) (sh->n_mail - n) * p->num_taxa, (size_t) n * p->num_taxa);
+			sh->n_mail -= n;
+			--sh->n_idle;
+		}
+		stop = sh->finished;
+		pthread_mutex_unlock(&sh->mu);
+		if (stop) break;
+		if (xmp_cuda_search_import_jobs(w->ctx, jobs, n)) { worker_fail(w, "importing jobs"); break; }
+		done = 0;
+	}
+	free(jobs);
+	return NULL;
+}
+
+int main(int argc, char **argv) {
+	cli c;
+	xmph_alignment a;
+	xmph_problem p;
+	double t_start = now_seconds(), t_order, t_upper, t_lower, t_search, t_output, t_end;
+
+	memset(&c, 0, sizeof c);
+	xmph_default_settings(&c.s);
+	c.update_secs = 2;
+	c.n_gpus = 1;
+	c.out = stdout;
+	if (!parse_args(argc, argv, &c)) return 0;
+	if (c.n_gpus == 0) c.n_gpus = 1;
+	report_settings(&c);
+
+	if (xmph_read_phylip(c.in, &a)) die(xmph_last_error());
+	if (!(c.s.options & XMPH_OPT_QUIET)) fprintf(stderr, "Nucleotide data for %u taxa x %u sites read in.\n", a.num_taxa, a.seq_len);
+	if (c.in != stdin) fclose(c.in);
+
+	t_order = now_seconds();   /* recoding and compression are counted as input time, as in the reference */
+	if (xmph_prepare(&a, &c.s, &p)) die(xmph_last_error());
+	t_upper = t_lower = now_seconds();
+	if (!(c.s.options & XMPH_OPT_QUIET)) {
+		fprintf(stderr, "%d constant sites.\n", (int) p.n_constant_sites);
+		fprintf(stderr, "%d non-parsimoniously-informative sites, having a total weight of %d.\n", (int) p.n_nonpi_sites, (int) p.constant_weight);
+		fprintf(stderr, "%d parsimoniously-informative sites.\n", (int) p.num_sites);
+	}
+	if ((c.s.options & XMPH_OPT_IMPROVEINITUPPERBOUND) && p.mst_upper_bound < c.s.bound && (c.s.options & XMPH_OPT_DISPLAYNEWBOUNDS)) {
+		fprintf(stderr, "Improving initial upper bound to %u, based on minimum spanning tree weight.\n", p.mst_upper_bound);
+	}
+	if (c.s.options & XMPH_OPT_SAVEREORDEREDDATASET) save_reordered(&p);
+	if (xmph_write_rest_bound(&p, "restBound.txt")) die(xmph_last_error());
+
+	if (c.s.options & XMPH_OPT_ONLYCOMPUTELOWERBOUND) return 0;
+	if (p.num_sites == 0) die("No parsimoniously-informative sites: every tree is equally parsimonious, nothing to search.");
+
+	int avail = xmp_cuda_device_count();
+	if (avail <= 0) die("No CUDA device found.  This program has no CPU search path, aborting.");
+	if ((int) c.n_gpus > avail) {
+		fprintf(stderr, "%u GPUs requested but only %d available, aborting.\n", c.n_gpus, avail);
+		exit(1);
+	}
+	if (!(c.s.options & XMPH_OPT_QUIET)) fprintf(stderr, "Beginning branch and bound search...\n");
+
+	shared_state sh;
+	memset(&sh, 0, sizeof sh);
+	pthread_mutex_init(&sh.mu, NULL);
+	pthread_cond_init(&sh.cv, NULL);
+	sh.bound = p.bound;
+	sh.n_workers = c.n_gpus;
+	sh.display_bounds = (c.s.options & XMPH_OPT_DISPLAYNEWBOUNDS) != 0;
+	worker *ws = (worker *) calloc(c.n_gpus, sizeof(worker));
+	pthread_t *th = (pthread_t *) calloc(c.n_gpus, sizeof(pthread_t));
+
+	t_search = now_seconds();
+	for (unsigned g = 0; g < c.n_gpus; ++g) {
+		ws[g].sh = &sh;
+		ws[g].p = &p;
+		ws[g].c = &c;
+		ws[g].index = g;
+		pthread_create(&th[g], NULL, worker_main, &ws[g]);
+	}
+	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_join(th[g], NULL);
+	if (sh.failed) die(sh.err);
+
+	/* Gather: every shard reports the trees it holds at the final bound. */
+	unsigned char *paths = NULL;
+	unsigned long long n_trees = 0;
+	xmp_search_stats total;
+	memset(&total, 0, sizeof total);
+	for (unsigned g = 0; g < c.n_gpus; ++g) {
+		unsigned score = 0;
+		unsigned long long n = 0;
+		xmp_search_stats st;
+		if (xmp_cuda_search_set_bound(ws[g].ctx, sh.bound)) die(xmp_cuda_last_error());
+		if (xmp_cuda_search_result(ws[g].ctx, &score, &n, NULL, 0)) die(xmp_cuda_last_error());
+		paths = (unsigned char *) realloc(paths, (size_t) (n_trees + n + 1) * p.num_taxa);
+		if (n && xmp_cuda_search_result(ws[g].ctx, &score, &n, paths + (size_t) n_trees * p.num_taxa, (size_t) n)) die(xmp_cuda_last_error());
+		n_trees += n;
+		if (xmp_cuda_search_stats(ws[g].ctx, &st)) die(xmp_cuda_last_error());
+		total.nodes += st.nodes;
+		total.score_calls += st.score_calls;
+		total.children += st.children;
+		total.full_trees += st.full_trees;
+		total.site_merges += st.site_merges;
+		total.launches += st.launches;
+		total.iterations += st.iterations;
+		if (st.seconds > total.seconds) total.seconds = st.seconds;
+	}
+	t_output = now_seconds();
+
+	xmph_sort_paths_dfs(paths, (size_t) n_trees, p.num_taxa);
+	size_t n_out = n_trees > c.s.max_trees ? c.s.max_trees : (size_t) n_trees;
+	if (xmph_write_trees(c.out, (c.s.options & XMPH_OPT_NEXUSFMT) != 0, sh.bound, &a, p.taxon_map, paths, n_out)) die(xmph_last_error());
+	if (c.out != stdout) fclose(c.out);
+	if (!(c.s.options & XMPH_OPT_QUIET) && n_trees == 0) {
+		fprintf(stderr, "NO BEST TREE FOUND!  (Have you specified an initial bound that is too low?)\n");
+	}
+	t_end = now_seconds();
+
+	if (!(c.s.options & XMPH_OPT_QUIET)) {
+		double dt = t_output - t_search;
+		fprintf(stderr, "Optimal trees found:            %20llu\n", n_trees);
+		fprintf(stderr, "BranchAndBound() executed       %20llu times\n", total.nodes);
+		fprintf(stderr, "ScoreFitch() executed           %20llu times\n", total.score_calls);
+		fprintf(stderr, "Partial trees built             %20llu\n", total.children);
+		fprintf(stderr, "Number of full trees considered:%20llu\n", total.full_trees);
+		fprintf(stderr, "Site merges                     %20llu (%.3f G/s)\n", total.site_merges, dt > 0 ? (double) total.site_merges / dt * 1e-9 : 0.0);
+		fprintf(stderr, "Kernel launches / batches       %20llu / %llu\n", total.launches, total.iterations);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to read input:", t_order - t_start);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to order taxa:", t_upper - t_order);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to determine initial upper bound:", t_lower - t_upper);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to determine lower bounds:", t_search - t_lower);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to perform branch and bound search:", t_output - t_search);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Time to write output:", t_end - t_output);
+		fprintf(stderr, "%-45s %11.2lfs\n", "Total time taken:", t_end - t_start);
+	}
+	for (unsigned g = 0; g < c.n_gpus; ++g) xmp_cuda_destroy(ws[g].ctx);
+	free(paths);
+	free(ws);
+	free(th);
+	xmph_free_problem(&p);
+	xmph_free_alignment(&a);
+	return 0;
+}

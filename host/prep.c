@@ -1,0 +1,461 @@
+/* Preprocessing: alignment -> packed, ordered, bounded search problem.
+ *
+ * Mirrors the reference's InitTreeData pipeline (reference src/common.c:1113-1224) stage by stage so
+ * that the search starts from exactly the same taxon order, column order, weights, upper bound and
+ * restBound[] as fastdnamp does:
+ *
+ *   recode columns        src/common.c:1293-1388   state bits in order of first appearance per column
+ *   merge equal columns   src/common.c:1159-1160, 1418-1438, 2813-2815
+ *   sort by weight        src/common.c:1163, 2821-2832   descending weight, then ascending column bytes
+ *   drop uninformative    src/common.c:1445-1496, 2660-2701
+ *   order taxa            src/ordertaxa.c:337-477  (MAXMINIORDER)
+ *   MST upper bound       src/common.c:2597-2604, src/seq_b1.c:58-152,260-275
+ *   lower bounds          src/bound.c:12-41, src/distbasesbound.c:21-160, src/mstbound.c:67-93
+ *   pack                  src/common.c:1034-1109, here with BYTESPERBLOCK 16
+ */
+#include <ctype.h>
+#include <stdlib.h>
+#include <string.h>
+#include "xmp_host.h"
+
+int xmph_fail(const char *fmt, ...);
+
+void xmph_default_settings(xmph_settings *s) {
+	s->options = XMPH_OPT_NEXUSFMT | XMPH_OPT_DISPLAYNEWBOUNDS | XMPH_OPT_DISPLAYNEWTREES |
+	             XMPH_OPT_USEDISTBASESBOUNDREST | XMPH_OPT_IMPROVEINITUPPERBOUND | XMPH_OPT_TBR;
+	s->bound = XMPH_NO_LIMIT;
+	s->max_trees = XMPH_NO_LIMIT;
+	s->start_col = 0;
+	s->end_col = XMPH_NO_LIMIT;
+	s->rest_bound_file = NULL;
+}
+
+/* IUPAC code -> set over {A=1, C=2, G=4, T=8}; gap and '?' are fully ambiguous (src/common.c:891-916). */
+static int base_set(int ch) {
+	switch (toupper(ch)) {
+	case 'A': return 1;
+	case 'C': return 2;
+	case 'G': return 4;
+	case 'U': case 'T': return 8;
+	case 'R': return 1 | 4;
+	case 'Y': return 2 | 8;
+	case 'S': return 2 | 4;
+	case 'W': return 1 | 8;
+	case 'K': return 4 | 8;
+	case 'M': return 1 | 2;
+	case 'B': return 2 | 4 | 8;
+	case 'D': return 1 | 4 | 8;
+	case 'H': return 1 | 2 | 8;
+	case 'V': return 1 | 2 | 4;
+	case '-': case '?': case 'N': return 15;
+	default: return -1;
+	}
+}
+
+/* ---- columns ------------------------------------------------------------------------------ */
+/* A column table is site-major: col[i] holds num_taxa recoded state sets, wt[i] its weight. */
+typedef struct {
+	unsigned n, num_taxa;
+	unsigned char *col;
+	unsigned *wt;
+} columns;
+
+/* Re-labels the states of every column by order of first appearance (taxon order, A<C<G<T inside an
+ * ambiguous set), so that columns with the same partition structure become byte-identical. */
+static int recode(const xmph_alignment *a, const xmph_settings *s, columns *c) {
+	unsigned end = s->end_col > a->seq_len ? a->seq_len : s->end_col;
+	c->num_taxa = a->num_taxa;
+	c->col = (unsigned char *) malloc((size_t) a->num_taxa * (a->seq_len + 1));
+	c->n = 0;
+	for (unsigned site = s->start_col; site < end; ++site) {
+		int relabel[4] = { -1, -1, -1, -1 };
+		int next = 0, keep = 1;
+		unsigned char *out = c->col + (size_t) c->n * a->num_taxa;
+		for (unsigned t = 0; t < a->num_taxa; ++t) {
+			int set = base_set(a->chars[(size_t) t * a->seq_len + site]);
+			if (set < 0) return xmph_fail("Invalid character '%c' in alignment, aborting.", a->chars[(size_t) t * a->seq_len + site]);
+			if ((set & (set - 1)) && (s->options & XMPH_OPT_DISCARDMISSAMBIG)) {
+				keep = 0;
+				break;
+			}
+			int coded = 0;
+			for (int b = 0; b < 4; ++b) {
+				if (!(set & (1 << b))) continue;
+				if (relabel[b] < 0) relabel[b] = next++;
+				coded |= 1 << relabel[b];
+			}
+			out[t] = (unsigned char) coded;
+		}
+		c->n += (unsigned) keep;
+	}
+	c->wt = (unsigned *) malloc(((size_t) c->n + 1) * sizeof(unsigned));
+	for (unsigned i = 0; i < c->n; ++i) c->wt[i] = 1;
+	return 0;
+}
+
+static unsigned g_cmp_width;   /* qsort has no context argument in C99 */
+typedef struct { unsigned wt; const unsigned char *col; } keyed;
+
+static int by_bytes(const void *x, const void *y) {
+	return memcmp(((const keyed *) x)->col, ((const keyed *) y)->col, g_cmp_width);
+}
+
+/* Heaviest first; equal weights in ascending byte order (a total order once columns are distinct). */
+static int by_weight_then_bytes(const void *x, const void *y) {
+	const keyed *a = (const keyed *) x, *b = (const keyed *) y;
+	if (a->wt != b->wt) return a->wt > b->wt ? -1 : 1;
+	return memcmp(a->col, b->col, g_cmp_width);
+}
+
+static void sort_columns(columns *c, int (*cmp)(const void *, const void *)) {
+	keyed *k = (keyed *) malloc(((size_t) c->n + 1) * sizeof(keyed));
+	unsigned char *ncol = (unsigned char *) malloc((size_t) c->num_taxa * (c->n + 1));
+	unsigned *nwt = (unsigned *) malloc(((size_t) c->n + 1) * sizeof(unsigned));
+	for (unsigned i = 0; i < c->n; ++i) {
+		k[i].wt = c->wt[i];
+		k[i].col = c->col + (size_t) i * c->num_taxa;
+	}
+	g_cmp_width = c->num_taxa;
+	qsort(k, c->n, sizeof(keyed), cmp);
+	for (unsigned i = 0; i < c->n; ++i) {
+		nwt[i] = k[i].wt;
+		memcpy(ncol + (size_t) i * c->num_taxa, k[i].col, c->num_taxa);
+	}
+	free(k);
+	free(c->col);
+	free(c->wt);
+	c->col = ncol;
+	c->wt = nwt;
+}
+
+/* Adjacent equal columns (after sorting by bytes) collapse into one whose weight is the sum. */
+static void merge_equal_columns(columns *c) {
+	unsigned j = 0;
+	if (c->n == 0) return;
+	for (unsigned i = 1; i < c->n; ++i) {
+		unsigned char *ci = c->col + (size_t) i * c->num_taxa, *cj = c->col + (size_t) j * c->num_taxa;
+		if (memcmp(cj, ci, c->num_taxa) == 0) {
+			c->wt[j] += c->wt[i];
+		} else {
+			++j;
+			memmove(c->col + (size_t) j * c->num_taxa, ci, c->num_taxa);
+			c->wt[j] = c->wt[i];
+		}
+	}
+	c->n = j + 1;
+}
+
+/* Length a column adds to every tree if it is parsimony-uninformative, else -1.  A column is
+ * uninformative when, for some state r ("the rest"; the reference also tries the impossible fifth
+ * state 16, kept here), the sets that do not contain r are pairwise disjoint: each of them then costs
+ * exactly one step on any tree. */
+static int uninformative_cost(const unsigned char *col, unsigned n) {
+	for (unsigned r = 1; r <= 16; r <<= 1) {
+		unsigned with_r = 0;
+		int disjoint = 1;
+		for (unsigned i = 0; i < n && disjoint; ++i) {
+			if (col[i] & r) { ++with_r; continue; }
+			for (unsigned j = i + 1; j < n; ++j) {
+				if (!(col[j] & r) && (col[i] & col[j])) { disjoint = 0; break; }
+			}
+		}
+		if (disjoint) return (int) (n - with_r);
+	}
+	return -1;
+}
+
+static void drop_uninformative(columns *c, xmph_problem *p) {
+	unsigned j = 0;
+	p->n_constant_sites = p->n_nonpi_sites = p->constant_weight = 0;
+	for (unsigned i = 0; i < c->n; ++i) {
+		const unsigned char *ci = c->col + (size_t) i * c->num_taxa;
+		unsigned common = 15;
+		for (unsigned t = 0; t < c->num_taxa && common; ++t) common &= ci[t];
+		if (common) {
+			p->n_constant_sites += c->wt[i];
+			continue;
+		}
+		int cost = uninformative_cost(ci, c->num_taxa);
+		if (cost >= 0) {
+			p->constant_weight += (unsigned) cost * c->wt[i];
+			p->n_nonpi_sites += c->wt[i];
+			continue;
+		}
+		if (i != j) {
+			memmove(c->col + (size_t) j * c->num_taxa, ci, c->num_taxa);
+			c->wt[j] = c->wt[i];
+		}
+		++j;
+	}
+	c->n = j;
+}
+
+/* ---- unpacked (one set per byte) distances -------------------------------------------------- */
+static unsigned fitch_distance(const unsigned char *a, const unsigned char *b, const unsigned *w, unsigned n) {
+	unsigned d = 0;
+	for (unsigned i = 0; i < n; ++i) {
+		if (!(a[i] & b[i])) d += w[i];
+	}
+	return d;
+}
+
+static unsigned strict_distance(const unsigned char *a, const unsigned char *b, const unsigned *w, unsigned n) {
+	unsigned d = 0;
+	for (unsigned i = 0; i < n; ++i) {
+		if (a[i] != b[i]) d += w[i];
+	}
+	return d;
+}
+
+/* Weight of a minimum spanning tree of the complete graph on `height` rows (Prim). */
+static unsigned mst_weight(const unsigned char *rows, unsigned n_sites, unsigned height, const unsigned *w, int strict) {
+	unsigned *best = (unsigned *) malloc(height * sizeof(unsigned));
+	unsigned char *in = (unsigned char *) calloc(height, 1);
+	unsigned total = 0;
+	if (height < 2) { free(best); free(in); return 0; }
+	in[0] = 1;
+	for (unsigned j = 1; j < height; ++j) {
+		best[j] = strict ? strict_distance(rows, rows + (size_t) j * n_sites, w, n_sites)
+		                 : fitch_distance(rows, rows + (size_t) j * n_sites, w, n_sites);
+	}
+	for (unsigned k = 1; k < height; ++k) {
+		unsigned pick = 0, d = 0xffffffffu;
+		for (unsigned j = 1; j < height; ++j) {
+			if (!in[j] && best[j] < d) { d = best[j]; pick = j; }
+		}
+		in[pick] = 1;
+		total += d;
+		for (unsigned j = 1; j < height; ++j) {
+			if (in[j]) continue;
+			unsigned e = strict ? strict_distance(rows + (size_t) pick * n_sites, rows + (size_t) j * n_sites, w, n_sites)
+			                    : fitch_distance(rows + (size_t) pick * n_sites, rows + (size_t) j * n_sites, w, n_sites);
+			if (e < best[j]) best[j] = e;
+		}
+	}
+	free(best);
+	free(in);
+	return total;
+}
+
+/* ---- taxon order ---------------------------------------------------------------------------- */
+static int cmp_unsigned(const void *a, const void *b) {
+	unsigned x = *(const unsigned *) a, y = *(const unsigned *) b;
+	return x < y ? -1 : x > y;
+}
+
+static void swap_rows(xmph_problem *p, unsigned a, unsigned b, unsigned char *tmp) {
+	size_t n = p->num_sites;
+	memcpy(tmp, p->sites + a * n, n);
+	memcpy(p->sites + a * n, p->sites + b * n, n);
+	memcpy(p->sites + b * n, tmp, n);
+}
+
+/* Max-mini order: the two most distant taxa first (first such pair in (i, j) order); then repeatedly
+ * the remaining taxon whose ascending-sorted vector of distances to the taxa already placed is
+ * lexicographically greatest (first such taxon on ties).  The last taxon is whatever is left. */
+static void order_taxa(xmph_problem *p) {
+	const unsigned n = p->num_taxa, ns = p->num_sites;
+	unsigned char *tmp = (unsigned char *) malloc(ns + 1);
+	unsigned *dist = (unsigned *) malloc(n * sizeof(unsigned));
+	unsigned *best = (unsigned *) malloc(n * sizeof(unsigned));
+	unsigned fi = 0, fj = 1, fd = 0;
+
+	for (unsigned i = 0; i < n; ++i) p->taxon_map[i] = i;
+	for (unsigned i = 0; i + 1 < n; ++i) {
+		for (unsigned j = i + 1; j < n; ++j) {
+			unsigned d = fitch_distance(p->sites + (size_t) i * ns, p->sites + (size_t) j * ns, p->site_weights, ns);
+			if (d > fd) { fi = i; fj = j; fd = d; }
+		}
+	}
+	if (fi != 0) {
+		swap_rows(p, 0, fi, tmp);
+		p->taxon_map[0] = fi;
+		p->taxon_map[fi] = 0;
+	}
+	if (fj != 1) {
+		swap_rows(p, 1, fj, tmp);
+		unsigned t = p->taxon_map[fj];
+		p->taxon_map[fj] = p->taxon_map[1];
+		p->taxon_map[1] = t;
+	}
+	for (unsigned k = 2; k + 1 < n; ++k) {
+		unsigned pick = k;
+		memset(best, 0, n * sizeof(unsigned));
+		for (unsigned i = k; i < n; ++i) {
+			for (unsigned j = 0; j < k; ++j) {
+				dist[j] = fitch_distance(p->sites + (size_t) i * ns, p->sites + (size_t) j * ns, p->site_weights, ns);
+			}
+			qsort(dist, k, sizeof(unsigned), cmp_unsigned);
+			for (unsigned j = 0; j < k; ++j) {
+				if (dist[j] > best[j]) {
+					pick = i;
+					memcpy(best, dist, k * sizeof(unsigned));
+					break;
+				}
+				if (dist[j] < best[j]) break;
+			}
+		}
+		if (pick != k) {
+			swap_rows(p, k, pick, tmp);
+			unsigned t = p->taxon_map[pick];
+			p->taxon_map[pick] = p->taxon_map[k];
+			p->taxon_map[k] = t;
+		}
+	}
+	free(best);
+	free(dist);
+	free(tmp);
+}
+
+/* ---- lower bounds --------------------------------------------------------------------------- */
+/* Distinct-bases bound.  For every column made only of single states: once taxa 0..k are on the
+ * tree, each state that occurs among the remaining taxa but not yet on the tree must cost one more
+ * step.  rest_bound[k] = weighted count of such (column, state) pairs. */
+static void distinct_bases_bound(xmph_problem *p) {
+	const unsigned n = p->num_taxa, ns = p->num_sites;
+	unsigned (*rest)[4] = (unsigned (*)[4]) calloc(ns + 1, sizeof(unsigned[4]));
+	unsigned char (*seen)[4] = (unsigned char (*)[4]) calloc(ns + 1, 4);
+	unsigned char *skip = (unsigned char *) calloc(ns + 1, 1);
+	static const signed char slot[16] = { -1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1 };
+
+	for (unsigned t = 0; t < n; ++t) {
+		for (unsigned i = 0; i < ns; ++i) {
+			int k = slot[p->sites[(size_t) t * ns + i] & 15];
+			if (k < 0) skip[i] = 1; else ++rest[i][k];
+		}
+	}
+	for (unsigned t = 0; t < n; ++t) {
+		unsigned total = 0;
+		for (unsigned i = 0; i < ns; ++i) {
+			if (skip[i]) continue;
+			int k = slot[p->sites[(size_t) t * ns + i] & 15];
+			seen[i][k] = 1;
+			--rest[i][k];
+			for (int b = 0; b < 4; ++b) {
+				if (!seen[i][b] && rest[i][b] > 0) total += p->site_weights[i];
+			}
+		}
+		if (total > p->rest_bound[t]) p->rest_bound[t] = total;
+	}
+	free(skip);
+	free(seen);
+	free(rest);
+}
+
+/* MST bound: half the MST weight (Fitch distances, so ambiguity never overestimates) over
+ * { union of taxa 0..k, taxon k+1, ..., taxon n-1 }, rounded down. */
+static void mst_bound(xmph_problem *p) {
+	const unsigned n = p->num_taxa, ns = p->num_sites;
+	unsigned char *rows = (unsigned char *) malloc((size_t) n * ns + 1);
+	memcpy(rows, p->sites, (size_t) n * ns);
+	for (unsigned k = 0; k + 1 < n; ++k) {
+		unsigned char *cur = rows + (size_t) k * ns;
+		unsigned b = mst_weight(cur, ns, n - k, p->site_weights, 0) / 2;
+		if (b > p->rest_bound[k]) p->rest_bound[k] = b;
+		for (unsigned i = 0; i < ns; ++i) cur[ns + i] |= cur[i];
+	}
+	free(rows);
+}
+
+/* Same text format as restBound.txt: a header line, then "<index> <bound>" lines. */
+static int load_rest_bound(xmph_problem *p, const char *path) {
+	char line[256];
+	unsigned idx, val, line_no = 2;
+	FILE *f = fopen(path, "rb");
+	if (!f) return xmph_fail("Unable to open file '%s' to retrieve restBound[] array, aborting.", path);
+	if (fgets(line, sizeof line, f)) {
+		while (fgets(line, sizeof line, f)) {
+			if (sscanf(line, "%u %u", &idx, &val) < 2) {
+				fclose(f);
+				return xmph_fail("Unable to parse line %u of '%s', aborting.", line_no, path);
+			}
+			if (idx >= p->num_taxa) {
+				fclose(f);
+				return xmph_fail("Line %u of '%s' names taxon index %u but there are only %u taxa, aborting.", line_no, path, idx, p->num_taxa);
+			}
+			p->rest_bound[idx] = val;
+			++line_no;
+		}
+	}
+	fclose(f);
+	return 0;
+}
+
+int xmph_write_rest_bound(const xmph_problem *p, const char *path) {
+	FILE *f = fopen(path, "wt");
+	if (!f) return xmph_fail("Unable to open '%s' for output.", path);
+	fprintf(f, "i\tMin weight added by taxa i+1, i+2, ..., n-1.\n");
+	for (unsigned i = 2; i < p->num_taxa; ++i) fprintf(f, "%u\t%u\n", i, p->rest_bound[i]);
+	fclose(f);
+	return 0;
+}
+
+/* ---- packing -------------------------------------------------------------------------------- */
+static void pack_rows(xmph_problem *p) {
+	const unsigned ns = p->num_sites;
+	p->n_blocks = ns ? (ns - 1) / XMPH_SITES_PER_BLOCK + 1 : 0;
+	const size_t row_bytes = (size_t) p->n_blocks * XMPH_BLOCK_BYTES, padded = row_bytes * 2;
+	if (posix_memalign((void **) &p->rows, 64, row_bytes * p->num_taxa + 64)) p->rows = NULL;
+	p->weights = (unsigned *) malloc((padded + 1) * sizeof(unsigned));
+	for (unsigned t = 0; t < p->num_taxa; ++t) {
+		unsigned char *row = p->rows + t * row_bytes;
+		for (size_t s = 0; s < padded; ++s) {
+			unsigned set = s < ns ? p->sites[(size_t) t * ns + s] : 15u;   /* padding never scores */
+			if (s & 1) row[s >> 1] |= (unsigned char) (set << 4); else row[s >> 1] = (unsigned char) set;
+		}
+	}
+	for (size_t s = 0; s < padded; ++s) p->weights[s] = s < ns ? p->site_weights[s] : 1;
+}
+
+void xmph_free_problem(xmph_problem *p) {
+	free(p->rows);
+	free(p->weights);
+	free(p->sites);
+	free(p->site_weights);
+	free(p->taxon_map);
+	free(p->rest_bound);
+	memset(p, 0, sizeof *p);
+}
+
+int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *p) {
+	columns c = { 0, 0, NULL, NULL };
+	const unsigned unsupported = XMPH_OPT_USEINCOMPATBOUNDREST | XMPH_OPT_USEKICKASSBOUNDREST | XMPH_OPT_USEKA2BOUNDREST |
+	                             XMPH_OPT_USEGREEDYHITTINGSETBOUND | XMPH_OPT_USEPARTBOUND;
+	memset(p, 0, sizeof *p);
+	if (a->num_taxa < 4) return xmph_fail("You must have four or more taxa to perform this analysis.");
+	if (a->num_taxa > XMPH_MAXTAXA) return xmph_fail("At most %d taxa are supported.", XMPH_MAXTAXA);
+	if (s->options & unsupported) {
+		return xmph_fail("Only the -Bd, -Bm and -Bf lower bounds are built into this program; compute other bounds with the reference and load its restBound.txt with -Bf <file>.");
+	}
+	if (recode(a, s, &c)) { free(c.col); return -1; }
+	sort_columns(&c, by_bytes);
+	merge_equal_columns(&c);
+	sort_columns(&c, by_weight_then_bytes);
+	drop_uninformative(&c, p);
+
+	p->num_taxa = a->num_taxa;
+	p->num_sites = c.n;
+	p->sites = (unsigned char *) malloc((size_t) c.n * a->num_taxa + 1);
+	for (unsigned i = 0; i < c.n; ++i) {
+		for (unsigned t = 0; t < a->num_taxa; ++t) p->sites[(size_t) t * c.n + i] = c.col[(size_t) i * a->num_taxa + t];
+	}
+	p->site_weights = c.wt;
+	free(c.col);
+	p->taxon_map = (unsigned *) malloc(a->num_taxa * sizeof(unsigned));
+	p->rest_bound = (unsigned *) calloc(a->num_taxa, sizeof(unsigned));
+	order_taxa(p);
+
+	p->bound = s->bound;
+	if (s->options & XMPH_OPT_IMPROVEINITUPPERBOUND) {
+		p->mst_upper_bound = mst_weight(p->sites, p->num_sites, p->num_taxa, p->site_weights, 1) + p->constant_weight;
+		if (p->mst_upper_bound < p->bound) p->bound = p->mst_upper_bound;
+	}
+	if (s->options & XMPH_OPT_USEDISTBASESBOUNDREST) distinct_bases_bound(p);
+	if ((s->options & XMPH_OPT_USELOADRESTBOUND) && load_rest_bound(p, s->rest_bound_file)) {
+		xmph_free_problem(p);
+		return -1;
+	}
+	if (s->options & XMPH_OPT_USEMSTBOUNDREST) mst_bound(p);
+	pack_rows(p);
+	return 0;
+}

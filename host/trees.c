@@ -1,0 +1,163 @@
+/* Trees as insertion paths: reconstruction, the reference's Newick text, its depth-first order and
+ * its result-file format (reference src/common.c:371-454 OutputResults, :933-974 PrintTree,
+ * src/yanbader.c:103,238-243 edge order).
+ *
+ * Edge ids (include/xmp_cuda.h): a tree on taxa 0..m-1 has edges 0..2m-4, each named after the node
+ * below it.  Edge 0 / 1: leaves 1 / 2; edge 2: the first internal node (LEFT = leaf 1, RIGHT = leaf 2),
+ * child of the root, which is taxon 0.  Inserting taxon t on edge v adds leaf edge 2t-3 and internal
+ * edge 2t-2, whose LEFT child is the new leaf and whose RIGHT child is v (src/common.c:735-736).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "xmp_host.h"
+
+int xmph_fail(const char *fmt, ...);
+
+#define NONE 0xFFu
+#define MAXE (2 * XMPH_MAXTAXA)
+
+typedef struct {
+	unsigned char par[MAXE], kid[MAXE][2];
+	unsigned top;     /* the root's only child */
+} topo;
+
+static int edge_is_leaf(unsigned e) { return e == 0 || (e & 1); }
+static unsigned edge_taxon(unsigned e) { return (e + 3) / 2; }
+
+static void topo_base(topo *t) {
+	t->par[0] = t->par[1] = 2;
+	t->par[2] = NONE;
+	t->kid[0][0] = t->kid[0][1] = t->kid[1][0] = t->kid[1][1] = NONE;
+	t->kid[2][0] = 0;
+	t->kid[2][1] = 1;
+	t->top = 2;
+}
+
+static void topo_insert(topo *t, unsigned taxon, unsigned v) {
+	const unsigned a = 2 * taxon - 3, b = 2 * taxon - 2, pv = t->par[v];
+	t->par[b] = (unsigned char) pv;
+	if (pv == NONE) t->top = b; else t->kid[pv][t->kid[pv][1] == v] = (unsigned char) b;
+	t->kid[b][0] = (unsigned char) a;
+	t->kid[b][1] = (unsigned char) v;
+	t->par[a] = t->par[v] = (unsigned char) b;
+	t->kid[a][0] = t->kid[a][1] = NONE;
+}
+
+/* Pre-order list of the edges: own edge, LEFT subtree, RIGHT subtree. */
+static unsigned topo_preorder(const topo *t, unsigned char *out) {
+	unsigned char stack[MAXE];
+	unsigned sp = 0, n = 0;
+	stack[sp++] = (unsigned char) t->top;
+	while (sp) {
+		unsigned e = stack[--sp];
+		out[n++] = (unsigned char) e;
+		if (!edge_is_leaf(e)) {
+			stack[sp++] = t->kid[e][1];
+			stack[sp++] = t->kid[e][0];
+		}
+	}
+	return n;
+}
+
+static char *put_unsigned(char *o, unsigned v) {
+	char tmp[12];
+	int n = 0;
+	do { tmp[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
+	while (n) *o++ = tmp[--n];
+	return o;
+}
+
+static char *put_subtree(const topo *t, unsigned e, const unsigned *taxon_map, char *o) {
+	if (edge_is_leaf(e)) return put_unsigned(o, taxon_map[edge_taxon(e)] + 1);
+	*o++ = '(';
+	o = put_subtree(t, t->kid[e][0], taxon_map, o);
+	*o++ = ',';
+	o = put_subtree(t, t->kid[e][1], taxon_map, o);
+	*o++ = ')';
+	return o;
+}
+
+size_t xmph_path_to_newick(const unsigned char *path, unsigned num_taxa, const unsigned *taxon_map, char *out) {
+	topo t;
+	char *o = out;
+	topo_base(&t);
+	for (unsigned k = 3; k < num_taxa; ++k) topo_insert(&t, k, path[k]);
+	*o++ = '(';
+	o = put_unsigned(o, taxon_map[0] + 1);
+	*o++ = ',';
+	o = put_subtree(&t, t.top, taxon_map, o);
+	*o++ = ')';
+	*o = 0;
+	return (size_t) (o - out);
+}
+
+void xmph_path_to_dfs(const unsigned char *path, unsigned num_taxa, unsigned char *dfs) {
+	topo t;
+	unsigned char order[MAXE];
+	topo_base(&t);
+	dfs[0] = dfs[1] = dfs[2] = 0;
+	for (unsigned k = 3; k < num_taxa; ++k) {
+		unsigned n = topo_preorder(&t, order), r = 0;
+		while (r < n && order[r] != path[k]) ++r;
+		dfs[k] = (unsigned char) r;
+		topo_insert(&t, k, path[k]);
+	}
+}
+
+void xmph_dfs_to_path(const unsigned char *dfs, unsigned num_taxa, unsigned char *path) {
+	topo t;
+	unsigned char order[MAXE];
+	topo_base(&t);
+	path[0] = path[1] = path[2] = 0;
+	for (unsigned k = 3; k < num_taxa; ++k) {
+		topo_preorder(&t, order);
+		path[k] = order[dfs[k]];
+		topo_insert(&t, k, path[k]);
+	}
+}
+
+static unsigned g_key_len;
+static int cmp_keyed_paths(const void *a, const void *b) {
+	return memcmp(a, b, g_key_len);
+}
+
+void xmph_sort_paths_dfs(unsigned char *paths, size_t n, unsigned num_taxa) {
+	/* record = dfs key (num_taxa bytes) followed by the path (num_taxa bytes) */
+	const size_t rec = 2 * (size_t) num_taxa;
+	unsigned char *tmp;
+	if (n < 2) return;
+	tmp = (unsigned char *) malloc(n * rec);
+	for (size_t i = 0; i < n; ++i) {
+		xmph_path_to_dfs(paths + i * num_taxa, num_taxa, tmp + i * rec);
+		memcpy(tmp + i * rec + num_taxa, paths + i * num_taxa, num_taxa);
+	}
+	g_key_len = num_taxa;
+	qsort(tmp, n, rec, cmp_keyed_paths);
+	for (size_t i = 0; i < n; ++i) memcpy(paths + i * num_taxa, tmp + i * rec + num_taxa, num_taxa);
+	free(tmp);
+}
+
+int xmph_write_trees(FILE *out, int nexus, unsigned score, const xmph_alignment *a, const unsigned *taxon_map,
+                     const unsigned char *paths, size_t n_trees) {
+	char *buf = (char *) malloc(16 * (size_t) a->num_taxa + 16);
+	if (nexus) {
+		fprintf(out,
+		        "#NEXUS\n"
+		        "[ Trees produced by fastDNAmp: Exact Maximum Parsimony Phylogenetic Tree Search v1.1\n"
+		        "> Each tree has score %u. ]\n"
+		        "BEGIN TREES;\n"
+		        "\tTRANSLATE\n", score);
+		for (unsigned i = 0; i < a->num_taxa; ++i) {
+			fprintf(out, "\t\t%u\t%s%c\n", i + 1, a->labels[i], i + 1 < a->num_taxa ? ',' : ';');
+		}
+	}
+	for (size_t k = 0; k < n_trees; ++k) {
+		size_t n = xmph_path_to_newick(paths + k * a->num_taxa, a->num_taxa, taxon_map, buf);
+		if (nexus) fprintf(out, "\tTREE FASTDNAMP_%zu = [&U] ", k + 1);
+		fwrite(buf, 1, n, out);
+		fputs(";\n", out);
+	}
+	if (nexus) fprintf(out, "END;\n");
+	free(buf);
+	return ferror(out) ? xmph_fail("Error writing result trees.") : 0;
+}

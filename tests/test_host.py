@@ -1,0 +1,155 @@
+"""Host C code (host/*.c through xmp_b200.hostlib) against the goldens generated from the reference:
+reader, preprocessing, taxon order, bounds, tree text.  No GPU needed."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import golden_output, golden_trees
+from tests.newick import canonical_newick
+from xmp_b200 import hostlib as xh
+
+FAST = ["mt-10", "rbc14x759", "h1", "h2", "h3", "h4", "h5", "mh1", "mh2", "mh3", "mh4", "mh6", "EukaryotesrDNA",
+        "Metazoan", "its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16"]
+
+
+def prepare(alignment_dir, goldens, name, **kw):
+    g = goldens[name]
+    a = xh.Alignment(str(alignment_dir / g["alignment"]))
+    opts = xh.OPT_NEXUSFMT | xh.OPT_IMPROVEINITUPPERBOUND
+    flags = g["flags"]
+    bound = xh.NO_LIMIT
+    if "-b" in flags:
+        bound = int(flags[flags.index("-b") + 1])
+    b = [f for f in flags if f.startswith("-B")]
+    letters = b[0][2:] if b else "d"
+    if "d" in letters:
+        opts |= xh.OPT_USEDISTBASESBOUNDREST
+    if "m" in letters:
+        opts |= xh.OPT_USEMSTBOUNDREST
+    return a, xh.Problem(a, options=opts, bound=bound, **kw)
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_preprocessing_matches_reference(alignment_dir, goldens, name):
+    g = goldens[name]
+    a, p = prepare(alignment_dir, goldens, name)
+    assert p.num_sites == g["pi_sites"]
+    assert p.n_constant_sites == g["constant_sites"]
+    assert p.n_nonpi_sites == g["nonpi_sites"]
+    assert p.constant_weight == g["constant_weight"]
+    assert [int(t) + 1 for t in p.taxon_map] == g["taxon_order"]
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
+    if g["initial_upper_bound"] is not None:
+        assert p.mst_upper_bound == g["initial_upper_bound"] and p.bound == g["initial_upper_bound"]
+    # packing: 16-byte blocks, padding nibbles 0xF with weight 1, weights descending
+    assert p.n_blocks == (p.num_sites + 31) // 32
+    w = p.weights
+    assert (np.diff(w.astype(np.int64)) <= 0).all() and (w[p.num_sites:] == 1).all()
+    nib = np.stack([p.rows & 15, p.rows >> 4], axis=2).reshape(p.num_taxa, -1)
+    assert (nib[:, :p.num_sites] == p.sites).all() and (nib[:, p.num_sites:] == 15).all()
+
+
+@pytest.mark.parametrize("name", ["mt-10.Bm", "h3.Bm", "h3.Bdm"])
+def test_mst_lower_bound_matches_reference(alignment_dir, goldens, name):
+    _, p = prepare(alignment_dir, goldens, name)
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == goldens[name]["rest_bound"]
+
+
+def test_survey_mst_goldens(alignment_dir, goldens):
+    """restBound values quoted in SURVEY.md section 8c (probe build with zero-initialised autos)."""
+    _, p = prepare(alignment_dir, goldens, "mt-10.Bm")
+    assert list(p.rest_bound[2:10]) == [3297, 1794, 1055, 650, 360, 176, 80, 0]
+    _, p = prepare(alignment_dir, goldens, "h3.Bm")
+    assert list(p.rest_bound[2:12]) == [99, 59, 36, 18, 9, 6, 5, 2, 1, 0]
+    _, p = prepare(alignment_dir, goldens, "mt-10")
+    assert list(p.rest_bound[2:10]) == [3106, 2109, 1440, 991, 614, 330, 161, 0]
+
+
+def test_rest_bound_file_round_trip(alignment_dir, goldens, tmp_path):
+    g = goldens["its36"]
+    f = tmp_path / "restBound.txt"
+    f.write_text("i\tMin weight added by taxa i+1, i+2, ..., n-1.\n" + "".join("%d\t%d\n" % (i, b) for i, b in g["rest_bound"]))
+    a = xh.Alignment(str(alignment_dir / g["alignment"]))
+    p = xh.Problem(a, options=xh.OPT_USELOADRESTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=233, rest_bound_file=str(f))
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
+    assert [int(t) + 1 for t in p.taxon_map] == g["taxon_order"]
+    assert p.bound == 233
+
+
+def test_unsupported_bounds_say_so(alignment_dir, goldens):
+    a = xh.Alignment(str(alignment_dir / "h3.phy"))
+    with pytest.raises(xh.HostError, match="-Bf"):
+        xh.Problem(a, options=8192)
+
+
+# ---- PHYLIP reader fixtures (reference data/phylip_format_testing; names encode the outcome) ----
+def test_phylip_ok_fixtures(alignment_dir):
+    d = alignment_dir / "phylip_format_testing"
+    a1 = xh.Alignment(str(d / "ok1.phy"))
+    for fn in ("ok2_lots_of_tabs_spaces_and_blank_lines.phy", "ok3_missing_final_newline.phy"):
+        a = xh.Alignment(str(d / fn))
+        assert (a.num_taxa, a.seq_len) == (a1.num_taxa, a1.seq_len)
+        assert a.labels == a1.labels
+        assert (a.chars == a1.chars).all()
+    assert a1.labels == ["T1", "T2", "T3", "T4"]
+    assert bytes(a1.chars[0]).decode() == "ACGTA"
+
+
+def test_phylip_bad_fixtures(alignment_dir):
+    d = alignment_dir / "phylip_format_testing"
+    with pytest.raises(xh.HostError, match="fewer sites than the first line"):
+        xh.Alignment(str(d / "bad1_T3_missing_1_base.phy"))
+    with pytest.raises(xh.HostError, match="input only contains"):
+        xh.Alignment(str(d / "bad2_T4_missing_final_line.phy"))
+
+
+def test_phylip_interleaved_and_errors(tmp_path):
+    f = tmp_path / "il.phy"
+    f.write_text(" 4 12\nAlpha     ACGTAC\nBeta  x   ACGTAC\nGamma     ACGTAC\nDelta     ACGTA-\n\nGTACGT\nGTACGT\ngtacgn\nGTACG?\n")
+    a = xh.Alignment(str(f))
+    assert a.labels == ["Alpha", "Beta  x", "Gamma", "Delta"]
+    assert bytes(a.chars[2]).decode() == "ACGTACGTACGN"
+    f.write_text("4 4\nA         AC!T\n")
+    with pytest.raises(xh.HostError, match="invalid character '!' on line 2"):
+        xh.Alignment(str(f))
+    f.write_text("4 4\nA         ACGTA\n")
+    with pytest.raises(xh.HostError, match="too many characters on line 2"):
+        xh.Alignment(str(f))
+    f.write_text("3 4\nA         ACGT\nB         ACGT\nC         ACGT\n")
+    with pytest.raises(xh.HostError, match="four or more taxa"):
+        xh.Problem(xh.Alignment(str(f)))
+
+
+# ---- trees ----
+def test_dfs_coordinates_round_trip():
+    rng = np.random.default_rng(3)
+    for n in (4, 7, 12, 36, 100):
+        for _ in range(20):
+            path = np.zeros(n, np.uint8)
+            for t in range(3, n):
+                path[t] = rng.integers(0, 2 * t - 3)
+            dfs = xh.path_to_dfs(path, n)
+            assert all(dfs[t] < 2 * t - 3 for t in range(3, n))
+            back = xh.dfs_to_path(dfs, n)
+            assert (back[3:] == path[3:]).all()
+
+
+def test_base_tree_newick(alignment_dir, goldens):
+    a, p = prepare(alignment_dir, goldens, "its10")
+    p.num_taxa_saved = p.num_taxa
+    # a 4-taxon path inserting taxon 3 on each of the three edges of the start tree
+    tm = p.taxon_map
+    p4 = lambda e: np.array([0, 0, 0, e], np.uint8)
+    L = xh.lib()
+    import ctypes as C
+    buf = C.create_string_buffer(256)
+    out = []
+    for e in range(3):
+        n = L.xmph_path_to_newick(p4(e).ctypes.data, 4, np.ascontiguousarray(tm, np.uint32).ctypes.data, buf)
+        out.append(buf.raw[:n].decode())
+    t = [int(x) + 1 for x in tm[:4]]
+    assert out[0] == "(%d,((%d,%d),%d))" % (t[0], t[3], t[1], t[2])     # above leaf 1: new leaf LEFT
+    assert out[1] == "(%d,(%d,(%d,%d)))" % (t[0], t[1], t[3], t[2])     # above leaf 2
+    assert out[2] == "(%d,(%d,(%d,%d)))" % (t[0], t[3], t[1], t[2])     # above the internal node

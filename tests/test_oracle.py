@@ -1,0 +1,112 @@
+"""Pins the CPU oracle (oracle/*.c): against the reference's own compiled Fitch code when
+oracle/_ref is present, against the committed known-answer vectors generated from it, and against the
+end-to-end goldens produced by running the reference program (tests/golden/datasets.json).  No GPU."""
+import gzip
+import hashlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol
+from tests.conftest import GOLDEN, golden_output, golden_trees
+from tests.newick import canonical_newick
+from tests.test_host import prepare
+
+O = ol.oracle()
+
+
+def test_kat_vectors():
+    cases = json.load(open(os.path.join(GOLDEN, "fitch_kat.json")))
+    assert len(cases) >= 20
+    for c in cases:
+        n = c["nbytes"]
+        s1, s2, prev = (np.frombuffer(bytes.fromhex(c[k]), np.uint8).copy() for k in ("s1", "s2", "prev"))
+        w = np.array(c["weights"], np.uint32)
+        dest = np.zeros(n, np.uint8)
+        O.xo_fitch_bases(ol.p(s1), ol.p(s2), ol.p(dest), n)
+        assert dest.tobytes().hex() == c["bases"]
+        d2 = np.zeros(n, np.uint8)
+        assert int(O.xo_fitch_bases_and_compare(ol.p(s1), ol.p(s2), ol.p(d2), ol.p(prev), n) != 0) == c["changed_vs_prev"]
+        assert int(O.xo_fitch_bases_and_compare(ol.p(s1), ol.p(s2), ol.p(d2), ol.p(dest), n) != 0) == c["changed_vs_self"]
+        assert O.xo_fitch_score_weight1(ol.p(s1), ol.p(s2), n) == c["score_weight1"]
+        assert O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(w), n) == c["score"]
+        assert O.xo_fitch_score_stopearly(ol.p(s1), ol.p(s2), ol.p(w), n, 8, 1, 0x7FFFFFFF) == c["score_fw1"]
+        assert O.xo_fitch_score_stopearly(ol.p(s1), ol.p(s2), ol.p(w), n, 8, 1, c["limit"]) == c["score_fw1_stopearly_w8"]
+        assert O.xo_fitch_score_weight1_stopearly(ol.p(s1), ol.p(s2), n, 8, c["score_weight1"] // 2) == c["score_weight1_stopearly_w8"]
+        if n:
+            d3 = np.zeros(n, np.uint8)
+            O.xo_fitch_bases_swar64(ol.p(s1), ol.p(s2), ol.p(d3), n // 8)
+            assert (d3 == dest).all()
+            assert O.xo_fitch_score_weight1_swar64(ol.p(s1), ol.p(s2), n // 8) == c["score_weight1"]
+            assert O.xo_fitch_score_swar64(ol.p(s1), ol.p(s2), ol.p(w), n // 8) == c["score"]
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_equals_compiled_reference_on_random_inputs():
+    R = ol.ref()
+    rng = np.random.default_rng(11)
+    for trial in range(3000):
+        nbytes = int(rng.integers(0, 12)) * 8
+        s1, s2, prev = (ol.random_sets(rng, nbytes, rng.choice([0.0, 0.1, 0.5])) for _ in range(3))
+        w = ol.random_weights(rng, nbytes * 2, heavy_fraction=rng.choice([0.0, 0.4, 1.0]), wmax=int(rng.choice([2, 9, 3000])))
+        n8, n4 = nbytes // 8, nbytes // 4
+        want = np.zeros(nbytes, np.uint8)
+        got = np.zeros(nbytes, np.uint8)
+        R.FitchBases_b2_w8_fastc64(ol.p(s1), ol.p(s2), ol.p(want), n8)
+        O.xo_fitch_bases(ol.p(s1), ol.p(s2), ol.p(got), nbytes)
+        assert (want == got).all()
+        for fam, nb in (("b2_w8_fastc64", n8), ("b2_w4_fastc", n4)):
+            assert getattr(R, "FitchScoreWeight1_" + fam)(ol.p(s1), ol.p(s2), nb) == O.xo_fitch_score_weight1(ol.p(s1), ol.p(s2), nbytes)
+            assert getattr(R, "FitchScore_" + fam)(ol.p(s1), ol.p(s2), ol.p(w), nb) == O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(w), nbytes)
+        assert R.FitchScore_b2_w1_basic(ol.p(s1), ol.p(s2), ol.p(w), nbytes) == O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(w), nbytes)
+        assert O.xo_fitch_score_swar64(ol.p(s1), ol.p(s2), ol.p(w), n8) == O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(w), nbytes)
+        limit = int(rng.integers(0, 40))
+        assert R.FitchScore_fw1_stopearly_b2_w8_fastc64(ol.p(s1), ol.p(s2), ol.p(w), n8, limit) == \
+            O.xo_fitch_score_stopearly(ol.p(s1), ol.p(s2), ol.p(w), nbytes, 8, 1, limit)
+        assert R.FitchScore_stopearly_b2_w4_fastc(ol.p(s1), ol.p(s2), ol.p(w), n4, limit) == \
+            O.xo_fitch_score_stopearly(ol.p(s1), ol.p(s2), ol.p(w), nbytes, 4, 0, limit)
+        assert int(R.FitchBasesAndCompare_b2_w8_fastc64(ol.p(s1), ol.p(s2), ol.p(want), ol.p(prev), n8) != 0) == \
+            int(O.xo_fitch_bases_and_compare(ol.p(s1), ol.p(s2), ol.p(got), ol.p(prev), nbytes) != 0)
+
+
+SEARCH_CASES = ["its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16", "mt-10", "EukaryotesrDNA"]
+
+
+@pytest.mark.parametrize("name", SEARCH_CASES)
+def test_oracle_search_reproduces_reference_output(alignment_dir, goldens, name):
+    """Score, tree count, canonical tree set and -- through the host writer -- the reference's result
+    file byte for byte (for mt-10 that file is the reference's own golden build-vswin32/mt-10.tre)."""
+    g = goldens[name]
+    a, p = prepare(alignment_dir, goldens, name)
+    score, n, trees, nodes, calls = ol.search(p)
+    assert (score, n) == (g["score"], g["num_trees"])
+    # same depth-first order, same bound updates => the very same nodes; the reference's counter also
+    # counts the two FitchScore calls of ConstructBaseTree (src/common.c:623-637)
+    assert nodes == g["ref_bandb_nodes"] and calls + 2 == g["ref_score_calls"]
+    canon = sorted(canonical_newick(t) for t in trees)
+    assert canon == golden_trees(name)
+    blob = ("\n".join(canon) + "\n").encode() if canon else b""
+    assert hashlib.sha256(blob).hexdigest() == g["canonical_sha256"]
+    # the oracle walks the reference's DFS order, so its text is the reference's tree block
+    body = "".join("\tTREE FASTDNAMP_%d = [&U] %s\n" % (i + 1, t) for i, t in enumerate(trees))
+    assert body.encode() in golden_output(name)
+
+
+def test_mt10_golden_is_the_reference_repo_file(goldens):
+    """tests/golden/trees/mt-10.out.gz equals reference build-vswin32/mt-10.tre (CRLF stripped); the sha
+    below was taken from that file when the fixture was generated."""
+    out = golden_output("mt-10")
+    assert hashlib.sha256(out).hexdigest() == goldens["mt-10"]["output_sha256"]
+    assert b"Each tree has score 16179" in out and out.count(b"TREE FASTDNAMP_") == 1
+    ref = "/root/reference/build-vswin32/mt-10.tre"
+    if os.path.exists(ref):
+        assert open(ref, "rb").read().replace(b"\r", b"") == out
+
+
+def test_too_low_bound_finds_nothing(alignment_dir, goldens):
+    a, p = prepare(alignment_dir, goldens, "its10")
+    score, n, trees, _, _ = ol.search(p, bound=goldens["its10"]["score"] - 1)
+    assert n == 0 and trees == [] and score == goldens["its10"]["score"] - 1

@@ -1,0 +1,103 @@
+// Device-side Fitch primitives on 32-bit words (8 sites) and 128-bit blocks (32 sites), sm_100a.
+//
+// Semantics: reference src/seq_b2_w1_basic.c:155-244 (per site: intersection if non-empty, else union
+// and charge the site's weight).  The SWAR formulation differs from the reference's 64-bit one
+// (src/seq_b2_w8_fastc64.c:11-23): the "empty" marker lives on bit 3 of every nibble so that it feeds
+// POPC directly, and weighted scoring uses bit-sliced weights (one POPC per weight bit) instead of
+// sixteen masked adds per word (src/fitchtemplate_b2_w8_fastc64.inc:118-152).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xmp {
+
+// Site weights, bit-sliced: plane k holds bit 3 of nibble s set iff bit k of weights[site s] is set.
+// Words >= heavy_words carry only weight-1 sites (weights are sorted descending, padding weighs 1),
+// so their cost is a plain population count -- the reference's FASTWEIGHT1FITCH hand-over
+// (src/fitchtemplate_b2_w8_fastc64.inc:105-113), at 8-site instead of 16-site granularity.
+struct WeightPlanes {
+	const unsigned *planes;   // [n_planes][n_words]
+	unsigned n_words;         // 32-bit words per state set = 4 * n_blocks
+	unsigned heavy_words;
+	unsigned n_planes;
+};
+
+// Bit 3 of each nibble set iff that site's sets do not intersect.
+__device__ __forceinline__ unsigned empty_mask(unsigned a, unsigned b) {
+	unsigned x = a & b;
+	return ~(((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u;
+}
+
+// Preliminary Fitch set of a node from its two neighbours.
+__device__ __forceinline__ unsigned fitch_word(unsigned a, unsigned b) {
+	unsigned e = empty_mask(a, b);
+	unsigned m = (e - (e >> 3)) | e;          // 0xF where the intersection is empty
+	return (a & b) | ((a | b) & m);
+}
+
+__device__ __forceinline__ uint4 fitch_block(const uint4 &a, const uint4 &b) {
+	return make_uint4(fitch_word(a.x, b.x), fitch_word(a.y, b.y), fitch_word(a.z, b.z), fitch_word(a.w, b.w));
+}
+
+__device__ __forceinline__ unsigned cost_word_w1(unsigned a, unsigned b) {
+	return __popc(empty_mask(a, b));
+}
+
+__device__ __forceinline__ unsigned cost_word(unsigned a, unsigned b, unsigned word, const WeightPlanes &wp) {
+	unsigned e = empty_mask(a, b);
+	if (word >= wp.heavy_words) return __popc(e);
+	unsigned s = 0;
+	for (unsigned k = 0; k < wp.n_planes; ++k) s += __popc(e & __ldg(wp.planes + (size_t) k * wp.n_words + word)) << k;
+	return s;
+}
+
+// Cost of one 128-bit block; `block` is its index inside the state set.
+__device__ __forceinline__ unsigned cost_block(const uint4 &a, const uint4 &b, unsigned block, const WeightPlanes &wp) {
+	unsigned w = 4 * block;
+	if (w >= wp.heavy_words) {
+		return __popc(empty_mask(a.x, b.x)) + __popc(empty_mask(a.y, b.y)) + __popc(empty_mask(a.z, b.z)) + __popc(empty_mask(a.w, b.w));
+	}
+	return cost_word(a.x, b.x, w, wp) + cost_word(a.y, b.y, w + 1, wp) + cost_word(a.z, b.z, w + 2, wp) + cost_word(a.w, b.w, w + 3, wp);
+}
+
+// Streaming 128-bit load: read once, do not keep in L1.
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+	v += __shfl_xor_sync(0xffffffffu, v, 16);
+	v += __shfl_xor_sync(0xffffffffu, v, 8);
+	v += __shfl_xor_sync(0xffffffffu, v, 4);
+	v += __shfl_xor_sync(0xffffffffu, v, 2);
+	v += __shfl_xor_sync(0xffffffffu, v, 1);
+	return v;
+}
+
+// The acceptance test of BandBScanEdge, in the reference's own signed arithmetic
+// (src/yanbader.c:115-116,152,176): ties are kept.
+__device__ __forceinline__ bool accept_insertion(unsigned cost, unsigned bound, unsigned score, unsigned rest) {
+	int allowable = (int) (bound - score - rest);
+	return (int) cost <= allowable;
+}
+
+// Warp-aggregated append: every lane with keep == true gets a distinct slot after *counter.
+__device__ __forceinline__ unsigned warp_append(bool keep, unsigned *counter) {
+	unsigned ballot = __ballot_sync(0xffffffffu, keep);
+	unsigned lane = threadIdx.x & 31u;
+	unsigned base = 0;
+	if (ballot) {
+		int leader = __ffs(ballot) - 1;
+		if ((int) lane == leader) base = atomicAdd(counter, (unsigned) __popc(ballot));
+		base = __shfl_sync(0xffffffffu, base, leader);
+	}
+	return base + __popc(ballot & ((1u << lane) - 1u));
+}
+
+// Edge-id helpers (include/xmp_cuda.h "Edge ids").
+__device__ __host__ __forceinline__ bool edge_is_leaf(unsigned e) { return e == 0 || (e & 1u); }
+__device__ __host__ __forceinline__ unsigned edge_taxon(unsigned e) { return (e + 3u) >> 1; }
+
+}  // namespace xmp

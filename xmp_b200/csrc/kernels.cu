@@ -1,0 +1,279 @@
+// Batched Fitch kernels for sm_100a: insertion scoring of (partial tree, edge) pairs, pruning with
+// ballot compaction, and construction of edge-indexed state-set arrays from tree topologies.
+//
+// What they replace in the reference: the per-pair CHOSEN_FitchScore call and acceptance test inside
+// BandBScanEdge (src/yanbader.c:152-176), and the FitchBases passes of ConstructBaseTree /
+// UpdateTreeAfterInsertion (src/common.c:559-620, src/yanbader.c:450-495).
+//
+// This is HBM-bound bitwise integer work: 0.5 B per site-merge for scoring.
+// No tensor cores; the design points are coalesced 128-bit loads, enough independent loads in flight
+// per SM to cover HBM latency, and one reduction per (pair, tile).
+#include "ctx.h"
+
+namespace xmp {
+
+// ---------------------------------------------------------------------------------------------
+// Wide state sets (n_blocks >= 32): one warp per (pair, tile); a tile is 32*K consecutive blocks.
+// The taxon's tile lives in registers for the whole CTA lifetime and is reused for every pair the
+// warp visits, so the only streamed operand is the edge state set: 16 B per lane per load,
+// 512 B per warp per load, 2*K independent loads in flight per lane.
+// Grid: x = tile, y = group of 8*pairs_per_warp pairs.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+k_score_wide(const uint4 *__restrict__ sets, unsigned long long tree_stride, unsigned pairs_per_tree,
+             const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned n_blocks,
+             unsigned long long n_pairs, unsigned pairs_per_warp, unsigned *__restrict__ cost) {
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const unsigned col0 = blockIdx.x * (32u * K) + lane;
+	const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+	uint4 t[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) t[k] = (col0 + 32u * k < n_blocks) ? __ldg(taxon_row + col0 + 32u * k) : ones;
+	const bool heavy = 4u * blockIdx.x * (32u * K) < wp.heavy_words;   // uniform over the CTA
+
+	unsigned long long p = ((unsigned long long) blockIdx.y * 8u + warp) * pairs_per_warp;
+	const unsigned long long p_end = min(p + pairs_per_warp, n_pairs);
+
+	auto base_of = [&](unsigned long long pair) {
+		return sets + (pair / pairs_per_tree) * tree_stride + (pair % pairs_per_tree) * (unsigned long long) n_blocks + col0;
+	};
+	auto tile_cost = [&](const uint4 (&v)[K]) {
+		unsigned s = 0;
+		if (!heavy) {
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				s += __popc(empty_mask(v[k].x, t[k].x)) + __popc(empty_mask(v[k].y, t[k].y)) +
+				     __popc(empty_mask(v[k].z, t[k].z)) + __popc(empty_mask(v[k].w, t[k].w));
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < K; ++k) s += cost_block(v[k], t[k], col0 + 32u * k, wp);
+		}
+		return warp_sum(s);
+	};
+
+	for (; p + 1 < p_end; p += 2) {
+		const uint4 *s0 = base_of(p), *s1 = base_of(p + 1);
+		uint4 v0[K], v1[K];
+#pragma unroll
+		for (int k = 0; k < K; ++k) v0[k] = (col0 + 32u * k < n_blocks) ? ld_stream(s0 + 32u * k) : ones;
+#pragma unroll
+		for (int k = 0; k < K; ++k) v1[k] = (col0 + 32u * k < n_blocks) ? ld_stream(s1 + 32u * k) : ones;
+		unsigned c0 = tile_cost(v0), c1 = tile_cost(v1);
+		if (lane == 0) {
+			atomicAdd(cost + p, c0);
+			atomicAdd(cost + p + 1, c1);
+		}
+	}
+	if (p < p_end) {
+		const uint4 *s0 = base_of(p);
+		uint4 v0[K];
+#pragma unroll
+		for (int k = 0; k < K; ++k) v0[k] = (col0 + 32u * k < n_blocks) ? ld_stream(s0 + 32u * k) : ones;
+		unsigned c0 = tile_cost(v0);
+		if (lane == 0) atomicAdd(cost + p, c0);
+	}
+}
+
+// Acceptance test + ballot compaction over finished costs (wide path only).
+__global__ void __launch_bounds__(256)
+k_prune(const unsigned *__restrict__ cost, unsigned long long n_pairs, unsigned pairs_per_tree,
+        const unsigned *__restrict__ base_score, unsigned bound, unsigned rest,
+        unsigned *__restrict__ survivors, unsigned *n_survivors) {
+	unsigned long long p = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	bool keep = false;
+	if (p < n_pairs) {
+		unsigned base = base_score ? __ldg(base_score + p / pairs_per_tree) : 0u;
+		keep = accept_insertion(cost[p], bound, base, rest);
+	}
+	unsigned slot = warp_append(keep, n_survivors);
+	if (keep) survivors[slot] = (unsigned) p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Narrow state sets: G lanes per pair (G = 1, 2, 4, 8, 16, 32), each lane takes blocks sub, sub+G, ...
+// The cost is complete inside the group, so scoring, the acceptance test and the ballot compaction
+// are one kernel.
+// ---------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+k_score_group(const uint4 *__restrict__ sets, unsigned long long tree_stride, unsigned pairs_per_tree,
+              const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned n_blocks, unsigned long long n_pairs,
+              const unsigned *__restrict__ base_score, unsigned bound, unsigned rest,
+              unsigned *__restrict__ cost, unsigned *__restrict__ survivors, unsigned *n_survivors) {
+	const unsigned long long gthread = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long pair = gthread / G;
+	const unsigned sub = (unsigned) (gthread % G);
+	const bool valid = pair < n_pairs;
+	unsigned s = 0;
+	if (valid) {
+		const uint4 *src = sets + (pair / pairs_per_tree) * tree_stride + (pair % pairs_per_tree) * (unsigned long long) n_blocks;
+		for (unsigned b = sub; b < n_blocks; b += G) s += cost_block(ld_stream(src + b), __ldg(taxon_row + b), b, wp);
+	}
+#pragma unroll
+	for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	bool keep = false;
+	if (valid && sub == 0) {
+		cost[pair] = s;
+		if (survivors) {
+			unsigned base = base_score ? __ldg(base_score + pair / pairs_per_tree) : 0u;
+			keep = accept_insertion(s, bound, base, rest);
+		}
+	}
+	if (survivors) {
+		unsigned slot = warp_append(keep, n_survivors);
+		if (keep) survivors[slot] = (unsigned) pair;
+	}
+}
+
+template <int G>
+static void launch_group(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree_stride, unsigned ppt, const uint4 *row,
+                         unsigned long long n_pairs, const unsigned *d_base, unsigned bound, unsigned rest, unsigned *d_cost,
+                         unsigned *d_surv, unsigned *d_nsurv) {
+	unsigned long long threads = n_pairs * G;
+	unsigned blocks = (unsigned) ((threads + 255) / 256);
+	k_score_group<G><<<blocks, 256, 0, ctx->stream>>>(d_sets, tree_stride, ppt, row, ctx->wp, ctx->n_blocks, n_pairs, d_base,
+	                                                  bound, rest, d_cost, d_surv, d_nsurv);
+}
+
+template <int K>
+static void launch_wide(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree_stride, unsigned ppt, const uint4 *row,
+                        unsigned long long n_pairs, unsigned *d_cost) {
+	const unsigned W = ctx->n_blocks;
+	const unsigned tiles = (W + 32 * K - 1) / (32 * K);
+	unsigned ppw = 32;
+	// Keep at least ~8 CTAs per SM in the grid so that the tail wave is short.
+	while (ppw > 1 && (unsigned long long) tiles * ((n_pairs + 8ull * ppw - 1) / (8ull * ppw)) < 8ull * ctx->sm_count) ppw >>= 1;
+	unsigned long long groups = (n_pairs + 8ull * ppw - 1) / (8ull * ppw);
+	if (groups > 65535ull) {
+		ppw = (unsigned) ((n_pairs + 8ull * 65535ull - 1) / (8ull * 65535ull));
+		groups = (n_pairs + 8ull * ppw - 1) / (8ull * ppw);
+	}
+	dim3 grid(tiles, (unsigned) groups);
+	k_score_wide<K><<<grid, 256, 0, ctx->stream>>>(d_sets, tree_stride, ppt, row, ctx->wp, W, n_pairs, ppw, d_cost);
+}
+
+int launch_score_sets(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree_stride, size_t n_pairs, unsigned ppt,
+                      unsigned taxon, const unsigned *d_base, unsigned bound, unsigned *d_cost, unsigned *d_surv,
+                      unsigned *d_nsurv) {
+	if (n_pairs == 0) return XMP_OK;
+	const uint4 *row = ctx->d_rows + (size_t) taxon * ctx->n_blocks;
+	const unsigned rest = ctx->rest_bound[taxon];
+	const unsigned W = ctx->n_blocks;
+	if (d_nsurv) XMP_CUDA(cudaMemsetAsync(d_nsurv, 0, sizeof(unsigned), ctx->stream));
+	if (W >= 64) {
+		XMP_CUDA(cudaMemsetAsync(d_cost, 0, n_pairs * sizeof(unsigned), ctx->stream));
+		if (W >= 256) launch_wide<8>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
+		else if (W >= 128) launch_wide<4>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
+		else launch_wide<2>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
+		if (d_surv) {
+			unsigned blocks = (unsigned) ((n_pairs + 255) / 256);
+			k_prune<<<blocks, 256, 0, ctx->stream>>>(d_cost, n_pairs, ppt, d_base, bound, rest, d_surv, d_nsurv);
+		}
+	} else if (W > 16) {
+		launch_group<32>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	} else if (W > 8) {
+		launch_group<16>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	} else if (W > 4) {
+		launch_group<8>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	} else if (W > 2) {
+		launch_group<4>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	} else if (W > 1) {
+		launch_group<2>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	} else {
+		launch_group<1>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_base, bound, rest, d_cost, d_surv, d_nsurv);
+	}
+	XMP_CUDA(cudaGetLastError());
+	return XMP_OK;
+}
+
+int launch_score_batch(xmp_ctx *ctx, const uint4 *d_sets, size_t n_pairs, unsigned pairs_per_tree, unsigned taxon,
+                       const unsigned *d_base_score, unsigned bound, unsigned *d_cost, unsigned *d_survivors,
+                       unsigned *d_n_survivors) {
+	if (pairs_per_tree == 0) pairs_per_tree = 1;
+	return launch_score_sets(ctx, d_sets, (unsigned long long) pairs_per_tree * ctx->n_blocks, n_pairs, pairs_per_tree, taxon,
+	                         d_base_score, bound, d_cost, d_survivors, d_n_survivors);
+}
+
+// ---------------------------------------------------------------------------------------------
+// State sets of whole trees from their topologies: one thread per (tree, 128-bit column).
+// UP sets in reverse pre-order, then DOWN and MIDPOINT in pre-order.
+// ---------------------------------------------------------------------------------------------
+template <int MAXE>
+__global__ void __launch_bounds__(128)
+k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp, const uint8_t *__restrict__ topo,
+             unsigned topo_stride, unsigned n_trees, unsigned m, uint4 *__restrict__ out, unsigned long long rec_blocks,
+             int store_all, unsigned *tree_len, unsigned constant_weight) {
+	const unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long tree = idx / n_blocks;
+	const unsigned col = (unsigned) (idx % n_blocks);
+	const bool valid = tree < n_trees;
+	const unsigned E = 2 * m - 3;
+	unsigned len = 0;
+	if (valid) {
+		const uint8_t *par = topo + tree * 4ull * topo_stride, *k0 = par + topo_stride, *k1 = k0 + topo_stride, *pre = k1 + topo_stride;
+		uint4 up[MAXE], down[MAXE];
+		for (int i = (int) E - 1; i >= 0; --i) {
+			unsigned e = pre[i];
+			if (edge_is_leaf(e)) {
+				up[e] = __ldg(rows + (size_t) edge_taxon(e) * n_blocks + col);
+			} else {
+				uint4 a = up[k0[e]], b = up[k1[e]];
+				len += cost_block(a, b, col, wp);
+				up[e] = fitch_block(a, b);
+			}
+		}
+		const uint4 r0 = __ldg(rows + col);
+		len += cost_block(up[pre[0]], r0, col, wp);
+		uint4 *rec = out + tree * rec_blocks;
+		for (unsigned i = 0; i < E; ++i) {
+			unsigned e = pre[i], p = par[e];
+			uint4 d;
+			if (p == 0xFFu) {
+				d = r0;
+			} else {
+				unsigned sib = (k0[p] == e) ? k1[p] : k0[p];
+				d = fitch_block(down[p], up[sib]);
+			}
+			down[e] = d;
+			rec[(size_t) e * n_blocks + col] = fitch_block(up[e], d);
+			if (store_all) {
+				rec[((size_t) E + e) * n_blocks + col] = up[e];
+				rec[((size_t) 2 * E + e) * n_blocks + col] = d;
+			}
+		}
+	}
+	if (tree_len) {
+		const unsigned long long t0 = __shfl_sync(0xffffffffu, tree, 0);
+		const bool uniform = __all_sync(0xffffffffu, tree == t0);
+		if (uniform) {
+			len = warp_sum(len);
+			if ((threadIdx.x & 31u) == 0 && valid) atomicAdd(tree_len + tree, len + (col == 0 ? constant_weight : 0u));
+		} else if (valid) {
+			atomicAdd(tree_len + tree, len + (col == 0 ? constant_weight : 0u));
+		}
+	}
+}
+
+int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m, uint4 *d_out,
+                      size_t rec_blocks, bool store_all, unsigned *d_tree_len) {
+	if (n_trees == 0) return XMP_OK;
+	const unsigned E = 2 * m - 3;
+	const unsigned long long threads = (unsigned long long) n_trees * ctx->n_blocks;
+	const unsigned blocks = (unsigned) ((threads + 127) / 128);
+	if (d_tree_len) XMP_CUDA(cudaMemsetAsync(d_tree_len, 0, (size_t) n_trees * sizeof(unsigned), ctx->stream));
+#define XMP_BUILD(MAXE)                                                                                             \
+	k_build_sets<MAXE><<<blocks, 128, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo, topo_stride, n_trees, m, \
+	                                                    d_out, rec_blocks, store_all ? 1 : 0, d_tree_len, ctx->constant_weight)
+	if (E <= 16) XMP_BUILD(16);
+	else if (E <= 32) XMP_BUILD(32);
+	else if (E <= 72) XMP_BUILD(72);
+	else if (E <= 128) XMP_BUILD(128);
+	else XMP_BUILD(200);
+#undef XMP_BUILD
+	XMP_CUDA(cudaGetLastError());
+	return XMP_OK;
+}
+
+}  // namespace xmp

@@ -1,0 +1,763 @@
+// Exact maximum-parsimony branch and bound on the device: a batched frontier in place of the
+// reference's recursive per-edge loop.
+//
+// Reference behaviour being replaced (all in src/yanbader.c): BranchAndBound (:21-109) visits one
+// partial tree; BandBScanEdge (:113-244) scores the next taxon against each of its 2m-3 edges and, for
+// every edge whose cost fits under the bound, InsertNode + UpdateTreeAfterInsertion (:450-495) build the
+// child tree's UP / DOWN / MIDPOINT sets and recurse; complete trees lower the bound and are recorded
+// (:195-213).  Here the same search tree is explored a batch of partial trees at a time:
+//
+//   k_expand_score   every (partial tree, edge) pair of the batch in one launch: weighted Fitch cost
+//                    (AND / empty-nibble mask / POPC), group-shuffle reduction, the reference's signed
+//                    acceptance test, ballot compaction of survivors; on the last level survivors are
+//                    complete trees: atomicMin on the bound and a tree record.
+//   k_build_children one thread per (survivor, 128-bit column): splices the new leaf into the parent's
+//                    topology and recomputes the child's state sets (UP along the root path, DOWN and
+//                    MIDPOINT in pre-order).
+//
+// Frontier layout in HBM: one pool per tree size m.  A node is a header (score, insertion path,
+// topology as three byte arrays over edge ids) plus a record of 3 * (2m-3) state sets laid out
+// [MIDPOINT | UP | DOWN][edge][block], so the scoring kernel streams a contiguous MIDPOINT array per
+// node.  Pools are stacks: the scheduler always expands the deepest level that holds a worthwhile
+// batch, which bounds memory like a depth-first search while keeping launches wide.
+//
+// Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
+// recorded carries its length and the final filter keeps those equal to the final bound.
+#include <algorithm>
+#include <string.h>
+#include "ctx.h"
+
+namespace xmp {
+
+struct Layout {
+	unsigned n;        // taxa in the problem
+	unsigned W;        // 128-bit blocks per state set
+	unsigned HB;       // header bytes (multiple of 16)
+	unsigned off_par, off_k0, off_k1;   // byte offsets of the topology arrays inside a header
+	unsigned trec;     // bytes per emitted tree record: score + path
+};
+// Header: [0,4) score | [4,4+n) path (byte 0 of it = the root's child) | par[] | kid0[] | kid1[]
+#define HDR_PATH 4u
+
+struct PoolView {
+	uint8_t *hdr;
+	uint4 *sets;
+	unsigned long long rec;   // uint4 per node
+};
+
+__device__ __forceinline__ unsigned path_hash(const uint8_t *path, unsigned m, unsigned e) {
+	unsigned h = 2166136261u;
+	for (unsigned t = 3; t < m; ++t) h = (h ^ path[t]) * 16777619u;
+	h = (h ^ e) * 16777619u;
+	return h ^ (h >> 15);
+}
+
+// ---- scoring + pruning of a batch of partial trees --------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256)
+k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes,
+               const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned rest, unsigned *bound_ptr, int last,
+               uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
+               unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
+	const unsigned E = 2 * m - 3;
+	const unsigned long long gthread = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long pair = gthread / G;
+	const unsigned sub = (unsigned) (gthread % G);
+	const bool valid = pair < n_nodes * E;
+	const unsigned long long node = first + pair / E;
+	const unsigned e = (unsigned) (pair % E);
+	unsigned s = 0;
+	if (valid) {
+		const uint4 *src = pool.sets + node * pool.rec + (unsigned long long) e * L.W;
+		for (unsigned b = sub; b < L.W; b += G) s += cost_block(src[b], __ldg(taxon_row + b), b, wp);
+	}
+#pragma unroll
+	for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+
+	bool keep = false;
+	unsigned new_score = 0;
+	const uint8_t *hdr = pool.hdr + node * L.HB;
+	if (valid && sub == 0) {
+		const unsigned score = *(const unsigned *) hdr;
+		const unsigned bound = *(volatile unsigned *) bound_ptr;
+		keep = accept_insertion(s, bound, score, rest);
+		new_score = score + s;
+		if (keep && shard_count > 1) keep = (path_hash(hdr + HDR_PATH, m, e) % shard_count) == shard_index;
+	}
+	if (last) {
+		if (keep) atomicMin(bound_ptr, new_score);
+		unsigned slot = warp_append(keep, n_trees);
+		if (keep && slot < trees_cap) {
+			uint8_t *rec = trees + (size_t) slot * L.trec;
+			*(unsigned *) rec = new_score;
+			for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = hdr[HDR_PATH + t];
+			rec[4 + m] = (uint8_t) e;
+		}
+	} else {
+		unsigned slot = warp_append(keep, n_surv);
+		if (keep) surv[slot] = make_uint4((unsigned) node, e, new_score, 0u);
+	}
+}
+
+// ---- child construction ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
+                 const unsigned *n_surv_ptr, unsigned long long child_first, const uint4 *__restrict__ rows,
+                 unsigned long long *merges) {
+	const unsigned n_surv = *n_surv_ptr;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, a = E, b = E + 1;
+	const unsigned long long total = (unsigned long long) n_surv * W;
+	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+	     idx += (unsigned long long) gridDim.x * blockDim.x) {
+		const unsigned s = (unsigned) (idx / W), col = (unsigned) (idx % W);
+		const uint4 sv = surv[s];
+		const unsigned pnode = sv.x, v = sv.y;
+		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
+		const uint8_t *ppar = ph + L.off_par, *pk0 = ph + L.off_k0, *pk1 = ph + L.off_k1;
+		const unsigned pv = ppar[v];
+		// The child's topology = the parent's with leaf a and internal node b spliced in above v.
+		auto par_of = [&](unsigned x) -> unsigned { return (x == a || x == v) ? b : (x == b ? pv : (unsigned) ppar[x]); };
+		auto kid0_of = [&](unsigned x) -> unsigned {
+			if (x == b) return a;
+			unsigned k = pk0[x];
+			return (x == pv && k == v) ? b : k;
+		};
+		auto kid1_of = [&](unsigned x) -> unsigned {
+			if (x == b) return v;
+			unsigned k = pk1[x];
+			return (x == pv && k == v) ? b : k;
+		};
+		const unsigned top = (pv == 0xFFu) ? b : (unsigned) ph[HDR_PATH];
+
+		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W;
+		uint4 *CM = child.sets + (child_first + s) * child.rec;
+		uint4 *CU = CM + (unsigned long long) Ec * W, *CD = CU + (unsigned long long) Ec * W;
+
+		// UP: unchanged off the root path; recomputed from the new leaf up to the root's child.
+#pragma unroll 4
+		for (unsigned e = 0; e < E; ++e) CU[(size_t) e * W + col] = __ldg(PU + (size_t) e * W + col);
+		const uint4 rt = __ldg(rows + (size_t) m * W + col);
+		CU[(size_t) a * W + col] = rt;
+		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W + col));
+		CU[(size_t) b * W + col] = u;
+		unsigned n_up = 1;
+		for (unsigned x = b;;) {
+			const unsigned p = par_of(x);
+			if (p == 0xFFu) break;
+			const unsigned k0 = kid0_of(p);
+			const unsigned other = (k0 == x) ? kid1_of(p) : k0;   // off the path: its UP is the parent tree's
+			u = fitch_block(u, __ldg(PU + (size_t) other * W + col));
+			CU[(size_t) p * W + col] = u;
+			x = p;
+			++n_up;
+		}
+
+		// DOWN and MIDPOINT for every edge, stackless pre-order walk.
+		const uint4 r0 = __ldg(rows + col);
+		uint4 dpar = r0;
+		bool have_dpar = false;
+		for (unsigned x = top;;) {
+			const unsigned p = par_of(x);
+			uint4 d;
+			if (p == 0xFFu) {
+				d = r0;
+			} else {
+				const unsigned k0 = kid0_of(p);
+				const unsigned sib = (k0 == x) ? kid1_of(p) : k0;
+				const uint4 dp = have_dpar ? dpar : CD[(size_t) p * W + col];
+				d = fitch_block(dp, CU[(size_t) sib * W + col]);
+			}
+			CD[(size_t) x * W + col] = d;
+			CM[(size_t) x * W + col] = fitch_block(CU[(size_t) x * W + col], d);
+			if (!edge_is_leaf(x)) {
+				dpar = d;
+				have_dpar = true;
+				x = kid0_of(x);
+				continue;
+			}
+			have_dpar = false;
+			bool finished = false;
+			for (;;) {
+				const unsigned q = par_of(x);
+				if (q == 0xFFu) { finished = true; break; }
+				if (kid0_of(q) == x) { x = kid1_of(q); break; }
+				x = q;
+			}
+			if (finished) break;
+		}
+
+		if (col == 0) {
+			uint8_t *ch = child.hdr + (size_t) (child_first + s) * L.HB;
+			for (unsigned i = 0; i < L.HB / 16; ++i) ((uint4 *) ch)[i] = ((const uint4 *) ph)[i];
+			*(unsigned *) ch = sv.z;
+			ch[HDR_PATH] = (uint8_t) top;
+			ch[HDR_PATH + m] = (uint8_t) v;
+			uint8_t *cpar = ch + L.off_par, *ck0 = ch + L.off_k0, *ck1 = ch + L.off_k1;
+			cpar[a] = cpar[v] = (uint8_t) b;
+			cpar[b] = (uint8_t) pv;
+			ck0[b] = (uint8_t) a;
+			ck1[b] = (uint8_t) v;
+			ck0[a] = ck1[a] = 0xFF;
+			if (pv != 0xFFu) {
+				if (pk0[pv] == v) ck0[pv] = (uint8_t) b; else ck1[pv] = (uint8_t) b;
+			}
+			atomicAdd(merges, (unsigned long long) (n_up + 2 * Ec));
+		}
+	}
+}
+
+// Headers for nodes whose sets were built from topologies (the root job, imported jobs).
+__global__ void k_write_headers(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n_jobs,
+                                const uint8_t *__restrict__ topo, unsigned topo_stride, const uint8_t *__restrict__ paths,
+                                const unsigned *__restrict__ tree_len) {
+	const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n_jobs) return;
+	const unsigned E = 2 * m - 3;
+	uint8_t *h = pool.hdr + (size_t) (first + j) * L.HB;
+	for (unsigned i = 4; i < L.HB; ++i) h[i] = 0xFF;
+	*(unsigned *) h = tree_len[j];
+	const uint8_t *t = topo + (size_t) j * 4 * topo_stride;
+	for (unsigned k = 0; k < L.n; ++k) h[HDR_PATH + k] = paths[(size_t) j * L.n + k];
+	h[HDR_PATH] = t[3 * topo_stride];   // first edge in pre-order = the root's child
+	for (unsigned e = 0; e < E; ++e) {
+		h[L.off_par + e] = t[e];
+		h[L.off_k0 + e] = t[topo_stride + e];
+		h[L.off_k1 + e] = t[2 * topo_stride + e];
+	}
+}
+
+__global__ void k_filter_trees(const uint8_t *__restrict__ src, unsigned n_src, unsigned trec, const unsigned *bound_ptr,
+                               uint8_t *__restrict__ dst, unsigned *n_dst) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool keep = false;
+	if (i < n_src) keep = *(const unsigned *) (src + (size_t) i * trec) <= *bound_ptr;
+	unsigned slot = warp_append(keep, n_dst);
+	if (keep) {
+		const unsigned *s = (const unsigned *) (src + (size_t) i * trec);
+		unsigned *d = (unsigned *) (dst + (size_t) slot * trec);
+		for (unsigned k = 0; k < trec / 4; ++k) d[k] = s[k];
+	}
+}
+
+__global__ void k_lower_bound(unsigned *bound_ptr, unsigned value) { atomicMin(bound_ptr, value); }
+
+// ---- host side ----------------------------------------------------------------------------------------
+struct Pool {
+	uint8_t *hdr = nullptr;
+	uint4 *sets = nullptr;
+	unsigned long long cap = 0, count = 0, rec = 0;
+	unsigned E = 0;
+	PoolView view() const { return PoolView{hdr, sets, rec}; }
+};
+
+struct Search {
+	xmp_search_params prm;
+	Layout L;
+	unsigned n = 0, split_level = 0;
+	Pool pool[XMP_MAX_TAXA + 2];
+	unsigned *d_bound = nullptr, *d_nsurv = nullptr, *d_ntrees = nullptr, *d_len = nullptr;
+	unsigned long long *d_merges = nullptr;
+	uint4 *d_surv = nullptr;
+	unsigned long long surv_cap = 0;
+	uint8_t *d_trees[2] = {nullptr, nullptr};
+	int cur = 0;
+	unsigned trees_cap = 0, ntrees_dev = 0;
+	unsigned *h_pin = nullptr;            // pinned copy of the device scalars: [0] bound, [1] n_surv, [2] n_trees
+	std::vector<uint8_t> host_trees;      // records (score + path) that left the device, each <= the bound at that time
+	unsigned bound = 0x7fffffffu;
+	bool done = false, finished = false;
+	xmp_search_stats st;
+	Scratch topo, pathbuf;
+};
+
+static const unsigned kMinBatchNodes = 4096;   // prefer levels holding at least this many open trees
+static const unsigned kBeam = 64;              // width of the initial greedy dive
+
+static double odd_factorial(unsigned m) {      // number of distinct trees on m taxa: (2m-5)!!
+	double t = 1;
+	for (unsigned k = 4; k <= m; ++k) t *= (double) (2 * k - 5);
+	return t;
+}
+
+void search_destroy(xmp_ctx *ctx) {
+	Search *S = ctx->search;
+	if (!S) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) {
+		if (S->pool[m].hdr) cudaFree(S->pool[m].hdr);
+		if (S->pool[m].sets) cudaFree(S->pool[m].sets);
+	}
+	if (S->d_bound) cudaFree(S->d_bound);
+	if (S->d_surv) cudaFree(S->d_surv);
+	if (S->d_trees[0]) cudaFree(S->d_trees[0]);
+	if (S->d_trees[1]) cudaFree(S->d_trees[1]);
+	if (S->d_len) cudaFree(S->d_len);
+	if (S->h_pin) cudaFreeHost(S->h_pin);
+	S->topo.release();
+	S->pathbuf.release();
+	delete S;
+	ctx->search = nullptr;
+}
+
+static int alloc_search(xmp_ctx *ctx, Search *S) {
+	const unsigned n = S->n, W = ctx->n_blocks, Emax = 2 * n - 3;
+	Layout &L = S->L;
+	L.n = n;
+	L.W = W;
+	L.off_par = HDR_PATH + n;
+	L.off_k0 = L.off_par + Emax;
+	L.off_k1 = L.off_k0 + Emax;
+	L.HB = (L.off_k1 + Emax + 15u) & ~15u;
+	L.trec = 4 + ((n + 3u) & ~3u);
+
+	size_t free_b = 0, total_b = 0;
+	XMP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>(free_b / 2, (size_t) 16 << 30);
+	S->trees_cap = 1u << 20;
+	const size_t fixed = 2 * (size_t) S->trees_cap * L.trec + ((size_t) 64 << 20);
+	if (budget < fixed + ((size_t) 64 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
+	budget -= fixed;
+
+	// Largest per-level capacity C such that all pools fit; a level never needs more than (2m-5)!! nodes.
+	auto bytes_for = [&](double C) {
+		double tot = 0;
+		for (unsigned m = 3; m < n; ++m) {
+			double c = std::min(C, odd_factorial(m));
+			tot += c * ((double) 3 * (2 * m - 3) * W * 16 + L.HB);
+		}
+		return tot + C * 16;   // survivors
+	};
+	double lo = 256, hi = 4194304.0;
+	if (bytes_for(lo) > (double) budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
+	while (hi - lo > 1) {
+		double mid = (lo + hi) / 2;
+		if (bytes_for(mid) <= (double) budget) lo = mid; else hi = mid;
+	}
+	const unsigned long long C = (unsigned long long) lo;
+	for (unsigned m = 3; m < n; ++m) {
+		Pool &P = S->pool[m];
+		P.E = 2 * m - 3;
+		P.rec = 3ull * P.E * W;
+		P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
+		P.count = 0;
+		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.HB));
+		XMP_CUDA(cudaMalloc(&P.sets, (size_t) P.cap * P.rec * 16));
+	}
+	S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) kBeam * Emax);
+	XMP_CUDA(cudaMalloc(&S->d_surv, (size_t) S->surv_cap * 16));
+	XMP_CUDA(cudaMalloc(&S->d_trees[0], (size_t) S->trees_cap * L.trec));
+	XMP_CUDA(cudaMalloc(&S->d_trees[1], (size_t) S->trees_cap * L.trec));
+	XMP_CUDA(cudaMalloc(&S->d_bound, 64));
+	S->d_nsurv = S->d_bound + 1;
+	S->d_ntrees = S->d_bound + 2;
+	S->d_merges = (unsigned long long *) (S->d_bound + 4);
+	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 64, ctx->stream));
+	XMP_CUDA(cudaMalloc(&S->d_len, 65536 * sizeof(unsigned)));
+	XMP_CUDA(cudaMallocHost(&S->h_pin, 64));
+	return XMP_OK;
+}
+
+// Creates open nodes from insertion paths (job descriptors): the thief-side "fast-forward" of the
+// reference (src/yanbader.c:95-99,136-143), done as one batched set construction per tree size.
+// jobs: n_jobs records of L.n bytes, byte 0 = tree size m, byte t (3 <= t < m) = path[t].
+static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n_jobs) {
+	const Layout &L = S->L;
+	for (unsigned m = 3; m < S->n; ++m) {
+		std::vector<uint8_t> sel;
+		for (unsigned j = 0; j < n_jobs; ++j) {
+			if (jobs[(size_t) j * L.n] == m) sel.insert(sel.end(), jobs + (size_t) j * L.n, jobs + (size_t) (j + 1) * L.n);
+		}
+		unsigned k = (unsigned) (sel.size() / L.n);
+		size_t done = 0;
+		while (done < k) {
+			unsigned part = (unsigned) std::min<size_t>(k - done, 65536);
+			Pool &P = S->pool[m];
+			if (P.count + part > P.cap) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m, P.cap);
+			const unsigned E = 2 * m - 3, stride = (E + 15u) & ~15u;
+			std::vector<uint8_t> h((size_t) part * 4 * stride, 0xFF);
+			HostTopo t;
+			for (unsigned i = 0; i < part; ++i) {
+				const uint8_t *path = sel.data() + (done + i) * L.n;
+				if (!t.from_path(path, m)) return set_error(XMP_ERR_ARG, "job %u names an edge that does not exist", i);
+				uint8_t *row = h.data() + (size_t) i * 4 * stride;
+				memcpy(row, t.par, E);
+				memcpy(row + stride, t.kid[0], E);
+				memcpy(row + 2 * stride, t.kid[1], E);
+				t.preorder(row + 3 * stride);
+			}
+			int rc = S->topo.reserve(h.size());
+			if (rc) return rc;
+			rc = S->pathbuf.reserve((size_t) part * L.n);
+			if (rc) return rc;
+			XMP_CUDA(cudaMemcpyAsync(S->topo.ptr, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
+			XMP_CUDA(cudaMemcpyAsync(S->pathbuf.ptr, sel.data() + done * L.n, (size_t) part * L.n, cudaMemcpyHostToDevice, ctx->stream));
+			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, P.sets + P.count * P.rec, (size_t) P.rec, true, S->d_len);
+			if (rc) return rc;
+			k_write_headers<<<(part + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, P.count, part, (const uint8_t *) S->topo.ptr, stride,
+			                                                            (const uint8_t *) S->pathbuf.ptr, S->d_len);
+			XMP_CUDA(cudaGetLastError());
+			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+			S->st.launches += 2;
+			P.count += part;
+			done += part;
+		}
+	}
+	return XMP_OK;
+}
+
+static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long first, unsigned long long chunk, bool shard) {
+	const Layout &L = S->L;
+	Pool &P = S->pool[m];
+	const int last = (m + 1 == S->n);
+	const uint4 *row = ctx->d_rows + (size_t) m * L.W;
+	const unsigned rest = ctx->rest_bound[m];
+	const unsigned sc = shard ? S->prm.shard_count : 1u, si = shard ? S->prm.shard_index : 0u;
+	const unsigned long long pairs = chunk * P.E;
+	uint8_t *trees = S->d_trees[S->cur];   // slots are absolute: d_ntrees already counts the records present
+	const unsigned room = S->trees_cap;
+#define XMP_EXPAND(G)                                                                                                   \
+	k_expand_score<G><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
+	                                                                              S->d_bound, last, S->d_surv, S->d_nsurv, trees,   \
+	                                                                              S->d_ntrees, room, sc, si)
+	const unsigned W = L.W;
+	if (W > 16) XMP_EXPAND(32);
+	else if (W > 8) XMP_EXPAND(16);
+	else if (W > 4) XMP_EXPAND(8);
+	else if (W > 2) XMP_EXPAND(4);
+	else if (W > 1) XMP_EXPAND(2);
+	else XMP_EXPAND(1);
+#undef XMP_EXPAND
+	XMP_CUDA(cudaGetLastError());
+	S->st.launches += 1;
+	return XMP_OK;
+}
+
+static int launch_children(xmp_ctx *ctx, Search *S, unsigned m) {
+	Pool &P = S->pool[m], &C = S->pool[m + 1];
+	const unsigned blocks = (unsigned) ctx->sm_count * 8;
+	k_build_children<<<blocks, 128, 0, ctx->stream>>>(P.view(), C.view(), S->L, m, S->d_surv, S->d_nsurv, C.count, ctx->d_rows, S->d_merges);
+	XMP_CUDA(cudaGetLastError());
+	S->st.launches += 1;
+	return XMP_OK;
+}
+
+// Reads back n_surv, n_trees, bound and the merge counter (one small pinned copy, one sync).
+static int fetch_counters(xmp_ctx *ctx, Search *S) {
+	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 32, cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	S->bound = S->h_pin[0];
+	return XMP_OK;
+}
+
+// Moves every tree record off the device into host_trees.
+static int drain_trees(xmp_ctx *ctx, Search *S) {
+	if (S->ntrees_dev) {
+		const size_t bytes = (size_t) S->ntrees_dev * S->L.trec, old = S->host_trees.size();
+		S->host_trees.resize(old + bytes);
+		XMP_CUDA(cudaMemcpyAsync(S->host_trees.data() + old, S->d_trees[S->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+		// Drop what the current bound already rules out.
+		size_t w = 0;
+		for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
+			unsigned sc;
+			memcpy(&sc, S->host_trees.data() + r, 4);
+			if (sc <= S->bound) {
+				if (w != r) memmove(S->host_trees.data() + w, S->host_trees.data() + r, S->L.trec);
+				w += S->L.trec;
+			}
+		}
+		S->host_trees.resize(w);
+	}
+	S->ntrees_dev = 0;
+	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+	return XMP_OK;
+}
+
+// Keeps the device tree buffer at most half full: first by discarding records above the bound.
+static int tidy_trees(xmp_ctx *ctx, Search *S) {
+	if (S->ntrees_dev <= S->trees_cap / 4) return XMP_OK;
+	const int other = S->cur ^ 1;
+	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+	k_filter_trees<<<(S->ntrees_dev + 255) / 256, 256, 0, ctx->stream>>>(S->d_trees[S->cur], S->ntrees_dev, S->L.trec, S->d_bound,
+	                                                                   S->d_trees[other], S->d_ntrees);
+	XMP_CUDA(cudaGetLastError());
+	S->st.launches += 1;
+	S->cur = other;
+	int rc = fetch_counters(ctx, S);
+	if (rc) return rc;
+	S->ntrees_dev = S->h_pin[2];
+	if (S->ntrees_dev > S->trees_cap / 2) return drain_trees(ctx, S);
+	return XMP_OK;
+}
+
+// One frontier batch at level m.  keep_best > 0 (the dive) keeps only that many cheapest children.
+static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chunk, unsigned keep_best) {
+	Pool &P = S->pool[m];
+	const bool last = (m + 1 == S->n);
+	const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level && keep_best == 0;
+	const unsigned long long first = P.count - chunk;
+	if (!last) XMP_CUDA(cudaMemsetAsync(S->d_nsurv, 0, sizeof(unsigned), ctx->stream));
+	int rc = launch_expand(ctx, S, m, first, chunk, shard);
+	if (rc) return rc;
+	S->st.nodes += chunk;
+	S->st.score_calls += chunk * P.E;
+	S->st.iterations += 1;
+	if (last) {
+		rc = fetch_counters(ctx, S);
+		if (rc) return rc;
+		S->st.full_trees += S->h_pin[2] - S->ntrees_dev;
+		S->ntrees_dev = S->h_pin[2];
+		P.count -= chunk;
+		return tidy_trees(ctx, S);
+	}
+	if (keep_best) {
+		rc = fetch_counters(ctx, S);
+		if (rc) return rc;
+		unsigned ns = S->h_pin[1];
+		if (ns > keep_best) {
+			std::vector<uint4> h(ns);
+			XMP_CUDA(cudaMemcpyAsync(h.data(), S->d_surv, (size_t) ns * 16, cudaMemcpyDeviceToHost, ctx->stream));
+			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+			std::sort(h.begin(), h.end(), [](const uint4 &x, const uint4 &y) {
+				if (x.z != y.z) return x.z < y.z;
+				if (x.x != y.x) return x.x < y.x;
+				return x.y < y.y;
+			});
+			ns = keep_best;
+			XMP_CUDA(cudaMemcpyAsync(S->d_surv, h.data(), (size_t) ns * 16, cudaMemcpyHostToDevice, ctx->stream));
+			XMP_CUDA(cudaMemcpyAsync(S->d_nsurv, &ns, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+		}
+	}
+	rc = launch_children(ctx, S, m);
+	if (rc) return rc;
+	rc = fetch_counters(ctx, S);
+	if (rc) return rc;
+	const unsigned ns = S->h_pin[1];
+	S->pool[m + 1].count += ns;
+	S->st.children += ns;
+	P.count -= chunk;
+	return XMP_OK;
+}
+
+static int push_root(xmp_ctx *ctx, Search *S) {
+	std::vector<uint8_t> job(S->L.n, 0);
+	job[0] = 3;
+	return import_nodes(ctx, S, job.data(), 1);
+}
+
+// Greedy beam descent from the 3-taxon tree: the same role as the reference's greedy stepwise-addition
+// tree (src/greedytree.c:51-105) -- a quick complete tree whose length tightens the bound.  It changes
+// how many nodes the search visits, never its result.
+static int dive(xmp_ctx *ctx, Search *S) {
+	int rc = push_root(ctx, S);
+	if (rc) return rc;
+	for (unsigned m = 3; m < S->n; ++m) {
+		if (S->pool[m].count == 0) break;
+		rc = run_batch(ctx, S, m, S->pool[m].count, kBeam);
+		if (rc) return rc;
+	}
+	for (unsigned m = 3; m < S->n; ++m) S->pool[m].count = 0;
+	// Trees found by the dive will be found again by the search proper.
+	S->ntrees_dev = 0;
+	S->host_trees.clear();
+	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+	return fetch_counters(ctx, S);
+}
+
+}  // namespace xmp
+
+using namespace xmp;
+
+extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *params) {
+	if (!ctx || !ctx->d_rows || !params) return set_error(XMP_ERR_ARG, "no problem loaded");
+	if (ctx->num_taxa < 4) return set_error(XMP_ERR_ARG, "the search needs at least four taxa");
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	search_destroy(ctx);
+	Search *S = new Search();
+	ctx->search = S;
+	S->prm = *params;
+	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
+	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
+	S->n = ctx->num_taxa;
+	memset(&S->st, 0, sizeof S->st);
+	int rc = alloc_search(ctx, S);
+	if (rc) { search_destroy(ctx); return rc; }
+	S->bound = params->bound;
+	XMP_CUDA(cudaMemcpyAsync(S->d_bound, &S->bound, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+
+	// Where the frontier is dealt out to shards: the first tree size with >= 64 subtrees per shard.
+	S->split_level = 0;
+	if (S->prm.shard_count > 1) {
+		unsigned s = S->prm.split_level;
+		if (s == 0) {
+			s = 4;
+			while (s + 1 < S->n && odd_factorial(s) < 64.0 * S->prm.shard_count) ++s;
+		}
+		if (s < 4) s = 4;
+		if (s > S->n - 1) s = S->n - 1;
+		S->split_level = s;
+	}
+	XMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (!(S->prm.flags & XMP_SEARCH_NO_DIVE)) {
+		rc = dive(ctx, S);
+		if (rc) return rc;
+	}
+	rc = push_root(ctx, S);
+	if (rc) return rc;
+	XMP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+	XMP_CUDA(cudaEventSynchronize(ctx->ev1));
+	float ms = 0;
+	XMP_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	S->st.seconds += ms * 1e-3;
+	return XMP_OK;
+}
+
+extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done) {
+	if (!ctx || !ctx->search) return set_error(XMP_ERR_ARG, "xmp_cuda_search_begin has not been called");
+	Search *S = ctx->search;
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	XMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+	unsigned batches = 0;
+	int rc = XMP_OK;
+	while (!S->done && (max_batches == 0 || batches < max_batches)) {
+		// Deepest level holding a worthwhile batch; otherwise the deepest non-empty one.
+		int pick = -1, fallback = -1;
+		unsigned long long pick_chunk = 0, fallback_chunk = 0;
+		for (unsigned m = S->n - 1; m >= 3; --m) {
+			Pool &P = S->pool[m];
+			if (P.count == 0) continue;
+			unsigned long long room = (m + 1 == S->n) ? (S->trees_cap - S->ntrees_dev) / P.E
+			                                          : (S->pool[m + 1].cap - S->pool[m + 1].count) / P.E;
+			unsigned long long chunk = std::min(P.count, room);
+			if (chunk == 0) continue;
+			if (fallback < 0) { fallback = (int) m; fallback_chunk = chunk; }
+			if (chunk >= kMinBatchNodes) { pick = (int) m; pick_chunk = chunk; break; }
+		}
+		if (pick < 0) { pick = fallback; pick_chunk = fallback_chunk; }
+		if (pick < 0) {
+			bool any = false;
+			for (unsigned m = 3; m < S->n; ++m) any |= S->pool[m].count != 0;
+			if (any) {
+				// Only possible when the tree buffer is full: make room and retry.
+				rc = drain_trees(ctx, S);
+				if (rc) break;
+				continue;
+			}
+			S->done = true;
+			break;
+		}
+		rc = run_batch(ctx, S, (unsigned) pick, pick_chunk, 0);
+		if (rc) break;
+		++batches;
+	}
+	if (rc == XMP_OK && S->done && !S->finished) {
+		rc = drain_trees(ctx, S);
+		if (rc == XMP_OK) rc = fetch_counters(ctx, S);
+		if (rc == XMP_OK) S->finished = true;
+	}
+	cudaEventRecord(ctx->ev1, ctx->stream);
+	cudaEventSynchronize(ctx->ev1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+	S->st.seconds += ms * 1e-3;
+	if (done) *done = S->done ? 1 : 0;
+	return rc;
+}
+
+extern "C" int xmp_cuda_search_get_bound(xmp_ctx *ctx, unsigned *bound) {
+	if (!ctx || !ctx->search || !bound) return set_error(XMP_ERR_ARG, "no search in progress");
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	int rc = fetch_counters(ctx, ctx->search);
+	*bound = ctx->search->bound;
+	return rc;
+}
+
+extern "C" int xmp_cuda_search_set_bound(xmp_ctx *ctx, unsigned bound) {
+	if (!ctx || !ctx->search) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	k_lower_bound<<<1, 1, 0, ctx->stream>>>(S->d_bound, bound);
+	XMP_CUDA(cudaGetLastError());
+	return fetch_counters(ctx, S);   // trees above a bound lowered by a peer are dropped in xmp_cuda_search_result
+}
+
+extern "C" int xmp_cuda_search_pending(xmp_ctx *ctx, unsigned long long *per_level) {
+	if (!ctx || !ctx->search || !per_level) return set_error(XMP_ERR_ARG, "no search in progress");
+	for (unsigned m = 0; m <= XMP_MAX_TAXA; ++m) per_level[m] = ctx->search->pool[m].count;
+	return XMP_OK;
+}
+
+extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uint8_t *jobs, unsigned *n_jobs) {
+	if (!ctx || !ctx->search || !jobs || !n_jobs) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	const Layout &L = S->L;
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	*n_jobs = 0;
+	for (unsigned m = 3; m < S->n; ++m) {
+		Pool &P = S->pool[m];
+		if (P.count == 0) continue;
+		// Like the reference's thief (src/mpiworker.c:169-181): take from the shallowest open level.
+		unsigned k = (unsigned) std::min<unsigned long long>(P.count, max_nodes);
+		std::vector<uint8_t> h((size_t) k * L.HB);
+		XMP_CUDA(cudaMemcpyAsync(h.data(), P.hdr + (size_t) (P.count - k) * L.HB, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (unsigned i = 0; i < k; ++i) {
+			uint8_t *job = jobs + (size_t) i * L.n;
+			memcpy(job, h.data() + (size_t) i * L.HB + HDR_PATH, L.n);
+			job[0] = (uint8_t) m;
+			job[1] = job[2] = 0;
+		}
+		P.count -= k;
+		*n_jobs = k;
+		return XMP_OK;
+	}
+	return XMP_OK;
+}
+
+extern "C" int xmp_cuda_search_import_jobs(xmp_ctx *ctx, const uint8_t *jobs, unsigned n_jobs) {
+	if (!ctx || !ctx->search || (!jobs && n_jobs)) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	if (n_jobs == 0) return XMP_OK;
+	if (S->finished) return set_error(XMP_ERR_ARG, "the search has already been finalised");
+	for (unsigned j = 0; j < n_jobs; ++j) {
+		unsigned m = jobs[(size_t) j * S->L.n];
+		if (m < 3 || m >= S->n) return set_error(XMP_ERR_ARG, "job %u has tree size %u, expected 3..%u", j, m, S->n - 1);
+	}
+	S->done = false;
+	return import_nodes(ctx, S, jobs, n_jobs);
+}
+
+extern "C" int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned long long *n_trees, uint8_t *paths, size_t cap) {
+	if (!ctx || !ctx->search) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	if (!S->finished) return set_error(XMP_ERR_ARG, "the search has not finished");
+	// Filter here, not when the frontier ran dry: a peer shard may have lowered the bound since.
+	const Layout &L = S->L;
+	unsigned long long count = 0;
+	for (size_t r = 0; r < S->host_trees.size(); r += L.trec) {
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		if (sc != S->bound) continue;
+		if (paths && count < cap) memcpy(paths + (size_t) count * L.n, S->host_trees.data() + r + 4, L.n);
+		++count;
+	}
+	if (score) *score = S->bound;
+	if (n_trees) *n_trees = count;
+	return XMP_OK;
+}
+
+extern "C" int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out) {
+	if (!ctx || !ctx->search || !out) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	unsigned long long merges = 0;
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	XMP_CUDA(cudaMemcpyAsync(&merges, S->d_merges, sizeof merges, cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	*out = S->st;
+	out->site_merges = (S->st.score_calls + merges) * ctx->real_sites;
+	return XMP_OK;
+}

@@ -1,0 +1,281 @@
+"""ctypes mirror of include/xmp_cuda.h (libxmp_b200.so, hand-written sm_100a CUDA behind a C ABI).
+
+There is no fallback of any kind here: if the library is not built, or there is no B200-class device,
+every entry point raises.  Device buffers may be torch CUDA tensors (their ``data_ptr()`` is passed
+through) -- torch is plumbing for memory and streams, the kernels are ours.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxmp_b200.so")
+_LIB = None
+NO_LIMIT = 0x7FFFFFFF
+SEARCH_NO_DIVE = 1
+
+EXPORTS = [
+    "xmp_cuda_last_error", "xmp_cuda_device_count", "xmp_cuda_init", "xmp_cuda_destroy", "xmp_cuda_set_stream",
+    "xmp_cuda_synchronize",
+    "FitchBases_b2_w16_cuda", "FitchBasesAndCompare_b2_w16_cuda", "FitchScoreWeight1_b2_w16_cuda",
+    "FitchScoreWeight1_stopearly_b2_w16_cuda", "FitchScore_b2_w16_cuda", "FitchScore_stopearly_b2_w16_cuda",
+    "FitchScore_fw1_b2_w16_cuda", "FitchScore_fw1_stopearly_b2_w16_cuda",
+    "xmp_cuda_load", "xmp_cuda_load_device_rows", "xmp_cuda_build_midpoints", "xmp_cuda_score_batch",
+    "xmp_cuda_score_insertions_host",
+    "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
+    "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
+    "xmp_cuda_search_result", "xmp_cuda_search_stats",
+]
+
+
+class XmpCudaError(RuntimeError):
+    pass
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("bound", C.c_uint), ("max_trees", C.c_uint), ("mem_budget", C.c_size_t),
+                ("shard_index", C.c_uint), ("shard_count", C.c_uint), ("split_level", C.c_uint), ("flags", C.c_uint)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("nodes", C.c_ulonglong), ("score_calls", C.c_ulonglong), ("children", C.c_ulonglong),
+                ("full_trees", C.c_ulonglong), ("site_merges", C.c_ulonglong), ("launches", C.c_ulonglong),
+                ("iterations", C.c_ulonglong), ("seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib():
+    """Loads libxmp_b200.so.  Raises if it has not been built -- never substitutes anything else."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise XmpCudaError("xmp_b200/libxmp_b200.so is missing: run `make cuda` (or __graft_entry__.build()). "
+                               "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.xmp_cuda_last_error.restype = C.c_char_p
+        vp, u, sz = C.c_void_p, C.c_uint, C.c_size_t
+        L.xmp_cuda_init.argtypes = [C.c_int, C.POINTER(vp)]
+        L.xmp_cuda_destroy.argtypes = [vp]
+        L.xmp_cuda_destroy.restype = None
+        L.xmp_cuda_set_stream.argtypes = [vp, vp]
+        L.xmp_cuda_synchronize.argtypes = [vp]
+        L.xmp_cuda_load.argtypes = [vp, vp, vp, u, u, vp, u]
+        L.xmp_cuda_load_device_rows.argtypes = [vp, vp, vp, u, u, vp, u]
+        L.xmp_cuda_build_midpoints.argtypes = [vp, vp, sz, u, u, vp, vp]
+        L.xmp_cuda_score_batch.argtypes = [vp, vp, sz, u, u, vp, u, vp, vp, vp]
+        L.xmp_cuda_score_insertions_host.argtypes = [vp, vp, sz, u, u, vp]
+        L.xmp_cuda_search_begin.argtypes = [vp, C.POINTER(SearchParams)]
+        L.xmp_cuda_search_run.argtypes = [vp, u, C.POINTER(C.c_int)]
+        L.xmp_cuda_search_get_bound.argtypes = [vp, C.POINTER(u)]
+        L.xmp_cuda_search_set_bound.argtypes = [vp, u]
+        L.xmp_cuda_search_pending.argtypes = [vp, vp]
+        L.xmp_cuda_search_export_jobs.argtypes = [vp, u, vp, C.POINTER(u)]
+        L.xmp_cuda_search_import_jobs.argtypes = [vp, vp, u]
+        L.xmp_cuda_search_result.argtypes = [vp, C.POINTER(u), C.POINTER(C.c_ulonglong), vp, sz]
+        L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
+        for name in ("FitchBases_b2_w16_cuda",):
+            getattr(L, name).restype = None
+        L.FitchBases_b2_w16_cuda.argtypes = [vp, vp, vp, u]
+        L.FitchBasesAndCompare_b2_w16_cuda.argtypes = [vp, vp, vp, vp, u]
+        L.FitchScoreWeight1_b2_w16_cuda.argtypes = [vp, vp, u]
+        L.FitchScoreWeight1_stopearly_b2_w16_cuda.argtypes = [vp, vp, u, u]
+        L.FitchScore_b2_w16_cuda.argtypes = [vp, vp, vp, u]
+        L.FitchScore_stopearly_b2_w16_cuda.argtypes = [vp, vp, vp, u, u]
+        L.FitchScore_fw1_b2_w16_cuda.argtypes = [vp, vp, vp, u]
+        L.FitchScore_fw1_stopearly_b2_w16_cuda.argtypes = [vp, vp, vp, u, u]
+        for name in EXPORTS[7:14]:
+            getattr(L, name).restype = C.c_uint
+        _LIB = L
+    return _LIB
+
+
+def _ptr(x):
+    """Device or host address of a torch tensor / numpy array / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+def _check(rc):
+    if rc != 0:
+        raise XmpCudaError("libxmp_b200 error %d: %s" % (rc, lib().xmp_cuda_last_error().decode()))
+
+
+class Context:
+    """One device context (reference analogue: the global TreeData of a process, src/common.c:42)."""
+
+    def __init__(self, device=0, stream=None):
+        L = lib()
+        h = C.c_void_p()
+        _check(L.xmp_cuda_init(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.num_taxa = self.n_blocks = 0
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().xmp_cuda_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, stream):
+        """stream: a raw cudaStream_t value (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        _check(lib().xmp_cuda_set_stream(self._h, stream))
+
+    def synchronize(self):
+        _check(lib().xmp_cuda_synchronize(self._h))
+
+    # ---- problem ----
+    def load(self, rows, weights=None, rest_bound=None, constant_weight=0):
+        """rows: host uint8 [num_taxa][n_blocks*16] (numpy), or a torch CUDA uint8 tensor of that shape."""
+        num_taxa, nbytes = rows.shape
+        assert nbytes % 16 == 0
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.uint32)
+        rb = None if rest_bound is None else np.ascontiguousarray(rest_bound, dtype=np.uint32)
+        if isinstance(rows, np.ndarray):
+            rows = np.ascontiguousarray(rows, dtype=np.uint8)
+            _check(lib().xmp_cuda_load(self._h, _ptr(rows), _ptr(w), num_taxa, nbytes // 16, _ptr(rb), constant_weight))
+        else:
+            assert rows.is_cuda and rows.is_contiguous()
+            self._rows_keepalive = rows
+            _check(lib().xmp_cuda_load_device_rows(self._h, _ptr(rows), _ptr(w), num_taxa, nbytes // 16, _ptr(rb), constant_weight))
+        self.num_taxa, self.n_blocks = num_taxa, nbytes // 16
+
+    def load_problem(self, problem):
+        self.load(problem.rows, problem.weights, problem.rest_bound, problem.constant_weight)
+
+    # ---- batched scoring ----
+    def build_midpoints(self, paths, m, d_mid, d_tree_len=None):
+        paths = np.ascontiguousarray(paths, dtype=np.uint8)
+        _check(lib().xmp_cuda_build_midpoints(self._h, _ptr(paths), paths.shape[1], paths.shape[0], m, _ptr(d_mid), _ptr(d_tree_len)))
+
+    def score_batch(self, d_sets, n_pairs, pairs_per_tree, taxon, d_cost, d_base_score=None, bound=NO_LIMIT,
+                    d_survivors=None, d_n_survivors=None):
+        _check(lib().xmp_cuda_score_batch(self._h, _ptr(d_sets), n_pairs, pairs_per_tree, taxon, _ptr(d_base_score), bound,
+                                          _ptr(d_cost), _ptr(d_survivors), _ptr(d_n_survivors)))
+
+    def score_insertions_host(self, paths, m, out=None):
+        paths = np.ascontiguousarray(paths, dtype=np.uint8)
+        n = paths.shape[0]
+        if out is None:
+            out = np.empty((n, 2 * m - 3), dtype=np.uint32)
+        _check(lib().xmp_cuda_score_insertions_host(self._h, _ptr(paths), paths.shape[1], n, m, _ptr(out)))
+        return out
+
+    # ---- search ----
+    def search_begin(self, bound=NO_LIMIT, max_trees=NO_LIMIT, mem_budget=0, shard_index=0, shard_count=1,
+                     split_level=0, flags=0):
+        p = SearchParams(bound, max_trees, mem_budget, shard_index, shard_count, split_level, flags)
+        _check(lib().xmp_cuda_search_begin(self._h, C.byref(p)))
+
+    def search_run(self, max_batches=0):
+        done = C.c_int(0)
+        _check(lib().xmp_cuda_search_run(self._h, max_batches, C.byref(done)))
+        return bool(done.value)
+
+    def search_get_bound(self):
+        b = C.c_uint(0)
+        _check(lib().xmp_cuda_search_get_bound(self._h, C.byref(b)))
+        return b.value
+
+    def search_set_bound(self, bound):
+        _check(lib().xmp_cuda_search_set_bound(self._h, int(bound)))
+
+    def search_pending(self):
+        a = np.zeros(101, dtype=np.uint64)
+        _check(lib().xmp_cuda_search_pending(self._h, _ptr(a)))
+        return a
+
+    def search_export_jobs(self, max_nodes):
+        jobs = np.zeros((max_nodes, self.num_taxa), dtype=np.uint8)
+        n = C.c_uint(0)
+        _check(lib().xmp_cuda_search_export_jobs(self._h, max_nodes, _ptr(jobs), C.byref(n)))
+        return jobs[:n.value].copy()
+
+    def search_import_jobs(self, jobs):
+        jobs = np.ascontiguousarray(jobs, dtype=np.uint8)
+        if len(jobs):
+            _check(lib().xmp_cuda_search_import_jobs(self._h, _ptr(jobs), len(jobs)))
+
+    def search_result(self):
+        """(optimal length, number of optimal trees, their insertion paths [n_trees][num_taxa])."""
+        score, n = C.c_uint(0), C.c_ulonglong(0)
+        _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), None, 0))
+        paths = np.zeros((n.value, self.num_taxa), dtype=np.uint8)
+        if n.value:
+            _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), _ptr(paths), n.value))
+        return score.value, n.value, paths
+
+    def search_stats(self):
+        st = SearchStats()
+        _check(lib().xmp_cuda_search_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+
+def search(problem, device=0, bound=None, **kw):
+    """Whole exact search of a prepared host problem on one GPU.  Returns (score, n_trees, paths, stats)."""
+    ctx = Context(device)
+    try:
+        ctx.load_problem(problem)
+        ctx.search_begin(bound=problem.bound if bound is None else bound, **kw)
+        while not ctx.search_run(0):
+            pass
+        score, n, paths = ctx.search_result()
+        return score, n, paths, ctx.search_stats()
+    finally:
+        ctx.close()
+
+
+# ---- the per-pair family, numpy in / numpy out (parity tests) ----
+def _pair_args(*arrays):
+    out = []
+    for a in arrays:
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        assert a.size % 16 == 0
+        out.append(a)
+    return out
+
+
+def fitch_bases(s1, s2):
+    s1, s2 = _pair_args(s1, s2)
+    dest = np.empty_like(s1)
+    lib().FitchBases_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(dest), s1.size // 16)
+    return dest
+
+
+def fitch_bases_and_compare(s1, s2, prev):
+    s1, s2, prev = _pair_args(s1, s2, prev)
+    dest = np.empty_like(s1)
+    ch = lib().FitchBasesAndCompare_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(dest), _ptr(prev), s1.size // 16)
+    return dest, int(ch)
+
+
+def fitch_score_weight1(s1, s2, max_score=None):
+    s1, s2 = _pair_args(s1, s2)
+    if max_score is None:
+        return int(lib().FitchScoreWeight1_b2_w16_cuda(_ptr(s1), _ptr(s2), s1.size // 16))
+    return int(lib().FitchScoreWeight1_stopearly_b2_w16_cuda(_ptr(s1), _ptr(s2), s1.size // 16, max_score))
+
+
+def fitch_score(s1, s2, weights, fw1=False, max_score=None):
+    s1, s2 = _pair_args(s1, s2)
+    w = np.ascontiguousarray(weights, dtype=np.uint32)
+    assert w.size == s1.size * 2
+    L, n = lib(), s1.size // 16
+    if fw1:
+        if max_score is None:
+            return int(L.FitchScore_fw1_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(w), n))
+        return int(L.FitchScore_fw1_stopearly_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(w), n, max_score))
+    if max_score is None:
+        return int(L.FitchScore_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(w), n))
+    return int(L.FitchScore_stopearly_b2_w16_cuda(_ptr(s1), _ptr(s2), _ptr(w), n, max_score))
