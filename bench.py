@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json config 2: batched Fitch insertion scoring, all edges of 4096 partial trees
+on a synthetic random 4-state alignment of 64 taxa x 2^20 sites, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over the whole batch: taxon m is scored against every edge
+MIDPOINT set of every partial tree (53,248 (tree, edge) pairs of 2^20 sites on each GPU), pruned against
+the bound and the survivors ballot-compacted.  All weights are 1, so the kernel under test is the
+weight-1 scorer (reference FitchScoreWeight1, src/fitchtemplate_b2_w8_fastc64.inc:43-80).
+
+  value     Gsite-merges/s, whole job (all ranks), MIDPOINT arrays resident in HBM (26 GiB per GPU, far
+            larger than the 126 MB L2, so every step streams from HBM)
+  e2e       the same count of insertion-scoring site-merges through the host-buffer C ABI
+            (xmp_cuda_load + xmp_cuda_score_insertions_host): alignment and topologies come from
+            pinned host memory every step, state sets are built on the device, costs are read back
+  roofline  algorithmic bytes (0.5 B per site-merge) / step time, against the measured HBM copy peak
+  cpu_baseline / --impl reference
+            the reference's own fastc64 Fitch code (oracle/_ref, compiled from its sources; the
+            oracle port if that is absent) doing the same host-inputs-to-costs work on the host cores
+
+N > 1 (torchrun, one rank per GPU): trees are independent, so every rank scores its own 4096 trees
+(weak scaling, no data-path collective); time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_TAXA = 64
+NUM_SITES = 1 << 20
+N_TREES = 4096
+M = 8                      # taxa on every partial tree; taxon M is the one inserted
+METRIC = "fitch_insertion_scoring_site_merges_per_s"
+UNIT = "Gsite-merges/s"
+
+
+def make_rows(torch, device, seed=1):
+    """64 x 2^20 i.i.d. uniform single-state sites, packed two per byte (even site = low nibble)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    states = torch.randint(0, 4, (NUM_TAXA, NUM_SITES), generator=g, device=device, dtype=torch.uint8)
+    nib = torch.bitwise_left_shift(torch.ones_like(states), states)
+    return (nib[:, 0::2] | (nib[:, 1::2] << 4)).contiguous()
+
+
+def make_paths(n_trees, m, seed=2):
+    """Random stepwise-addition topologies on taxa 0..m-1 as insertion paths."""
+    rng = np.random.default_rng(seed)
+    paths = np.zeros((n_trees, NUM_TAXA), dtype=np.uint8)
+    for t in range(3, m):
+        paths[:, t] = rng.integers(0, 2 * t - 3, n_trees)
+    return paths
+
+
+def make_workload(torch, n_trees=N_TREES, m=M, device="cuda", seed_offset=0):
+    d_rows = make_rows(torch, device, 1)
+    paths = make_paths(n_trees, m, 2 + seed_offset)
+    n_blocks = d_rows.shape[1] // 16
+    E = 2 * m - 3
+    d_mid = torch.empty((n_trees * E, n_blocks * 16), dtype=torch.uint8, device=device)
+    return {"d_rows": d_rows, "paths": paths, "m": m, "E": E, "n_blocks": n_blocks, "d_mid": d_mid,
+            "n_pairs": n_trees * E, "n_trees": n_trees}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 5 ms through NVML while the timed region
+    runs (nvidia-smi's own loop is too coarse for a region of ~100 ms)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        import threading
+        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.005)
+
+    def stop(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self._stop.set()
+        self.t.join()
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------------------- CPU reference legs
+def cpu_cost_of_trees(paths, rows, m, threads, seconds_budget):
+    """The reference's own Fitch code turning host inputs (alignment, topologies) into insertion costs:
+    for each tree build every MIDPOINT set (FitchBases) and score taxon m on every edge
+    (FitchScoreWeight1).  Returns (trees done, seconds, kind, score-only seconds for the same trees)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests import oracle_lib as ol
+    nbytes = rows.shape[1]
+    if ol.have_ref():
+        R = ol.ref()
+        kind = "reference"
+
+        def bases(a, b, d):
+            R.FitchBases_b2_w8_fastc64(a, b, d, nbytes // 8)
+
+        def score1(a, b):
+            return R.FitchScoreWeight1_b2_w8_fastc64(a, b, nbytes // 8)
+    else:
+        O = ol.oracle()
+        kind = "port"
+
+        def bases(a, b, d):
+            O.xo_fitch_bases_swar64(a, b, d, nbytes // 8)
+
+        def score1(a, b):
+            return O.xo_fitch_score_weight1_swar64(a, b, nbytes // 8)
+
+    E = 2 * m - 3
+    rowp = [rows[t].ctypes.data for t in range(rows.shape[0])]
+
+    def topo(path):
+        par, kid = {0: 2, 1: 2, 2: None}, {2: (0, 1)}
+        top = 2
+        for t in range(3, m):
+            v, a, b = int(path[t]), 2 * t - 3, 2 * t - 2
+            pv = par[v]
+            par[b] = pv
+            if pv is None:
+                top = b
+            else:
+                kid[pv] = tuple(b if k == v else k for k in kid[pv])
+            kid[b] = (a, v)
+            par[a] = par[v] = b
+        pre, stack = [], [top]
+        while stack:
+            e = stack.pop()
+            pre.append(e)
+            if e in kid:
+                stack.extend((kid[e][1], kid[e][0]))
+        return par, kid, pre
+
+    score_only = [0.0] * threads
+
+    def one(args):
+        slot, path = args
+        buf = one.bufs[slot]
+        up, down, mid = buf[0], buf[1], buf[2]
+        par, kid, pre = topo(path)
+        upp = {}
+        for e in reversed(pre):
+            if e in kid:
+                bases(upp[kid[e][0]], upp[kid[e][1]], up[e].ctypes.data)
+                upp[e] = up[e].ctypes.data
+            else:
+                upp[e] = rowp[(e + 3) // 2]
+        dn = {}
+        for e in pre:
+            p = par[e]
+            if p is None:
+                dn[e] = rowp[0]
+            else:
+                sib = kid[p][1] if kid[p][0] == e else kid[p][0]
+                bases(dn[p], upp[sib], down[e].ctypes.data)
+                dn[e] = down[e].ctypes.data
+            bases(upp[e], dn[e], mid[e].ctypes.data)
+        t0 = time.perf_counter()
+        costs = [score1(mid[e].ctypes.data, rowp[m]) for e in range(E)]
+        score_only[slot] += time.perf_counter() - t0
+        return costs
+
+    one.bufs = [np.zeros((3, E, nbytes), np.uint8) for _ in range(threads)]
+    done, t_start = 0, time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        # waves of `threads` trees, one scratch slot per worker
+        while done < len(paths) and time.perf_counter() - t_start < seconds_budget:
+            wave = [(i, paths[done + i]) for i in range(min(threads, len(paths) - done))]
+            list(ex.map(one, wave))
+            done += len(wave)
+    return done, time.perf_counter() - t_start, kind, max(score_only)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch  # only for the same seeded alignment
+    rows = make_rows(torch, "cpu", 1).numpy()
+    paths = make_paths(N_TREES, M, 2)
+    threads = os.cpu_count() or 1
+    E = 2 * M - 3
+    per_tree = E * NUM_SITES
+    budget = 8.0
+    vals, tot_trees, tot_s = [], 0, 0.0
+    for step in range(args.warmup + args.steps):
+        done, secs, kind, _ = cpu_cost_of_trees(paths, rows, M, threads, budget)
+        if step >= args.warmup:
+            vals.append(done * per_tree / secs / 1e9)
+            tot_trees += done
+            tot_s += secs
+    value = tot_trees * per_tree / tot_s / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "64 taxa x 2^20 sites, insertion scoring of all 13 edges of partial trees on 8 taxa; "
+                               "host inputs (alignment + topologies) to costs on the host cores", "trees_per_step": tot_trees // max(args.steps, 1),
+                   "taxa": NUM_TAXA, "sites": NUM_SITES, "m": M},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d of %d trees per step (time-boxed to %.0f s), build MIDPOINT sets + score, %d threads" % (tot_trees // max(args.steps, 1), N_TREES, budget, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import xmp_b200.cuda as xc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: xmp_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    n_trees = args.trees
+    wl = make_workload(torch, n_trees, M, dev, seed_offset=rank)
+    # Launch on a torch side stream so that torch.cuda.Event brackets exactly our kernels (the default
+    # stream's handle is 0, which the C ABI reads as "use the context's own stream").
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    ctx = xc.Context(local, stream=side.cuda_stream)
+    ctx.load(wl["d_rows"])
+    ctx.build_midpoints(wl["paths"], M, wl["d_mid"])
+    n_pairs, E = wl["n_pairs"], wl["E"]
+    d_cost = torch.zeros(n_pairs, dtype=torch.int32, device=dev)
+    d_surv = torch.zeros(n_pairs, dtype=torch.int32, device=dev)
+    d_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    # bound: the median insertion cost, so that about half of the pairs survive the pruning
+    ctx.score_batch(wl["d_mid"], n_pairs, E, M, d_cost)
+    ctx.synchronize()
+    bound = int(d_cost.float().median().item())
+
+    def step():
+        ctx.score_batch(wl["d_mid"], n_pairs, E, M, d_cost, None, bound, d_surv, d_n)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    ms_steps = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    ms_total = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.stop() if sampler else None
+    checksum = int(d_cost.to(torch.int64).sum().item())
+    survivors = int(d_n.item())
+
+    if args.kernel_only:
+        print(json.dumps({"kernel_only": True, "ms_per_step": ms_total / args.steps, "ms_steps": ms_steps, "checksum": checksum}))
+        return
+    # ---- end to end through the host-buffer C ABI, same trees
+    rows_pinned = wl["d_rows"].cpu().pin_memory()
+    rows_np = rows_pinned.numpy()
+    e2e_trees = n_trees
+    cost_host = np.zeros((e2e_trees, E), dtype=np.uint32)
+    ctx2 = xc.Context(local)
+    h2d = rows_np.nbytes + wl["paths"].nbytes
+    d2h = cost_host.nbytes
+
+    def e2e_step():
+        ctx2.load(rows_np)
+        ctx2.score_insertions_host(wl["paths"][:e2e_trees], M, cost_host)
+
+    del wl["d_mid"]
+    torch.cuda.empty_cache()
+    e2e_step()
+    barrier()
+    e2e_reps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_reps
+    assert int(cost_host.astype(np.int64).sum()) == checksum, "end-to-end costs differ from the resident-input costs"
+    ctx2.close()
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    merges_per_step = n_pairs * NUM_SITES * world
+    value = merges_per_step * args.steps / (ms_total * 1e-3) / 1e9
+    e2e_value = e2e_trees * E * NUM_SITES * world / (e2e_ms * 1e-3) / 1e9
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ms_kernel = statistics.median(ms_steps)
+    achieved = n_pairs * NUM_SITES * 0.5 / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_score_wide_dram_bytes_per_launch")
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": "synthetic 64 taxa x 2^20 sites (i.i.d. uniform over 4 states, seed 1), all weights 1; taxon 8 scored against "
+                               "all 13 edges of %d random partial trees on 8 taxa per GPU (%d pairs, %.1f GiB of MIDPOINT state per GPU)" % (n_trees, n_pairs, n_pairs * NUM_SITES / 2 / 2**30),
+                   "trees_per_gpu": n_trees, "taxa": NUM_TAXA, "sites": NUM_SITES, "m": M, "pairs_per_gpu": n_pairs,
+                   "cache": "inputs larger than L2 (%.1f GiB per step vs 126 MB), no flush needed" % (n_pairs * NUM_SITES / 2 / 2**30),
+                   "bound": bound, "survivors_last_step": survivors, "cost_checksum": checksum},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "what": "xmp_cuda_load(alignment from pinned host memory) + xmp_cuda_score_insertions_host(topologies) -> costs in host memory; "
+                        "state sets are built on the device inside the timed region; counts insertion-scoring site-merges only"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "k_score_wide<8>", "algorithmic_bytes_per_launch": n_pairs * NUM_SITES // 2,
+                     "launch_ms": ms_kernel, "peak_source": peak_src,
+                     "note": "launch_ms is the median CUDA-event time of one step = k_score_wide + k_prune + two 4-byte/213-KB memsets; "
+                             "the ncu launch list under profiles/ gives k_score_wide's share"},
+    }
+    if world == 1:
+        rows = rows_np
+        threads = os.cpu_count() or 1
+        done, secs, kind, score_s = cpu_cost_of_trees(wl["paths"], rows, M, threads, 12.0)
+        out["cpu_baseline"] = {"value": done * E * NUM_SITES / secs / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": "%d of %d trees, host inputs to costs (build MIDPOINT sets with FitchBases, then FitchScoreWeight1), "
+                                         "time-boxed to 12 s" % (done, n_trees),
+                               "score_only_value": done * E * NUM_SITES / max(score_s, 1e-9) / 1e9}
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trees", type=int, default=N_TREES, help="partial trees per GPU (default: the BASELINE workload)")
+    ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip the end-to-end and CPU legs")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,10 @@ static void forest_init(forest *f, const uint8_t *rows, size_t nbytes, unsigned 
 	f->setmem = (uint8_t *) aligned_alloc(64, ((2 * (size_t) max_taxa * 3 * nbytes + 64) + 63) / 64 * 64);
 	f->used = 0;
 	f->skip_cost = 0;
+	if (!f->pool || !f->setmem) {
+		fprintf(stderr, "oracle: out of memory allocating %zu bytes of state sets\n", 2 * (size_t) max_taxa * 3 * nbytes);
+		abort();
+	}
 }
 
 static void forest_free(forest *f) {
@@ -174,7 +178,8 @@ typedef struct {
 	forest f;
 	xnode *root;
 	unsigned bound, score;
-	size_t cap;
+	size_t cap, pcap;
+	uint8_t cur_path[256];
 	uint8_t **level_mid;      /* per tree size: MIDPOINT of every edge in pre-order */
 	xnode ***level_edge;      /* per tree size: the node below every edge in pre-order */
 } search;
@@ -206,6 +211,13 @@ static void print_sub(search *s, const xnode *n) {
 static void record_tree(search *s) {
 	xo_result *r = s->r;
 	if (r->num_trees < s->p->max_trees) {
+		const unsigned n = s->p->num_taxa;
+		if (r->paths_len + n > s->pcap) {
+			s->pcap = (r->paths_len + n) * 2 + 4096;
+			r->paths = (uint8_t *) realloc(r->paths, s->pcap);
+		}
+		memcpy(r->paths + r->paths_len, s->cur_path, n);
+		r->paths_len += n;
 		char buf[16];
 		emit(s, "(", 1);
 		emit(s, buf, (size_t) sprintf(buf, "%u", s->p->taxon_map[0] + 1));
@@ -242,12 +254,14 @@ static void branch_and_bound(search *s, unsigned m) {
 		++s->r->score_calls;
 		s->score += (unsigned) inc;
 		if (inc <= allowable) {
+			s->cur_path[m] = (uint8_t) edges[e]->edge;
 			xnode *in = insert_above(&s->f, edges[e], (int) m);
 			if (m + 1 == p->num_taxa) {
 				if (s->score < s->bound) {
 					s->bound = s->score;
 					s->r->num_trees = 0;
 					s->r->newick_len = 0;
+					s->r->paths_len = 0;
 				}
 				record_tree(s);
 			} else {
@@ -259,29 +273,35 @@ static void branch_and_bound(search *s, unsigned m) {
 	}
 }
 
-int xo_search(const xo_problem *p, xo_result *r) {
+int xo_search_subtree(const xo_problem *p, const uint8_t *path, unsigned m, xo_result *r) {
 	search s;
 	memset(&s, 0, sizeof s);
 	memset(r, 0, sizeof *r);
-	if (p->num_taxa < 4) return -1;
+	if (p->num_taxa < 4 || p->num_taxa > 128 || m < 3 || m >= p->num_taxa) return -1;
 	s.p = p;
 	s.r = r;
 	forest_init(&s.f, p->char_mat, p->nbytes, p->num_taxa);
 	s.root = base_tree(&s.f);
+	for (unsigned t = 3; t < m; ++t) {
+		xnode *v = find_edge(s.root->kid[0], path[t]);
+		if (!v) { forest_free(&s.f); return -1; }
+		insert_above(&s.f, v, (int) t);
+		s.cur_path[t] = path[t];
+	}
 	s.level_mid = (uint8_t **) calloc(p->num_taxa + 1, sizeof(uint8_t *));
 	s.level_edge = (xnode ***) calloc(p->num_taxa + 1, sizeof(xnode **));
-	for (unsigned m = 3; m < p->num_taxa; ++m) {
-		s.level_mid[m] = (uint8_t *) malloc((size_t) (2 * m - 3) * p->nbytes);
-		s.level_edge[m] = (xnode **) malloc((size_t) (2 * m - 3) * sizeof(xnode *));
+	for (unsigned k = m; k < p->num_taxa; ++k) {
+		s.level_mid[k] = (uint8_t *) malloc((size_t) (2 * k - 3) * p->nbytes);
+		s.level_edge[k] = (xnode **) malloc((size_t) (2 * k - 3) * sizeof(xnode *));
 	}
 	s.bound = p->bound;
 	s.score = recompute(&s.f, s.root, p->weights) + p->constant_weight;
 	s.f.skip_cost = 1;
-	branch_and_bound(&s, 3);
+	branch_and_bound(&s, m);
 	r->score = s.bound;
-	for (unsigned m = 3; m < p->num_taxa; ++m) {
-		free(s.level_mid[m]);
-		free(s.level_edge[m]);
+	for (unsigned k = m; k < p->num_taxa; ++k) {
+		free(s.level_mid[k]);
+		free(s.level_edge[k]);
 	}
 	free(s.level_mid);
 	free(s.level_edge);
@@ -289,8 +309,14 @@ int xo_search(const xo_problem *p, xo_result *r) {
 	return 0;
 }
 
+int xo_search(const xo_problem *p, xo_result *r) {
+	return xo_search_subtree(p, NULL, 3, r);
+}
+
 void xo_result_free(xo_result *r) {
 	free(r->newick);
+	free(r->paths);
 	r->newick = NULL;
-	r->newick_len = 0;
+	r->paths = NULL;
+	r->newick_len = r->paths_len = 0;
 }

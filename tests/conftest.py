@@ -44,3 +44,12 @@ def golden_trees(name):
 
 def golden_output(name):
     return gzip.open(os.path.join(GOLDEN, "trees", name + ".out.gz")).read()
+
+
+@pytest.fixture(autouse=True)
+def _rss_report(request):
+    """With XMP_TEST_RSS=1 prints the resident set size after every test (debugging aid)."""
+    yield
+    if os.environ.get("XMP_TEST_RSS"):
+        import resource
+        print("\n[rss] %s: %d MiB" % (request.node.name, resource.getrusage(resource.RUSAGE_SELF).ru_maxrss // 1024), flush=True)

@@ -21,7 +21,8 @@ class XoProblem(C.Structure):
 
 class XoResult(C.Structure):
     _fields_ = [("score", C.c_uint), ("num_trees", C.c_ulonglong), ("nodes", C.c_ulonglong),
-                ("score_calls", C.c_ulonglong), ("newick", C.c_void_p), ("newick_len", C.c_size_t)]
+                ("score_calls", C.c_ulonglong), ("newick", C.c_void_p), ("newick_len", C.c_size_t),
+                ("paths", C.c_void_p), ("paths_len", C.c_size_t)]
 
 
 def oracle():
@@ -42,6 +43,7 @@ def oracle():
         L.xo_fitch_score_swar64.argtypes = [vp, vp, vp, sz]
         L.xo_tree_sets.argtypes = [vp, sz, vp, u, vp, vp, vp, vp]
         L.xo_search.argtypes = [C.POINTER(XoProblem), C.POINTER(XoResult)]
+        L.xo_search_subtree.argtypes = [C.POINTER(XoProblem), vp, u, C.POINTER(XoResult)]
         L.xo_result_free.argtypes = [C.POINTER(XoResult)]
         for f in ("xo_fitch_bases_and_compare", "xo_fitch_score_weight1", "xo_fitch_score", "xo_fitch_score_stopearly",
                   "xo_fitch_score_weight1_stopearly", "xo_fitch_score_weight1_swar64", "xo_fitch_score_swar64", "xo_tree_sets"):
@@ -114,20 +116,39 @@ def tree_sets(rows, m, path, weights=None):
     return mid, up, down, int(length)
 
 
+def _problem(problem, bound, max_trees):
+    keep = (np.ascontiguousarray(problem.rows, dtype=np.uint8), np.ascontiguousarray(problem.weights, dtype=np.uint32),
+            np.ascontiguousarray(problem.rest_bound, dtype=np.uint32), np.ascontiguousarray(problem.taxon_map, dtype=np.uint32))
+    rows, w, rb, tm = keep
+    pr = XoProblem(problem.num_taxa, rows.shape[1], p(rows), p(w), p(rb), p(tm), problem.constant_weight,
+                   problem.bound if bound is None else bound, max_trees)
+    return pr, keep
+
+
 def search(problem, bound=None, max_trees=0x7FFFFFFF):
     """Oracle exact search of a prepared host problem (xmp_b200.hostlib.Problem).
     Returns (score, num_trees, [newick strings in DFS order], nodes, score_calls)."""
-    rows = np.ascontiguousarray(problem.rows, dtype=np.uint8)
-    w = np.ascontiguousarray(problem.weights, dtype=np.uint32)
-    rb = np.ascontiguousarray(problem.rest_bound, dtype=np.uint32)
-    tm = np.ascontiguousarray(problem.taxon_map, dtype=np.uint32)
-    pr = XoProblem(problem.num_taxa, rows.shape[1], p(rows), p(w), p(rb), p(tm), problem.constant_weight,
-                   problem.bound if bound is None else bound, max_trees)
+    pr, keep = _problem(problem, bound, max_trees)
     res = XoResult()
     rc = oracle().xo_search(C.byref(pr), C.byref(res))
     assert rc == 0
     text = C.string_at(res.newick, res.newick_len).decode() if res.newick_len else ""
     out = (res.score, res.num_trees, text.split(), res.nodes, res.score_calls)
+    oracle().xo_result_free(C.byref(res))
+    return out
+
+
+def search_subtree(problem, path, m, bound):
+    """Oracle search below one partial tree.  Returns (bound afterwards, paths of the trees found at
+    that bound [k][num_taxa], nodes)."""
+    pr, keep = _problem(problem, bound, 0x7FFFFFFF)
+    res = XoResult()
+    path = np.ascontiguousarray(path, dtype=np.uint8)
+    rc = oracle().xo_search_subtree(C.byref(pr), p(path), m, C.byref(res))
+    assert rc == 0
+    n = problem.num_taxa
+    paths = np.frombuffer(C.string_at(res.paths, res.paths_len), np.uint8).reshape(-1, n).copy() if res.paths_len else np.zeros((0, n), np.uint8)
+    out = (res.score, paths, res.nodes)
     oracle().xo_result_free(C.byref(res))
     return out
 

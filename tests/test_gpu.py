@@ -1,0 +1,390 @@
+"""Parity tests proper (run with -m gpu on a B200): every entry point of the C ABI against the CPU
+oracle on seeded inputs, against the committed known-answer vectors, and against the goldens
+generated from the reference program.  Integer work: everything is compared bit for bit."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol
+from tests.conftest import GOLDEN, ROOT, golden_output, golden_trees
+from tests.newick import canonical_newick
+from tests.test_host import prepare
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xc():
+    import xmp_b200.cuda as xc
+    return xc
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture()
+def ctx(xc):
+    c = xc.Context(0)
+    yield c
+    c.close()
+
+
+O = ol.oracle()
+
+
+# ---------------------------------------------------------------------------------- per-pair family
+def test_pair_family_known_answers(xc):
+    cases = json.load(open(os.path.join(GOLDEN, "fitch_kat.json")))
+    for c in cases:
+        if c["nbytes"] % 16:
+            continue
+        s1, s2, prev = (np.frombuffer(bytes.fromhex(c[k]), np.uint8).copy() for k in ("s1", "s2", "prev"))
+        w = np.array(c["weights"], np.uint32)
+        assert xc.fitch_bases(s1, s2).tobytes().hex() == c["bases"]
+        d, ch = xc.fitch_bases_and_compare(s1, s2, prev)
+        assert d.tobytes().hex() == c["bases"] and int(ch != 0) == c["changed_vs_prev"]
+        _, ch = xc.fitch_bases_and_compare(s1, s2, d)
+        assert int(ch != 0) == c["changed_vs_self"]
+        assert xc.fitch_score_weight1(s1, s2) == c["score_weight1"]
+        assert xc.fitch_score(s1, s2, w) == c["score"]
+        assert xc.fitch_score(s1, s2, w, fw1=True) == c["score_fw1"]
+        # stop-early contract: exact when within the limit, otherwise anything above the limit
+        for got, true, limit in ((xc.fitch_score(s1, s2, w, fw1=True, max_score=c["limit"]), c["score_fw1"], c["limit"]),
+                                 (xc.fitch_score(s1, s2, w, max_score=c["limit"]), c["score"], c["limit"]),
+                                 (xc.fitch_score_weight1(s1, s2, max_score=c["score_weight1"] // 2), c["score_weight1"], c["score_weight1"] // 2)):
+            assert got == true if true <= limit else got > limit
+
+
+def test_pair_family_random_vs_oracle(xc):
+    rng = np.random.default_rng(5)
+    for nbytes in (16, 48, 80, 1248, 4096 + 16):
+        for amb in (0.0, 0.3):
+            s1, s2, prev = (ol.random_sets(rng, nbytes, amb) for _ in range(3))
+            w = ol.random_weights(rng, nbytes * 2, 0.4, 3000)
+            want = np.zeros(nbytes, np.uint8)
+            O.xo_fitch_bases(ol.p(s1), ol.p(s2), ol.p(want), nbytes)
+            assert (xc.fitch_bases(s1, s2) == want).all()
+            assert xc.fitch_score_weight1(s1, s2) == O.xo_fitch_score_weight1(ol.p(s1), ol.p(s2), nbytes)
+            assert xc.fitch_score(s1, s2, w) == O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(w), nbytes)
+            # unsorted weights: the plain variant is exact, fw1 follows the reference's hand-over rule
+            wu = rng.integers(1, 9, nbytes * 2).astype(np.uint32)
+            assert xc.fitch_score(s1, s2, wu) == O.xo_fitch_score(ol.p(s1), ol.p(s2), ol.p(wu), nbytes)
+            assert xc.fitch_score(s1, s2, wu, fw1=True) == O.xo_fitch_score_stopearly(ol.p(s1), ol.p(s2), ol.p(wu), nbytes, 16, 1, 0x7FFFFFFF)
+    e = np.zeros(0, np.uint8)
+    assert xc.fitch_score_weight1(e, e) == 0 and xc.fitch_bases(e, e).size == 0
+
+
+# ------------------------------------------------------------------------------- batched scoring
+def oracle_costs(rows, weights, sets, taxon):
+    nbytes = rows.shape[1]
+    w = None if weights is None else np.ascontiguousarray(weights, np.uint32)
+    out = np.zeros(len(sets), np.uint32)
+    for i, s in enumerate(sets):
+        s = np.ascontiguousarray(s)
+        out[i] = (O.xo_fitch_score(ol.p(s), ol.p(rows[taxon]), ol.p(w), nbytes) if w is not None
+                  else O.xo_fitch_score_weight1(ol.p(s), ol.p(rows[taxon]), nbytes))
+    return out
+
+
+@pytest.mark.parametrize("n_blocks", [1, 2, 3, 5, 9, 17, 33, 64, 78, 130, 300, 513])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_score_batch_matches_oracle(ctx, torch, n_blocks, weighted):
+    rng = np.random.default_rng(n_blocks * 2 + weighted)
+    num_taxa, n_pairs, ppt = 6, 1000 + n_blocks, 7
+    nbytes = n_blocks * 16
+    rows = np.stack([ol.random_sets(rng, nbytes, 0.1) for _ in range(num_taxa)])
+    weights = ol.random_weights(rng, nbytes * 2, 0.35, 500) if weighted else None
+    rest = rng.integers(0, 5, num_taxa).astype(np.uint32)
+    sets = np.stack([ol.random_sets(rng, nbytes, 0.2) for _ in range(n_pairs)])
+    base = rng.integers(0, 50, (n_pairs + ppt - 1) // ppt).astype(np.uint32)
+    ctx.load(rows, weights, rest, 0)
+    d_sets = torch.from_numpy(sets).cuda()
+    d_base = torch.from_numpy(base.astype(np.int32)).cuda()
+    d_cost = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    d_surv = torch.full((n_pairs,), -1, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    taxon = 4
+    want = oracle_costs(rows, weights, sets, taxon)
+    bound = int(np.median(want + base[np.arange(n_pairs) // ppt])) + int(rest[taxon])
+    ctx.score_batch(d_sets, n_pairs, ppt, taxon, d_cost, d_base, bound, d_surv, d_n)
+    ctx.synchronize()
+    got = d_cost.cpu().numpy().astype(np.uint32)
+    assert (got == want).all()
+    keep = (want.astype(np.int64) <= bound - base[np.arange(n_pairs) // ppt].astype(np.int64) - int(rest[taxon]))
+    n = int(d_n.item())
+    assert n == int(keep.sum())
+    assert sorted(d_surv[:n].cpu().numpy().tolist()) == np.nonzero(keep)[0].tolist()
+    # no pruning requested
+    ctx.score_batch(d_sets, n_pairs, ppt, taxon, d_cost)
+    ctx.synchronize()
+    assert (d_cost.cpu().numpy().astype(np.uint32) == want).all()
+
+
+def test_score_batch_empty_and_single(ctx, torch):
+    rng = np.random.default_rng(1)
+    rows = np.stack([ol.random_sets(rng, 32) for _ in range(4)])
+    ctx.load(rows)
+    d_n = torch.ones(1, dtype=torch.int32, device="cuda")
+    d_cost = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_surv = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx.score_batch(None, 0, 1, 3, d_cost, None, 5, d_surv, d_n)
+    ctx.synchronize()
+    assert int(d_n.item()) == 0
+    one = torch.from_numpy(rows[1].copy()).cuda()
+    ctx.score_batch(one, 1, 1, 3, d_cost)
+    ctx.synchronize()
+    assert int(d_cost.item()) == O.xo_fitch_score_weight1(ol.p(rows[1]), ol.p(rows[3]), 32)
+
+
+@pytest.mark.parametrize("m,n_blocks,weighted", [(3, 2, True), (4, 1, False), (8, 5, True), (13, 40, True), (20, 3, False), (40, 2, True), (64, 2, False)])
+def test_build_midpoints_and_insertion_costs(ctx, torch, m, n_blocks, weighted):
+    rng = np.random.default_rng(m * 31 + n_blocks)
+    num_taxa, n_trees = m + 1, 37
+    nbytes = n_blocks * 16
+    rows = np.stack([ol.random_sets(rng, nbytes, 0.1) for _ in range(num_taxa)])
+    weights = ol.random_weights(rng, nbytes * 2, 0.3, 77) if weighted else None
+    ctx.load(rows, weights, None, 11)
+    paths = ol.random_paths(rng, n_trees, m, num_taxa)
+    E = 2 * m - 3
+    d_mid = torch.zeros((n_trees, E, nbytes), dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(n_trees, dtype=torch.int32, device="cuda")
+    ctx.build_midpoints(paths, m, d_mid, d_len)
+    ctx.synchronize()
+    got_mid = d_mid.cpu().numpy()
+    got_len = d_len.cpu().numpy()
+    costs = ctx.score_insertions_host(paths, m)
+    for i in range(n_trees):
+        mid, _, _, length = ol.tree_sets(rows, m, paths[i], weights)
+        assert (got_mid[i] == mid).all(), i
+        assert got_len[i] == length + 11
+        assert (costs[i] == oracle_costs(rows, weights, mid, m)).all()
+
+
+def test_invalid_arguments_are_reported(ctx, xc):
+    with pytest.raises(xc.XmpCudaError, match="no problem loaded"):
+        ctx.score_insertions_host(np.zeros((1, 8), np.uint8), 5)
+    rng = np.random.default_rng(2)
+    ctx.load(np.stack([ol.random_sets(rng, 16) for _ in range(6)]))
+    bad = np.zeros((1, 6), np.uint8)
+    bad[0, 4] = 9   # a 4-taxon tree has edges 0..4
+    with pytest.raises(xc.XmpCudaError, match="does not exist"):
+        ctx.score_insertions_host(bad, 5)
+    with pytest.raises(xc.XmpCudaError, match="no search in progress"):
+        ctx.search_result()
+
+
+# --------------------------------------------------------------------------------------- the search
+def run_search(xc, p, **kw):
+    score, n, paths, stats = xc.search(p, **kw)
+    return score, n, p.newick_list(paths), stats
+
+
+QUICK = ["its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16", "mt-10", "EukaryotesrDNA",
+         "h3", "mh6", "mt-10.Bm", "h3.Bm", "h3.Bdm", "h3.b359"]
+HARD = ["h1", "h2", "mh1", "mh2", "mh4", "rbc14x759", "Metazoan", "h4", "h5"]
+
+
+def check_against_golden(name, g, p, score, n, trees):
+    assert (score, n) == (g["score"], g["num_trees"]), name
+    canon = sorted(canonical_newick(t) for t in trees)
+    blob = ("\n".join(canon) + "\n").encode() if canon else b""
+    assert hashlib.sha256(blob).hexdigest() == g["canonical_sha256"]
+    if n <= 2000:
+        assert canon == golden_trees(name)
+        # sorted into the reference's depth-first order the text is the reference's tree block
+        body = "".join("\tTREE FASTDNAMP_%d = [&U] %s\n" % (i + 1, t) for i, t in enumerate(trees))
+        assert body.encode() in golden_output(name)
+
+
+@pytest.mark.parametrize("name", QUICK + HARD)
+def test_search_matches_reference(xc, alignment_dir, goldens, name):
+    g = goldens[name]
+    a, p = prepare(alignment_dir, goldens, name)
+    score, n, trees, stats = run_search(xc, p)
+    check_against_golden(name, g, p, score, n, trees)
+    print("\n%s: %.3f s device, %d nodes (reference %d, %.2f s CPU), %d batches" %
+          (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
+
+
+def test_search_its36_with_loaded_partition_bound(xc, alignment_dir, goldens, tmp_path):
+    """The author's own its36 setting (-Bp -b 233 -m 100000): restBound[] comes from the reference's
+    restBound.txt through -Bf, as INTEGRATION.md describes."""
+    from xmp_b200 import hostlib as xh
+    g = goldens["its36"]
+    f = tmp_path / "restBound.txt"
+    f.write_text("i\tbound\n" + "".join("%d\t%d\n" % (i, b) for i, b in g["rest_bound"]))
+    a = xh.Alignment(str(alignment_dir / g["alignment"]))
+    p = xh.Problem(a, options=xh.OPT_USELOADRESTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=233, max_trees=100000, rest_bound_file=str(f))
+    score, n, trees, stats = run_search(xc, p)
+    check_against_golden("its36", g, p, score, n, trees)
+
+
+def test_search_mh3_large_tree_set(xc, alignment_dir, goldens):
+    g = goldens["mh3"]
+    a, p = prepare(alignment_dir, goldens, "mh3")
+    score, n, trees, stats = run_search(xc, p)
+    check_against_golden("mh3", g, p, score, n, trees)
+
+
+def test_search_bound_edge_cases(xc, alignment_dir, goldens):
+    a, p = prepare(alignment_dir, goldens, "h3")
+    g = goldens["h3"]
+    # a bound below the optimum finds nothing and reports the bound (reference: "NO BEST TREE FOUND")
+    score, n, trees, _ = run_search(xc, p, bound=g["score"] - 1)
+    assert (score, n, trees) == (goldens["h3.b358"]["score"], 0, [])
+    # a bound equal to the optimum keeps ties
+    score, n, trees, _ = run_search(xc, p, bound=g["score"])
+    check_against_golden("h3.b359", goldens["h3.b359"], p, score, n, trees)
+
+
+def test_search_is_independent_of_scheduling(xc, alignment_dir, goldens):
+    """Same tree set without the greedy dive, with a frontier budget that forces small batches, and in
+    slices of a few batches at a time."""
+    g = goldens["mh6"]
+    a, p = prepare(alignment_dir, goldens, "mh6")
+    for kw in ({"flags": xc.SEARCH_NO_DIVE}, {"mem_budget": 600 << 20}):
+        score, n, trees, stats = run_search(xc, p, **kw)
+        check_against_golden("mh6", g, p, score, n, trees)
+    ctx = xc.Context(0)
+    ctx.load_problem(p)
+    ctx.search_begin(bound=p.bound)
+    slices = 0
+    while not ctx.search_run(3):
+        slices += 1
+    score, n, paths = ctx.search_result()
+    check_against_golden("mh6", g, p, score, n, p.newick_list(paths))
+    assert slices > 1
+    ctx.close()
+
+
+def test_sharded_search_union_equals_whole(xc, alignment_dir, goldens):
+    """Two shards (run one after the other on this GPU) with bound exchange: the union of their tree
+    sets is the reference's set, each tree found exactly once."""
+    for name in ("mh6", "h3", "53humans.16"):
+        g = goldens[name]
+        a, p = prepare(alignment_dir, goldens, name)
+        ctxs = [xc.Context(0) for _ in range(3)]
+        for i, c in enumerate(ctxs):
+            c.load_problem(p)
+            c.search_begin(bound=p.bound, shard_index=i, shard_count=3)
+        done = [False] * 3
+        while not all(done):
+            for i, c in enumerate(ctxs):
+                if not done[i]:
+                    done[i] = c.search_run(8)
+            best = min(c.search_get_bound() for c in ctxs)
+            for c in ctxs:
+                c.search_set_bound(best)
+        allpaths = []
+        for c in ctxs:
+            score, n, paths = c.search_result()
+            assert score == g["score"]
+            allpaths.append(paths)
+            c.close()
+        paths = np.concatenate(allpaths)
+        check_against_golden(name, g, p, g["score"], len(paths), p.newick_list(paths))
+
+
+def test_job_export_import_moves_work_between_contexts(xc, alignment_dir, goldens):
+    """Work stealing primitive: open subtrees detached from one context as job descriptors and replayed
+    in another give the same overall result."""
+    g = goldens["mh6"]
+    a, p = prepare(alignment_dir, goldens, "mh6")
+    c0, c1 = xc.Context(0), xc.Context(0)
+    for c in (c0, c1):
+        c.load_problem(p)
+    c0.search_begin(bound=p.bound)
+    c1.search_begin(bound=p.bound, flags=xc.SEARCH_NO_DIVE)
+    assert len(c1.search_export_jobs(16)) == 1          # throw c1's own root away: it only gets stolen work
+    assert c1.search_run(0)                             # nothing to do: done, and may be woken up again
+    c0.search_run(6)
+    moved, rounds = 0, 0
+    done0 = done1 = False
+    while not (done0 and done1):
+        jobs = c0.search_export_jobs(64) if rounds % 2 == 0 else np.zeros((0, p.num_taxa), np.uint8)
+        moved += len(jobs)
+        c1.search_import_jobs(jobs)
+        done0 = c0.search_run(5)
+        done1 = c1.search_run(5)
+        best = min(c0.search_get_bound(), c1.search_get_bound())
+        c0.search_set_bound(best)
+        c1.search_set_bound(best)
+        rounds += 1
+    assert moved > 0
+    s0, n0, p0 = c0.search_result()
+    s1, n1, p1 = c1.search_result()
+    assert s0 == s1 == g["score"]
+    paths = np.concatenate([p0, p1])
+    check_against_golden("mh6", g, p, g["score"], len(paths), p.newick_list(paths))
+    c0.close()
+    c1.close()
+
+
+# ------------------------------------------------------------------------------------------ the CLI
+@pytest.mark.parametrize("name", ["mt-10", "h3", "mh6", "EukaryotesrDNA", "quick2"])
+def test_cli_writes_the_reference_result_file(alignment_dir, goldens, tmp_path, name):
+    """fastdnamp_b200 with the reference's measurement flags produces the reference's output file byte
+    for byte (for mt-10 that is build-vswin32/mt-10.tre) and its restBound.txt."""
+    g = goldens[name]
+    out = tmp_path / "out.nex"
+    r = subprocess.run([os.path.join(ROOT, "fastdnamp_b200"), "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n",
+                        "--updatesecs=0", "-o", str(out), str(alignment_dir / g["alignment"])], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == golden_output(name)
+    rb = [[int(x) for x in line.split()] for line in (tmp_path / "restBound.txt").read_text().splitlines()[1:]]
+    assert rb == g["rest_bound"]
+    assert "%d parsimoniously-informative sites." % g["pi_sites"] in r.stderr
+    raw = subprocess.run([os.path.join(ROOT, "fastdnamp_b200"), "-q", "-r", "-m", "2", str(alignment_dir / g["alignment"])],
+                         cwd=tmp_path, capture_output=True, text=True)
+    assert raw.returncode == 0 and raw.stderr == ""
+    want = [l.split("] ")[1] for l in golden_output(name).decode().splitlines() if "TREE FASTDNAMP_" in l][:2]
+    assert raw.stdout.splitlines() == want
+
+
+# ----------------------------------------------------------- BASELINE.json sizes: structural properties
+def test_full_size_microbench_properties(ctx, torch):
+    """64 taxa x 2^20 sites (BASELINE config 2), all weights 1: at this size the oracle is only run on a
+    few trees; the rest is checked through size-independent properties of the scores."""
+    import bench
+    wl = bench.make_workload(torch, n_trees=64, m=8)
+    ctx.load(wl["d_rows"])
+    ctx.build_midpoints(wl["paths"], wl["m"], wl["d_mid"])
+    n_pairs = wl["n_pairs"]
+    d_cost = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    ctx.score_batch(wl["d_mid"], n_pairs, wl["E"], wl["m"], d_cost)
+    ctx.synchronize()
+    cost = d_cost.cpu().numpy().reshape(-1, wl["E"])
+    rows = wl["d_rows"].cpu().numpy()
+    # (1) oracle on three trees
+    for i in (0, 31, 63):
+        mid, _, _, _ = ol.tree_sets(rows[:wl["m"] + 1], wl["m"], wl["paths"][i])
+        assert (cost[i] == oracle_costs(rows, None, mid, wl["m"])).all()
+    # (2) scoring a taxon against its own leaf edge costs 0; against another taxon's leaf edge it is
+    #     their Hamming distance when the leaf's DOWN set does not help, never more
+    d_self = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    ctx.score_batch(wl["d_mid"], n_pairs, wl["E"], 1, d_self)
+    ctx.synchronize()
+    assert (d_self.cpu().numpy().reshape(-1, wl["E"])[:, 0] == 0).all()    # edge 0 = leaf of taxon 1
+    # (3) additivity over site ranges: scoring the two halves separately sums to the whole
+    half = wl["n_blocks"] // 2
+    lo = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    d_mid = wl["d_mid"].view(n_pairs, wl["n_blocks"] * 16)
+    c2 = __import__("xmp_b200.cuda", fromlist=["Context"]).Context(0)
+    c2.load(wl["d_rows"][:, :half * 16].contiguous())
+    c2.score_batch(d_mid[:, :half * 16].contiguous(), n_pairs, wl["E"], wl["m"], lo)
+    c2.synchronize()
+    hi = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    c2.load(wl["d_rows"][:, half * 16:].contiguous())
+    c2.score_batch(d_mid[:, half * 16:].contiguous(), n_pairs, wl["E"], wl["m"], hi)
+    c2.synchronize()
+    assert ((lo + hi).cpu().numpy().reshape(-1, wl["E"]) == cost).all()
+    c2.close()

@@ -722,12 +722,12 @@ extern "C" int xmp_cuda_search_import_jobs(xmp_ctx *ctx, const uint8_t *jobs, un
 	Search *S = ctx->search;
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	if (n_jobs == 0) return XMP_OK;
-	if (S->finished) return set_error(XMP_ERR_ARG, "the search has already been finalised");
 	for (unsigned j = 0; j < n_jobs; ++j) {
 		unsigned m = jobs[(size_t) j * S->L.n];
 		if (m < 3 || m >= S->n) return set_error(XMP_ERR_ARG, "job %u has tree size %u, expected 3..%u", j, m, S->n - 1);
 	}
-	S->done = false;
+	S->done = false;       // an idle shard that receives stolen work is searching again
+	S->finished = false;
 	return import_nodes(ctx, S, jobs, n_jobs);
 }
 

@@ -116,6 +116,7 @@ class Context:
         h = C.c_void_p()
         _check(L.xmp_cuda_init(device, C.byref(h)))
         self._h = h
+        self._destroy = L.xmp_cuda_destroy     # kept for interpreter shutdown, when module globals are gone
         self.device = device
         self.num_taxa = self.n_blocks = 0
         if stream is not None:
@@ -123,7 +124,7 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().xmp_cuda_destroy(self._h)
+            self._destroy(self._h)
             self._h = None
 
     __del__ = close

@@ -1,0 +1,92 @@
+"""One-process-per-GPU exact search over torch.distributed: the replacement for the reference's MPI
+boss/worker scheduler (reference src/mpiboss.c:30-429, src/mpiworker.c:214-380) when the host is
+Python (bench.py under torchrun).  The C host (host/fastdnamp.c) does the same with threads.
+
+Differences from the reference, by design:
+  * no boss: every rank searches (the reference's rank 0 only relays, src/fastdnamp.c:112-118);
+  * the upper bound is kept consistent by an all-reduce(min) of one word every round instead of
+    worker -> boss -> all workers point-to-point relays (src/mpiboss.c:162-171, src/mpiworker.c:19-41);
+  * work stealing is decided collectively from an all-gather of the open-node counts: ranks that ran
+    dry receive job descriptors (insertion paths, a few hundred bytes) from the ranks holding the most
+    open subtrees, point-to-point (over NVLink with the nccl backend); the thief rebuilds the subtree
+    state from the descriptor alone, as the reference's fast-forward does (src/yanbader.c:136-143);
+  * termination: the all-gathered counts are all zero.
+
+The engine is any object with the search_* methods of xmp_b200.cuda.Context; the CPU tests drive the
+same protocol over gloo with an oracle-backed stand-in.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _t(x, device, dtype=torch.int64):
+    return torch.tensor(x, dtype=dtype, device=device)
+
+
+def sharded_search(engine, num_taxa, device="cpu", slice_batches=64, steal_nodes=256, group=None, on_round=None):
+    """Runs engine (already search_begin()'ed with this rank's shard_index / shard_count) to completion
+    together with the other ranks.  Returns (score, total number of optimal trees, this rank's optimal
+    paths, number of rounds).  Every rank returns the same score and total."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    rounds = 0
+    done = False
+    while True:
+        if not done:
+            done = engine.search_run(slice_batches)
+        # upper bound: all-reduce(min) of one word
+        b = _t([engine.search_get_bound()], device)
+        dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
+        engine.search_set_bound(int(b.item()))
+        # open subtrees per rank
+        mine = int(np.asarray(engine.search_pending()).sum())
+        counts = [_t([0], device) for _ in range(world)]
+        dist.all_gather(counts, _t([mine], device), group=group)
+        counts = [int(c.item()) for c in counts]
+        rounds += 1
+        if on_round:
+            on_round(rounds, counts, int(b.item()))
+        if sum(counts) == 0:
+            break
+        # collective steal plan, identical on every rank: the i-th idle rank takes from the i-th richest
+        idle = [r for r in range(world) if counts[r] == 0]
+        donors = sorted((r for r in range(world) if counts[r] > 1), key=lambda r: (-counts[r], r))
+        plan = [(donors[i % len(donors)], thief) for i, thief in enumerate(idle)] if donors else []
+        for donor, thief in plan:
+            if rank == donor:
+                jobs = engine.search_export_jobs(min(steal_nodes, max(1, counts[donor] // (2 * max(1, len(idle))))))
+                n = _t([len(jobs)], device)
+                dist.send(n, thief, group=group)
+                if len(jobs):
+                    dist.send(torch.from_numpy(np.ascontiguousarray(jobs)).to(device), thief, group=group)
+            elif rank == thief:
+                n = _t([0], device)
+                dist.recv(n, donor, group=group)
+                k = int(n.item())
+                if k:
+                    buf = torch.zeros((k, num_taxa), dtype=torch.uint8, device=device)
+                    dist.recv(buf, donor, group=group)
+                    engine.search_import_jobs(buf.cpu().numpy())
+                    done = False
+    score, n, paths = engine.search_result()
+    tot = _t([n], device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return score, int(tot.item()), paths, rounds
+
+
+def gather_paths(paths, num_taxa, device="cpu", group=None):
+    """All ranks' optimal paths on every rank (the reference's MSG_TREES collection, src/common.c:397-413)."""
+    world = dist.get_world_size(group)
+    n = _t([len(paths)], device)
+    sizes = [_t([0], device) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    mine = torch.zeros((cap, num_taxa), dtype=torch.uint8, device=device)
+    if len(paths):
+        mine[:len(paths)] = torch.from_numpy(np.ascontiguousarray(paths)).to(device)
+    bufs = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    parts = [bufs[r][:sizes[r]].cpu().numpy() for r in range(world)]
+    return np.concatenate(parts) if parts else np.zeros((0, num_taxa), np.uint8)
