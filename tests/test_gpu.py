@@ -251,7 +251,8 @@ def test_search_is_independent_of_scheduling(xc, alignment_dir, goldens):
     slices of a few batches at a time."""
     g = goldens["mh6"]
     a, p = prepare(alignment_dir, goldens, "mh6")
-    for kw in ({"flags": xc.SEARCH_NO_DIVE}, {"mem_budget": 600 << 20}):
+    for kw in ({"flags": xc.SEARCH_NO_DIVE}, {"mem_budget": 600 << 20}, {"flags": xc.SEARCH_NO_FUSE},
+               {"flags": xc.SEARCH_NO_FUSE | xc.SEARCH_NO_DIVE, "mem_budget": 400 << 20}):
         score, n, trees, stats = run_search(xc, p, **kw)
         check_against_golden("mh6", g, p, score, n, trees)
     ctx = xc.Context(0)
@@ -348,6 +349,36 @@ def test_cli_writes_the_reference_result_file(alignment_dir, goldens, tmp_path, 
     assert raw.returncode == 0 and raw.stderr == ""
     want = [l.split("] ")[1] for l in golden_output(name).decode().splitlines() if "TREE FASTDNAMP_" in l][:2]
     assert raw.stdout.splitlines() == want
+
+
+# -------------------------------------------------------------------------------------- two GPUs
+def _n_gpus():
+    try:
+        import xmp_b200.cuda as xc
+        return xc.lib().xmp_cuda_device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("name", ["mh6", "h1"])
+def test_cli_two_gpus_same_result_file(alignment_dir, goldens, tmp_path, name):
+    g = goldens[name]
+    out = tmp_path / "out.nex"
+    r = subprocess.run([os.path.join(ROOT, "fastdnamp_b200"), "--gpus=2", "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n",
+                        "--updatesecs=0", "-o", str(out), str(alignment_dir / g["alignment"])], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == golden_output(name)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_torchrun_sharded_search_two_gpus():
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "mh6", "h3", "mh1", "53humans.16"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" OK ") == 8 and "MISMATCH" not in r.stdout
 
 
 # ----------------------------------------------------------- BASELINE.json sizes: structural properties

@@ -206,6 +206,140 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	}
 }
 
+
+// ---- last two levels fused ---------------------------------------------------------------------------
+// Parents have n-2 taxa.  A surviving child (n-1 taxa) is only ever scored once more, against the last
+// taxon, so it is never written to HBM: G lanes per child (one per 128-bit column) walk the child's
+// topology, form each edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the
+// columns), apply the acceptance test and emit complete trees.  This replaces k_build_children for the
+// deepest pool and the whole k_expand_score pass over it -- where almost all nodes of a search live.
+//
+// Per-lane state that needs dynamic indexing lives in shared memory, element k of thread t at
+// [k * blockDim.x + t]: 16-byte accesses are then bank-conflict free whatever k each lane uses (local
+// memory would serialise into one wavefront per distinct index).  Only two small stacks are needed:
+//   upath[k]   UP sets recomputed along the path from the new internal node (k = 0) to the root's child;
+//              every other UP set is the parent tree's and is read from its record (L1/L2 hits: the lanes
+//              of a warp mostly share a parent);
+//   dstack[d]  DOWN set of the current ancestor at depth d.
+template <int G>
+__global__ void __launch_bounds__(128)
+k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
+                    unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
+                    unsigned *bound_ptr, uint8_t *__restrict__ trees, unsigned *n_trees, unsigned trees_cap,
+                    unsigned long long *merges, unsigned D) {
+	extern __shared__ uint4 smem[];
+	const unsigned T = blockDim.x;
+	uint4 *upath = smem + threadIdx.x;
+	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, a = E, b = E + 1;
+	const unsigned n_surv = min(*n_surv_ptr, s_end);
+	const unsigned lane = threadIdx.x & 31u, sub = lane % G;
+	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - sub));
+	const unsigned groups_per_block = T / G;
+	const bool col_ok = sub < W;
+	const unsigned col = col_ok ? sub : 0;
+	const uint4 r0 = __ldg(rows + col);
+	const uint4 rt = __ldg(rows + (size_t) m * W + col);
+	const uint4 rl = __ldg(rows + (size_t) (m + 1) * W + col);
+	for (unsigned long long s = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + threadIdx.x / G; s < n_surv;
+	     s += (unsigned long long) gridDim.x * groups_per_block) {
+		const uint4 sv = surv[s];
+		const unsigned pnode = sv.x, v = sv.y, score = sv.z;
+		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
+		const uint8_t *ppar = ph + L.off_par, *pk0 = ph + L.off_k0, *pk1 = ph + L.off_k1;
+		const unsigned pv = ppar[v];
+		auto par_of = [&](unsigned x) -> unsigned { return (x == a || x == v) ? b : (x == b ? pv : (unsigned) ppar[x]); };
+		auto kid0_of = [&](unsigned x) -> unsigned {
+			if (x == b) return a;
+			unsigned k = pk0[x];
+			return (x == pv && k == v) ? b : k;
+		};
+		auto kid1_of = [&](unsigned x) -> unsigned {
+			if (x == b) return v;
+			unsigned k = pk1[x];
+			return (x == pv && k == v) ? b : k;
+		};
+		const unsigned top = (pv == 0xFFu) ? b : (unsigned) ph[HDR_PATH];
+		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
+
+		// UP along the root path, remembering which edges are on it.
+		unsigned on0 = 0, on1 = 0, on2 = 0;
+		auto mark = [&](unsigned e) {
+			if (e < 32) on0 |= 1u << e; else if (e < 64) on1 |= 1u << (e - 32); else on2 |= 1u << (e - 64);
+		};
+		auto on_path = [&](unsigned e) -> bool {
+			const unsigned w = e < 32 ? on0 : (e < 64 ? on1 : on2);
+			return (w >> (e & 31u)) & 1u;
+		};
+		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W));
+		upath[0] = u;
+		mark(b);
+		unsigned k = 1;
+		for (unsigned x = b;;) {
+			const unsigned p = par_of(x);
+			if (p == 0xFFu) break;
+			const unsigned k0 = kid0_of(p);
+			const unsigned other = (k0 == x) ? kid1_of(p) : k0;      // hangs off the path: unchanged
+			u = fitch_block(u, __ldg(PU + (size_t) other * W));
+			upath[(size_t) k * T] = u;
+			mark(p);
+			++k;
+			x = p;
+		}
+		const unsigned last = k - 1;      // depth of b
+		auto up_of = [&](unsigned y, unsigned depth) -> uint4 {
+			if (on_path(y)) return upath[(size_t) (last - depth) * T];
+			if (y == a) return rt;
+			return __ldg(PU + (size_t) y * W);
+		};
+
+		const unsigned bound = *(volatile unsigned *) bound_ptr;
+		unsigned depth = 0;
+		for (unsigned x = top;;) {
+			const unsigned p = par_of(x);
+			uint4 d;
+			if (p == 0xFFu) {
+				d = r0;
+			} else {
+				const unsigned k0 = kid0_of(p);
+				const unsigned sib = (k0 == x) ? kid1_of(p) : k0;
+				d = fitch_block(dstack[(size_t) (depth - 1) * T], up_of(sib, depth));
+			}
+			const uint4 mid = fitch_block(up_of(x, depth), d);
+			unsigned c = col_ok ? cost_block(mid, rl, col, wp) : 0u;
+#pragma unroll
+			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
+			if (sub == 0 && accept_insertion(c, bound, score, rest_last)) {
+				atomicMin(bound_ptr, score + c);
+				const unsigned slot = atomicAdd(n_trees, 1u);
+				if (slot < trees_cap) {
+					uint8_t *rec = trees + (size_t) slot * L.trec;
+					*(unsigned *) rec = score + c;
+					for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = ph[HDR_PATH + t];
+					rec[4 + m] = (uint8_t) v;
+					rec[4 + m + 1] = (uint8_t) x;
+				}
+			}
+			if (!edge_is_leaf(x)) {
+				dstack[(size_t) depth * T] = d;
+				x = kid0_of(x);
+				++depth;
+				continue;
+			}
+			bool finished = false;
+			for (;;) {
+				const unsigned q = par_of(x);
+				if (q == 0xFFu) { finished = true; break; }
+				if (kid0_of(q) == x) { x = kid1_of(q); break; }
+				x = q;
+				--depth;
+			}
+			if (finished) break;
+		}
+		if (sub == 0) atomicAdd(merges, (unsigned long long) (k + 2 * Ec));
+	}
+}
+
 // Headers for nodes whose sets were built from topologies (the root job, imported jobs).
 __global__ void k_write_headers(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n_jobs,
                                 const uint8_t *__restrict__ topo, unsigned topo_stride, const uint8_t *__restrict__ paths,
@@ -266,6 +400,7 @@ struct Search {
 	std::vector<uint8_t> host_trees;      // records (score + path) that left the device, each <= the bound at that time
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
+	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	xmp_search_stats st;
 	Scratch topo, pathbuf;
 };
@@ -319,11 +454,16 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	if (budget < fixed + ((size_t) 64 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
 	budget -= fixed;
 
+	// The deepest pool is skipped when the last two levels are fused (narrow state sets): it then only
+	// ever holds imported jobs.
+	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 4 && n >= 5 && n <= 41;
+	const double last_cap = S->fused_last ? 1024.0 : 1e300;
 	// Largest per-level capacity C such that all pools fit; a level never needs more than (2m-5)!! nodes.
 	auto bytes_for = [&](double C) {
 		double tot = 0;
 		for (unsigned m = 3; m < n; ++m) {
 			double c = std::min(C, odd_factorial(m));
+			if (m + 1 == n) c = std::min(c, last_cap);
 			tot += c * ((double) 3 * (2 * m - 3) * W * 16 + L.HB);
 		}
 		return tot + C * 16;   // survivors
@@ -340,6 +480,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		P.E = 2 * m - 3;
 		P.rec = 3ull * P.E * W;
 		P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
+		if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
 		P.count = 0;
 		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.HB));
 		XMP_CUDA(cudaMalloc(&P.sets, (size_t) P.cap * P.rec * 16));
@@ -442,6 +583,30 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m) {
 	return XMP_OK;
 }
 
+static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, unsigned s_end) {
+	const Layout &L = S->L;
+	Pool &P = S->pool[m];
+	const unsigned D = m + 1;                        // a tree on m + 1 taxa is at most m edges deep
+	unsigned threads = 128;
+	if ((size_t) 2 * D * 16 * threads > (size_t) 96 << 10) threads = 64;
+	const size_t smem = (size_t) 2 * D * 16 * threads;
+	const unsigned blocks = (unsigned) ctx->sm_count * 16;
+#define XMP_FUSED(G)                                                                                                          \
+	do {                                                                                                                      \
+		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
+		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, S->d_surv, S->d_nsurv, s_begin, s_end,     \
+		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
+		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D); \
+	} while (0)
+	if (L.W == 1) XMP_FUSED(1);
+	else if (L.W == 2) XMP_FUSED(2);
+	else XMP_FUSED(4);
+#undef XMP_FUSED
+	XMP_CUDA(cudaGetLastError());
+	S->st.launches += 1;
+	return XMP_OK;
+}
+
 // Reads back n_surv, n_trees, bound and the merge counter (one small pinned copy, one sync).
 static int fetch_counters(xmp_ctx *ctx, Search *S) {
 	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 32, cudaMemcpyDeviceToHost, ctx->stream));
@@ -529,6 +694,52 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 			XMP_CUDA(cudaMemcpyAsync(S->d_nsurv, &ns, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
 			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 		}
+	}
+	if (S->fused_last && m + 2 == S->n) {
+		// Children of this level are scored against the last taxon without ever being stored.
+		const unsigned before = S->ntrees_dev;
+		rc = launch_fused(ctx, S, m, 0, 0xffffffffu);
+		if (rc) return rc;
+		rc = fetch_counters(ctx, S);
+		if (rc) return rc;
+		const unsigned ns = S->h_pin[1];
+		if (S->h_pin[2] > S->trees_cap) {
+			// The tree buffer overflowed and records were dropped: put the counter back, make room and
+			// redo the survivors in halves (emission is idempotent: records carry their own length).
+			struct Range { unsigned lo, hi; };
+			std::vector<Range> todo;
+			todo.push_back(Range{0, ns});
+			S->ntrees_dev = before;
+			while (!todo.empty()) {
+				Range r = todo.back();
+				todo.pop_back();
+				rc = drain_trees(ctx, S);
+				if (rc) return rc;
+				rc = launch_fused(ctx, S, m, r.lo, r.hi);
+				if (rc) return rc;
+				rc = fetch_counters(ctx, S);
+				if (rc) return rc;
+				if (S->h_pin[2] > S->trees_cap) {
+					if (r.hi - r.lo < 2) return set_error(XMP_ERR_NOMEM, "tree buffer too small for a single partial tree's completions");
+					const unsigned mid = r.lo + (r.hi - r.lo) / 2;
+					todo.push_back(Range{mid, r.hi});
+					todo.push_back(Range{r.lo, mid});
+					S->ntrees_dev = 0;
+					XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+					continue;
+				}
+				S->st.full_trees += S->h_pin[2];
+				S->ntrees_dev = S->h_pin[2];
+			}
+		} else {
+			S->st.full_trees += S->h_pin[2] - before;
+			S->ntrees_dev = S->h_pin[2];
+		}
+		S->st.children += ns;
+		S->st.nodes += ns;
+		S->st.score_calls += (unsigned long long) ns * (P.E + 2);
+		P.count -= chunk;
+		return tidy_trees(ctx, S);
 	}
 	rc = launch_children(ctx, S, m);
 	if (rc) return rc;
@@ -629,8 +840,10 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		for (unsigned m = S->n - 1; m >= 3; --m) {
 			Pool &P = S->pool[m];
 			if (P.count == 0) continue;
-			unsigned long long room = (m + 1 == S->n) ? (S->trees_cap - S->ntrees_dev) / P.E
-			                                          : (S->pool[m + 1].cap - S->pool[m + 1].count) / P.E;
+			unsigned long long room;
+			if (m + 1 == S->n) room = (S->trees_cap - S->ntrees_dev) / P.E;
+			else if (S->fused_last && m + 2 == S->n) room = S->surv_cap / P.E;     // survivors are consumed in place
+			else room = (S->pool[m + 1].cap - S->pool[m + 1].count) / P.E;
 			unsigned long long chunk = std::min(P.count, room);
 			if (chunk == 0) continue;
 			if (fallback < 0) { fallback = (int) m; fallback_chunk = chunk; }

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libxmp_b200.so")
 _LIB = None
 NO_LIMIT = 0x7FFFFFFF
 SEARCH_NO_DIVE = 1
+SEARCH_NO_FUSE = 2
 
 EXPORTS = [
     "xmp_cuda_last_error", "xmp_cuda_device_count", "xmp_cuda_init", "xmp_cuda_destroy", "xmp_cuda_set_stream",

@@ -13,7 +13,7 @@ Differences from the reference, by design:
   * termination: the all-gathered counts are all zero.
 
 The engine is any object with the search_* methods of xmp_b200.cuda.Context; the CPU tests drive the
-same protocol over gloo with an oracle-backed stand-in.
+same protocol over gloo with a CPU stand-in engine (tests/test_distributed.py).
 """
 import numpy as np
 import torch
