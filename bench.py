@@ -321,6 +321,7 @@ def run_ours(args):
     wl = make_workload(torch, n_trees, M, dev, seed_offset=rank)
     # Launch on a torch side stream so that torch.cuda.Event brackets exactly our kernels (the default
     # stream's handle is 0, which the C ABI reads as "use the context's own stream").
+    torch.cuda.synchronize()         # the workload above was generated on torch's default stream
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     ctx = xc.Context(local, stream=side.cuda_stream)

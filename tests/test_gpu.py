@@ -113,6 +113,7 @@ def test_score_batch_matches_oracle(ctx, torch, n_blocks, weighted):
     d_surv = torch.full((n_pairs,), -1, dtype=torch.int32, device="cuda")
     d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
     taxon = 4
+    torch.cuda.synchronize()     # torch filled the buffers on its own stream; the library launches on another
     want = oracle_costs(rows, weights, sets, taxon)
     bound = int(np.median(want + base[np.arange(n_pairs) // ppt])) + int(rest[taxon])
     ctx.score_batch(d_sets, n_pairs, ppt, taxon, d_cost, d_base, bound, d_surv, d_n)
@@ -136,16 +137,19 @@ def test_score_batch_empty_and_single(ctx, torch):
     d_n = torch.ones(1, dtype=torch.int32, device="cuda")
     d_cost = torch.zeros(1, dtype=torch.int32, device="cuda")
     d_surv = torch.zeros(1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     ctx.score_batch(None, 0, 1, 3, d_cost, None, 5, d_surv, d_n)
     ctx.synchronize()
     assert int(d_n.item()) == 0
     one = torch.from_numpy(rows[1].copy()).cuda()
+    torch.cuda.synchronize()
     ctx.score_batch(one, 1, 1, 3, d_cost)
     ctx.synchronize()
     assert int(d_cost.item()) == O.xo_fitch_score_weight1(ol.p(rows[1]), ol.p(rows[3]), 32)
 
 
-@pytest.mark.parametrize("m,n_blocks,weighted", [(3, 2, True), (4, 1, False), (8, 5, True), (13, 40, True), (20, 3, False), (40, 2, True), (64, 2, False)])
+@pytest.mark.parametrize("m,n_blocks,weighted", [(3, 2, True), (4, 1, False), (8, 5, True), (13, 40, True), (20, 3, False), (40, 2, True), (64, 2, False),
+                                                  (8, 300, True), (13, 513, False), (20, 256, True), (40, 257, False)])
 def test_build_midpoints_and_insertion_costs(ctx, torch, m, n_blocks, weighted):
     rng = np.random.default_rng(m * 31 + n_blocks)
     num_taxa, n_trees = m + 1, 37
@@ -157,6 +161,7 @@ def test_build_midpoints_and_insertion_costs(ctx, torch, m, n_blocks, weighted):
     E = 2 * m - 3
     d_mid = torch.zeros((n_trees, E, nbytes), dtype=torch.uint8, device="cuda")
     d_len = torch.zeros(n_trees, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     ctx.build_midpoints(paths, m, d_mid, d_len)
     ctx.synchronize()
     got_mid = d_mid.cpu().numpy()
@@ -387,10 +392,12 @@ def test_full_size_microbench_properties(ctx, torch):
     few trees; the rest is checked through size-independent properties of the scores."""
     import bench
     wl = bench.make_workload(torch, n_trees=64, m=8)
+    torch.cuda.synchronize()
     ctx.load(wl["d_rows"])
     ctx.build_midpoints(wl["paths"], wl["m"], wl["d_mid"])
     n_pairs = wl["n_pairs"]
     d_cost = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     ctx.score_batch(wl["d_mid"], n_pairs, wl["E"], wl["m"], d_cost)
     ctx.synchronize()
     cost = d_cost.cpu().numpy().reshape(-1, wl["E"])
@@ -402,6 +409,7 @@ def test_full_size_microbench_properties(ctx, torch):
     # (2) scoring a taxon against its own leaf edge costs 0; against another taxon's leaf edge it is
     #     their Hamming distance when the leaf's DOWN set does not help, never more
     d_self = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
     ctx.score_batch(wl["d_mid"], n_pairs, wl["E"], 1, d_self)
     ctx.synchronize()
     assert (d_self.cpu().numpy().reshape(-1, wl["E"])[:, 0] == 0).all()    # edge 0 = leaf of taxon 1
@@ -410,12 +418,13 @@ def test_full_size_microbench_properties(ctx, torch):
     lo = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
     d_mid = wl["d_mid"].view(n_pairs, wl["n_blocks"] * 16)
     c2 = __import__("xmp_b200.cuda", fromlist=["Context"]).Context(0)
-    c2.load(wl["d_rows"][:, :half * 16].contiguous())
-    c2.score_batch(d_mid[:, :half * 16].contiguous(), n_pairs, wl["E"], wl["m"], lo)
-    c2.synchronize()
     hi = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")
-    c2.load(wl["d_rows"][:, half * 16:].contiguous())
-    c2.score_batch(d_mid[:, half * 16:].contiguous(), n_pairs, wl["E"], wl["m"], hi)
-    c2.synchronize()
+    parts = [(wl["d_rows"][:, :half * 16].contiguous(), d_mid[:, :half * 16].contiguous(), lo),
+             (wl["d_rows"][:, half * 16:].contiguous(), d_mid[:, half * 16:].contiguous(), hi)]
+    torch.cuda.synchronize()
+    for r, s_, out in parts:
+        c2.load(r)
+        c2.score_batch(s_, n_pairs, wl["E"], wl["m"], out)
+        c2.synchronize()
     assert ((lo + hi).cpu().numpy().reshape(-1, wl["E"]) == cost).all()
     c2.close()

@@ -129,11 +129,15 @@ extern "C" int xmp_cuda_init(int device, xmp_ctx **out) {
 	return XMP_OK;
 }
 
-static void free_problem(xmp_ctx *ctx) {
-	if (ctx->d_rows_owned) cudaFree(ctx->d_rows_owned);
+// keep_rows: leave the owned row buffer in place so that a reload of the same shape reuses it.
+static void free_problem(xmp_ctx *ctx, bool keep_rows = false) {
+	if (ctx->d_rows_owned && !keep_rows) {
+		cudaFree(ctx->d_rows_owned);
+		ctx->d_rows_owned = nullptr;
+		ctx->rows_owned_bytes = 0;
+	}
 	if (ctx->d_planes) cudaFree(ctx->d_planes);
 	if (ctx->d_rest_bound) cudaFree(ctx->d_rest_bound);
-	ctx->d_rows_owned = nullptr;
 	ctx->d_rows = nullptr;
 	ctx->d_planes = nullptr;
 	ctx->d_rest_bound = nullptr;
@@ -201,9 +205,6 @@ static int load_common(xmp_ctx *ctx, const unsigned *weights, unsigned num_taxa,
 	ctx->wp = WeightPlanes{ctx->d_planes, n_words, heavy_words, n_planes};
 	memset(ctx->rest_bound, 0, sizeof ctx->rest_bound);
 	if (rest_bound) memcpy(ctx->rest_bound, rest_bound, num_taxa * sizeof(unsigned));
-	XMP_CUDA(cudaMalloc(&ctx->d_rest_bound, (XMP_MAX_TAXA + 1) * sizeof(unsigned)));
-	XMP_CUDA(cudaMemcpyAsync(ctx->d_rest_bound, ctx->rest_bound, (XMP_MAX_TAXA + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->real_sites = (unsigned long long) n_blocks * 32;
 	return XMP_OK;
 }
@@ -213,11 +214,14 @@ extern "C" int xmp_cuda_load(xmp_ctx *ctx, const void *rows, const unsigned *wei
 	if (!ctx || !rows) return set_error(XMP_ERR_ARG, "null argument");
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	search_destroy(ctx);
-	free_problem(ctx);
+	const size_t bytes = (size_t) num_taxa * n_blocks * 16;
+	free_problem(ctx, ctx->rows_owned_bytes >= bytes);
 	int rc = load_common(ctx, weights, num_taxa, n_blocks, rest_bound, constant_weight);
 	if (rc) return rc;
-	const size_t bytes = (size_t) num_taxa * n_blocks * 16;
-	XMP_CUDA(cudaMalloc(&ctx->d_rows_owned, bytes));
+	if (!ctx->d_rows_owned) {
+		XMP_CUDA(cudaMalloc(&ctx->d_rows_owned, bytes));
+		ctx->rows_owned_bytes = bytes;
+	}
 	XMP_CUDA(cudaMemcpyAsync(ctx->d_rows_owned, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->d_rows = ctx->d_rows_owned;
@@ -311,6 +315,20 @@ extern "C" int xmp_cuda_score_insertions_host(xmp_ctx *ctx, const uint8_t *paths
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	const unsigned E = 2 * m - 3;
 	const size_t n_pairs = (size_t) n_trees * E;
+	if (ctx->n_blocks >= 256) {
+		// Wide state sets: topologies -> costs in one fused pass, nothing but the costs touches HBM.
+		unsigned stride = 0;
+		int rc = upload_topologies(ctx, paths, path_stride, n_trees, m, ctx->scratch, &stride);
+		if (rc) return rc;
+		rc = ctx->scratch2.reserve(n_pairs * sizeof(unsigned) + 256);
+		if (rc) return rc;
+		unsigned *d_cost = (unsigned *) ctx->scratch2.ptr;
+		rc = launch_score_trees_wide(ctx, (const uint8_t *) ctx->scratch.ptr, stride, n_trees, m, m, d_cost);
+		if (rc) return rc;
+		XMP_CUDA(cudaMemcpyAsync(cost_out, d_cost, n_pairs * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+		return XMP_OK;
+	}
 	const size_t set_bytes = n_pairs * ctx->n_blocks * 16;
 	int rc = ctx->scratch2.reserve(set_bytes + n_pairs * sizeof(unsigned) + 256);
 	if (rc) return rc;

@@ -54,6 +54,7 @@ struct xmp_ctx {
 	unsigned num_taxa = 0, n_blocks = 0, num_sites_padded = 0;
 	const uint4 *d_rows = nullptr;      // [num_taxa][n_blocks]
 	uint4 *d_rows_owned = nullptr;
+	size_t rows_owned_bytes = 0;
 	unsigned *d_planes = nullptr;
 	xmp::WeightPlanes wp{nullptr, 0, 0, 0};
 	unsigned *d_rest_bound = nullptr;
@@ -79,5 +80,7 @@ int launch_score_sets(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree
 // rec_blocks = uint4 per tree record; kinds: MID at 0, UP at E*W, DOWN at 2*E*W when store_all.
 int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
                       uint4 *d_out, size_t rec_blocks, bool store_all, unsigned *d_tree_len);
+int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
+                            unsigned taxon, unsigned *d_cost);
 void search_destroy(xmp_ctx *ctx);
 }  // namespace xmp

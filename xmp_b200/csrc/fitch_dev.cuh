@@ -96,6 +96,28 @@ __device__ __forceinline__ unsigned warp_append(bool keep, unsigned *counter) {
 	return base + __popc(ballot & ((1u << lane) - 1u));
 }
 
+// Block-aggregated append for 256-thread CTAs: ONE atomic on *counter per CTA instead of one per warp.
+// A counter that every warp of a large grid bumps serialises at a single L2 slice (~0.5 ns per atomic):
+// at 64 K warps per launch that alone was most of the scoring kernel's time on small batches.
+// Must be called by all threads of the block.
+__device__ __forceinline__ unsigned block_append(bool keep, unsigned *counter, unsigned *s_warp /*[9]*/) {
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+	const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+	if (lane == 0) s_warp[warp] = (unsigned) __popc(ballot);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned total = 0;
+		for (unsigned w = 0; w < n_warps; ++w) {
+			unsigned c = s_warp[w];
+			s_warp[w] = total;
+			total += c;
+		}
+		s_warp[8] = total ? atomicAdd(counter, total) : 0u;
+	}
+	__syncthreads();
+	return s_warp[8] + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+}
+
 // Edge-id helpers (include/xmp_cuda.h "Edge ids").
 __device__ __host__ __forceinline__ bool edge_is_leaf(unsigned e) { return e == 0 || (e & 1u); }
 __device__ __host__ __forceinline__ unsigned edge_taxon(unsigned e) { return (e + 3u) >> 1; }

@@ -256,6 +256,79 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Topologies -> insertion costs in one pass, for wide state sets: the MIDPOINT sets are formed in
+// registers / local arrays and scored at once, never written to HBM (saves 1.5 B written + 0.5 B read
+// per site-merge against k_build_sets followed by k_score_wide).  One CTA = one tree x 256 columns, so
+// every lane of a warp follows the same topology (coalesced local arrays); per-edge costs are summed by
+// warp shuffle, then shared-memory atomics, then one global RED per (tree, edge, tile).
+// ---------------------------------------------------------------------------------------------
+template <int MAXE>
+__global__ void __launch_bounds__(256)
+k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp, const uint8_t *__restrict__ topo,
+                   unsigned topo_stride, unsigned m, unsigned taxon, unsigned *__restrict__ cost) {
+	__shared__ unsigned acc[MAXE];
+	__shared__ uint8_t s_par[MAXE], s_k0[MAXE], s_k1[MAXE], s_pre[MAXE];
+	const unsigned tree = blockIdx.y, E = 2 * m - 3;
+	const unsigned col = blockIdx.x * 256u + threadIdx.x;
+	const bool ok = col < n_blocks;
+	const uint8_t *t = topo + (size_t) tree * 4 * topo_stride;
+	for (unsigned i = threadIdx.x; i < E; i += 256) {
+		s_par[i] = t[i];
+		s_k0[i] = t[topo_stride + i];
+		s_k1[i] = t[2 * topo_stride + i];
+		s_pre[i] = t[3 * topo_stride + i];
+		acc[i] = 0;
+	}
+	__syncthreads();
+	const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+	uint4 up[MAXE], down[MAXE];
+	for (int i = (int) E - 1; i >= 0; --i) {
+		const unsigned e = s_pre[i];
+		if (edge_is_leaf(e)) up[e] = ok ? __ldg(rows + (size_t) edge_taxon(e) * n_blocks + col) : ones;
+		else up[e] = fitch_block(up[s_k0[e]], up[s_k1[e]]);
+	}
+	const uint4 r0 = ok ? __ldg(rows + col) : ones;
+	const uint4 rx = ok ? __ldg(rows + (size_t) taxon * n_blocks + col) : ones;
+	for (unsigned i = 0; i < E; ++i) {
+		const unsigned e = s_pre[i], p = s_par[e];
+		uint4 d;
+		if (p == 0xFFu) {
+			d = r0;
+		} else {
+			const unsigned sib = (s_k0[p] == e) ? s_k1[p] : s_k0[p];
+			d = fitch_block(down[p], up[sib]);
+		}
+		down[e] = d;
+		unsigned c = cost_block(fitch_block(up[e], d), rx, ok ? col : 0u, wp);
+		c = warp_sum(ok ? c : 0u);
+		if ((threadIdx.x & 31u) == 0 && c) atomicAdd(&acc[e], c);
+	}
+	__syncthreads();
+	for (unsigned e = threadIdx.x; e < E; e += 256) {
+		if (acc[e]) atomicAdd(cost + (size_t) tree * E + e, acc[e]);
+	}
+}
+
+// cost[tree][edge] of inserting `taxon` on every edge of trees whose topologies are in d_topo.
+int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
+                            unsigned taxon, unsigned *d_cost) {
+	const unsigned E = 2 * m - 3;
+	XMP_CUDA(cudaMemsetAsync(d_cost, 0, (size_t) n_trees * E * sizeof(unsigned), ctx->stream));
+	for (unsigned t0 = 0; t0 < n_trees; t0 += 65535u) {
+		const unsigned nt = n_trees - t0 < 65535u ? n_trees - t0 : 65535u;
+		dim3 grid((ctx->n_blocks + 255) / 256, nt);
+		const uint8_t *topo = d_topo + (size_t) t0 * 4 * topo_stride;
+		unsigned *cost = d_cost + (size_t) t0 * E;
+		if (E <= 16) k_score_trees_wide<16><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
+		else if (E <= 32) k_score_trees_wide<32><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
+		else if (E <= 72) k_score_trees_wide<72><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
+		else k_score_trees_wide<200><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
+	}
+	XMP_CUDA(cudaGetLastError());
+	return XMP_OK;
+}
+
 int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m, uint4 *d_out,
                       size_t rec_blocks, bool store_all, unsigned *d_tree_len) {
 	if (n_trees == 0) return XMP_OK;

@@ -24,6 +24,7 @@
 // Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
 // recorded carries its length and the final filter keeps those equal to the final bound.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include "ctx.h"
 
@@ -59,6 +60,8 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
                const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned rest, unsigned *bound_ptr, int last,
                uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
                unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
+	__shared__ unsigned s_bound, s_warp[9];
+	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
 	const unsigned E = 2 * m - 3;
 	const unsigned long long gthread = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned long long pair = gthread / G;
@@ -67,6 +70,7 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	const unsigned long long node = first + pair / E;
 	const unsigned e = (unsigned) (pair % E);
 	unsigned s = 0;
+	__syncthreads();
 	if (valid) {
 		const uint4 *src = pool.sets + node * pool.rec + (unsigned long long) e * L.W;
 		for (unsigned b = sub; b < L.W; b += G) s += cost_block(src[b], __ldg(taxon_row + b), b, wp);
@@ -79,14 +83,13 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	const uint8_t *hdr = pool.hdr + node * L.HB;
 	if (valid && sub == 0) {
 		const unsigned score = *(const unsigned *) hdr;
-		const unsigned bound = *(volatile unsigned *) bound_ptr;
-		keep = accept_insertion(s, bound, score, rest);
+		keep = accept_insertion(s, s_bound, score, rest);
 		new_score = score + s;
 		if (keep && shard_count > 1) keep = (path_hash(hdr + HDR_PATH, m, e) % shard_count) == shard_index;
 	}
 	if (last) {
-		if (keep) atomicMin(bound_ptr, new_score);
-		unsigned slot = warp_append(keep, n_trees);
+		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
+		unsigned slot = block_append(keep, n_trees, s_warp);
 		if (keep && slot < trees_cap) {
 			uint8_t *rec = trees + (size_t) slot * L.trec;
 			*(unsigned *) rec = new_score;
@@ -94,7 +97,7 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 			rec[4 + m] = (uint8_t) e;
 		}
 	} else {
-		unsigned slot = warp_append(keep, n_surv);
+		unsigned slot = block_append(keep, n_surv, s_warp);
 		if (keep) surv[slot] = make_uint4((unsigned) node, e, new_score, 0u);
 	}
 }
@@ -107,6 +110,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	const unsigned n_surv = *n_surv_ptr;
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, a = E, b = E + 1;
 	const unsigned long long total = (unsigned long long) n_surv * W;
+	unsigned my_merges = 0;
 	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
 	     idx += (unsigned long long) gridDim.x * blockDim.x) {
 		const unsigned s = (unsigned) (idx / W), col = (unsigned) (idx % W);
@@ -201,9 +205,12 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 			if (pv != 0xFFu) {
 				if (pk0[pv] == v) ck0[pv] = (uint8_t) b; else ck1[pv] = (uint8_t) b;
 			}
-			atomicAdd(merges, (unsigned long long) (n_up + 2 * Ec));
+			my_merges += n_up + 2 * Ec;
 		}
 	}
+	// statistics: one atomic per warp that did any work, not one per child
+	my_merges = warp_sum(my_merges);
+	if ((threadIdx.x & 31u) == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
 }
 
 
@@ -241,6 +248,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	const uint4 r0 = __ldg(rows + col);
 	const uint4 rt = __ldg(rows + (size_t) m * W + col);
 	const uint4 rl = __ldg(rows + (size_t) (m + 1) * W + col);
+	unsigned my_merges = 0;
 	for (unsigned long long s = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + threadIdx.x / G; s < n_surv;
 	     s += (unsigned long long) gridDim.x * groups_per_block) {
 		const uint4 sv = surv[s];
@@ -293,7 +301,14 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			return __ldg(PU + (size_t) y * W);
 		};
 
-		const unsigned bound = *(volatile unsigned *) bound_ptr;
+		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
+		unsigned bound = 0;
+		{
+			const unsigned active = __activemask();
+			const int leader = __ffs(active) - 1;
+			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
+			bound = __shfl_sync(active, bound, leader);
+		}
 		unsigned depth = 0;
 		for (unsigned x = top;;) {
 			const unsigned p = par_of(x);
@@ -310,7 +325,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
 			if (sub == 0 && accept_insertion(c, bound, score, rest_last)) {
-				atomicMin(bound_ptr, score + c);
+				if (score + c < bound) atomicMin(bound_ptr, score + c);
 				const unsigned slot = atomicAdd(n_trees, 1u);
 				if (slot < trees_cap) {
 					uint8_t *rec = trees + (size_t) slot * L.trec;
@@ -336,8 +351,10 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			}
 			if (finished) break;
 		}
-		if (sub == 0) atomicAdd(merges, (unsigned long long) (k + 2 * Ec));
+		if (sub == 0) my_merges += k + 2 * Ec;
 	}
+	my_merges = warp_sum(my_merges);
+	if (lane == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
 }
 
 // Headers for nodes whose sets were built from topologies (the root job, imported jobs).
@@ -401,12 +418,21 @@ struct Search {
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
+	unsigned min_batch = 32768, beam = 512, policy = 1;
 	xmp_search_stats st;
 	Scratch topo, pathbuf;
 };
 
-static const unsigned kMinBatchNodes = 4096;   // prefer levels holding at least this many open trees
-static const unsigned kBeam = 64;              // width of the initial greedy dive
+// Scheduler knobs (defaults chosen on B200, see profiles/r01_search_tuning.md; overridable for tuning
+// through XMP_MIN_BATCH / XMP_BEAM): prefer levels holding at least min_batch open trees; width of the
+// initial greedy dive.
+static unsigned env_unsigned(const char *name, unsigned dflt) {
+	const char *v = getenv(name);
+	if (!v || !*v) return dflt;
+	char *end = nullptr;
+	unsigned long x = strtoul(v, &end, 10);
+	return end != v ? (unsigned) x : dflt;
+}
 
 static double odd_factorial(unsigned m) {      // number of distinct trees on m taxa: (2m-5)!!
 	double t = 1;
@@ -456,7 +482,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 
 	// The deepest pool is skipped when the last two levels are fused (narrow state sets): it then only
 	// ever holds imported jobs.
-	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 4 && n >= 5 && n <= 41;
+	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 32 && n >= 5 && n <= 41;
 	const double last_cap = S->fused_last ? 1024.0 : 1e300;
 	// Largest per-level capacity C such that all pools fit; a level never needs more than (2m-5)!! nodes.
 	auto bytes_for = [&](double C) {
@@ -485,7 +511,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.HB));
 		XMP_CUDA(cudaMalloc(&P.sets, (size_t) P.cap * P.rec * 16));
 	}
-	S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) kBeam * Emax);
+	S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) S->beam * Emax);
 	XMP_CUDA(cudaMalloc(&S->d_surv, (size_t) S->surv_cap * 16));
 	XMP_CUDA(cudaMalloc(&S->d_trees[0], (size_t) S->trees_cap * L.trec));
 	XMP_CUDA(cudaMalloc(&S->d_trees[1], (size_t) S->trees_cap * L.trec));
@@ -600,7 +626,10 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
-	else XMP_FUSED(4);
+	else if (L.W <= 4) XMP_FUSED(4);
+	else if (L.W <= 8) XMP_FUSED(8);
+	else if (L.W <= 16) XMP_FUSED(16);
+	else XMP_FUSED(32);
 #undef XMP_FUSED
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
@@ -766,7 +795,7 @@ static int dive(xmp_ctx *ctx, Search *S) {
 	if (rc) return rc;
 	for (unsigned m = 3; m < S->n; ++m) {
 		if (S->pool[m].count == 0) break;
-		rc = run_batch(ctx, S, m, S->pool[m].count, kBeam);
+		rc = run_batch(ctx, S, m, S->pool[m].count, S->beam);
 		if (rc) return rc;
 	}
 	for (unsigned m = 3; m < S->n; ++m) S->pool[m].count = 0;
@@ -792,6 +821,9 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
 	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
 	S->n = ctx->num_taxa;
+	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
+	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
+	S->policy = env_unsigned("XMP_POLICY", 1);
 	memset(&S->st, 0, sizeof S->st);
 	int rc = alloc_search(ctx, S);
 	if (rc) { search_destroy(ctx); return rc; }
@@ -834,7 +866,8 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 	unsigned batches = 0;
 	int rc = XMP_OK;
 	while (!S->done && (max_batches == 0 || batches < max_batches)) {
-		// Deepest level holding a worthwhile batch; otherwise the deepest non-empty one.
+		// Deepest level holding a worthwhile batch; otherwise the fullest one (policy 1, default).
+		// Policy 0 falls back to the deepest non-empty level, policy 2 always takes the fullest.
 		int pick = -1, fallback = -1;
 		unsigned long long pick_chunk = 0, fallback_chunk = 0;
 		for (unsigned m = S->n - 1; m >= 3; --m) {
@@ -846,8 +879,13 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 			else room = (S->pool[m + 1].cap - S->pool[m + 1].count) / P.E;
 			unsigned long long chunk = std::min(P.count, room);
 			if (chunk == 0) continue;
-			if (fallback < 0) { fallback = (int) m; fallback_chunk = chunk; }
-			if (chunk >= kMinBatchNodes) { pick = (int) m; pick_chunk = chunk; break; }
+			if (S->policy == 0) {
+				if (fallback < 0) { fallback = (int) m; fallback_chunk = chunk; }
+			} else if (chunk > fallback_chunk) {
+				fallback = (int) m;
+				fallback_chunk = chunk;
+			}
+			if (S->policy != 2 && chunk >= S->min_batch) { pick = (int) m; pick_chunk = chunk; break; }
 		}
 		if (pick < 0) { pick = fallback; pick_chunk = fallback_chunk; }
 		if (pick < 0) {
