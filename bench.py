@@ -393,6 +393,7 @@ def run_ours(args):
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0].item()), float(t[1].item())
+    int_peak = ctx.int_pipe_peak() if rank == 0 else None
     bandb = None
     if not args.no_bandb:
         bandb = run_bandb(torch, xc, dist, rank, world, local, BANDB_DATASETS)
@@ -436,7 +437,13 @@ def run_ours(args):
                      "note": "launch_ms is the median CUDA-event time of one step = k_score_wide + k_prune + two 4-byte/213-KB memsets; "
                              "the ncu launch list under profiles/ gives k_score_wide's share"},
     }
+    out["int_pipe_peak"] = {"unit": "Gsite-ops/s", "what": "register-resident microbenchmark of the Fitch instruction mixes on this GPU "
+                            "(xmp_cuda_int_pipe_peak): the integer roofline for narrow state sets; the wide scoring kernel above "
+                            "runs at %.1f %% of the weight-1 cost rate, i.e. it is HBM-bound, not ALU-bound" % (100.0 * value / world / int_peak["cost_w1"]),
+                            **int_peak}
     if bandb is not None:
+        for b in bandb:
+            b["frac_of_int_pipe_merge_cost_peak"] = b["gsite_merges_per_s"] / world / int_peak["merge_cost"]
         out["bandb"] = {"what": "exact branch and bound, default -Bd bound, time from upload to proven optimum with the full MP set "
                                 "(wall clock around barriers, max over ranks); reference_cpu_* are the reference's serial fastc64 "
                                 "program measured when the goldens were generated (tests/golden/datasets.json)",

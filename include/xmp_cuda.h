@@ -161,6 +161,13 @@ int xmp_cuda_search_import_jobs(xmp_ctx *ctx, const uint8_t *jobs, unsigned n_jo
 int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned long long *n_trees, uint8_t *paths, size_t cap);
 int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aid: what the integer pipe sustains on the Fitch instruction mixes with operands in
+ * registers (no memory traffic), in G site-operations per second: out[0] weight-1 cost, out[1] merge
+ * (FitchBases), out[2] merge + cost.  The denominator of the integer roofline.
+ * ---------------------------------------------------------------------------------------------- */
+int xmp_cuda_int_pipe_peak(xmp_ctx *ctx, double *out);
+
 #ifdef __cplusplus
 }
 #endif

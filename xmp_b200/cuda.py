@@ -26,7 +26,7 @@ EXPORTS = [
     "xmp_cuda_score_insertions_host",
     "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
-    "xmp_cuda_search_result", "xmp_cuda_search_stats",
+    "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
         L.xmp_cuda_search_import_jobs.argtypes = [vp, vp, u]
         L.xmp_cuda_search_result.argtypes = [vp, C.POINTER(u), C.POINTER(C.c_ulonglong), vp, sz]
         L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
+        L.xmp_cuda_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
         for name in ("FitchBases_b2_w16_cuda",):
             getattr(L, name).restype = None
         L.FitchBases_b2_w16_cuda.argtypes = [vp, vp, vp, u]
@@ -173,6 +174,12 @@ class Context:
             out = np.empty((n, 2 * m - 3), dtype=np.uint32)
         _check(lib().xmp_cuda_score_insertions_host(self._h, _ptr(paths), paths.shape[1], n, m, _ptr(out)))
         return out
+
+    def int_pipe_peak(self):
+        """G site-operations/s the integer pipe sustains: {'cost_w1', 'merge', 'merge_cost'}."""
+        out = (C.c_double * 3)()
+        _check(lib().xmp_cuda_int_pipe_peak(self._h, out))
+        return {"cost_w1": out[0], "merge": out[1], "merge_cost": out[2]}
 
     # ---- search ----
     def search_begin(self, bound=NO_LIMIT, max_trees=NO_LIMIT, mem_budget=0, shard_index=0, shard_count=1,

@@ -8,8 +8,8 @@ Differences from the reference, by design:
     worker -> boss -> all workers point-to-point relays (src/mpiboss.c:162-171, src/mpiworker.c:19-41);
   * work stealing is decided collectively from an all-gather of the open-node counts: ranks that ran
     dry receive job descriptors (insertion paths, a few hundred bytes) from the ranks holding the most
-    open subtrees, point-to-point (over NVLink with the nccl backend); the thief rebuilds the subtree
-    state from the descriptor alone, as the reference's fast-forward does (src/yanbader.c:136-143);
+    open subtrees through one more all-gather (over NVLink with the nccl backend); the thief rebuilds the
+    subtree state from the descriptor alone, as the reference's fast-forward does (src/yanbader.c:136-143);
   * termination: the all-gathered counts are all zero.
 
 The engine is any object with the search_* methods of xmp_b200.cuda.Context; the CPU tests drive the
@@ -27,48 +27,59 @@ def _t(x, device, dtype=torch.int64):
 def sharded_search(engine, num_taxa, device="cpu", slice_batches=64, steal_nodes=256, group=None, on_round=None):
     """Runs engine (already search_begin()'ed with this rank's shard_index / shard_count) to completion
     together with the other ranks.  Returns (score, total number of optimal trees, this rank's optimal
-    paths, number of rounds).  Every rank returns the same score and total."""
+    paths, number of rounds).  Every rank returns the same score and total.
+
+    One collective per round (an all-gather of [bound, open subtrees] per rank) plus, only in rounds
+    where some rank ran dry, one all-gather of job descriptors.  Point-to-point send/recv is avoided on
+    purpose: with NCCL every new (donor, thief) pair pays a connection set-up of ~100 ms, more than a
+    whole search of the hard datasets takes."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     rounds = 0
     done = False
+    rec = num_taxa + 1
+    state = torch.zeros(world * 2, dtype=torch.int64, device=device)          # flat: gloo wants 1-D outputs
+    outbox = torch.zeros(steal_nodes * rec, dtype=torch.uint8, device=device)
+    inbox = torch.zeros(world * steal_nodes * rec, dtype=torch.uint8, device=device)
     while True:
         if not done:
             done = engine.search_run(slice_batches)
-        # upper bound: all-reduce(min) of one word
-        b = _t([engine.search_get_bound()], device)
-        dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
-        engine.search_set_bound(int(b.item()))
-        # open subtrees per rank
-        mine = int(np.asarray(engine.search_pending()).sum())
-        counts = [_t([0], device) for _ in range(world)]
-        dist.all_gather(counts, _t([mine], device), group=group)
-        counts = [int(c.item()) for c in counts]
+        mine = torch.tensor([engine.search_get_bound(), int(np.asarray(engine.search_pending()).sum())], dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(state, mine, group=group)
+        st = state.cpu().numpy().reshape(world, 2)
+        bound = int(st[:, 0].min())                       # upper bound: min over ranks
+        counts = [int(c) for c in st[:, 1]]
+        engine.search_set_bound(bound)
         rounds += 1
         if on_round:
-            on_round(rounds, counts, int(b.item()))
+            on_round(rounds, counts, bound)
         if sum(counts) == 0:
             break
         # collective steal plan, identical on every rank: the i-th idle rank takes from the i-th richest
         idle = [r for r in range(world) if counts[r] == 0]
         donors = sorted((r for r in range(world) if counts[r] > 1), key=lambda r: (-counts[r], r))
-        plan = [(donors[i % len(donors)], thief) for i, thief in enumerate(idle)] if donors else []
-        for donor, thief in plan:
-            if rank == donor:
-                jobs = engine.search_export_jobs(min(steal_nodes, max(1, counts[donor] // (2 * max(1, len(idle))))))
-                n = _t([len(jobs)], device)
-                dist.send(n, thief, group=group)
-                if len(jobs):
-                    dist.send(torch.from_numpy(np.ascontiguousarray(jobs)).to(device), thief, group=group)
-            elif rank == thief:
-                n = _t([0], device)
-                dist.recv(n, donor, group=group)
-                k = int(n.item())
-                if k:
-                    buf = torch.zeros((k, num_taxa), dtype=torch.uint8, device=device)
-                    dist.recv(buf, donor, group=group)
-                    engine.search_import_jobs(buf.cpu().numpy())
-                    done = False
+        if not idle or not donors:
+            continue
+        plan = [(donors[i % len(donors)], thief) for i, thief in enumerate(idle)]
+        out = np.zeros((steal_nodes, num_taxa + 1), dtype=np.uint8)     # column 0: destination rank + 1 (0 = empty slot)
+        mine_out = [thief for donor, thief in plan if donor == rank]
+        used = 0
+        for thief in mine_out:
+            want = min((steal_nodes - used), max(1, counts[rank] // (2 * (len(mine_out) + 1))))
+            if want <= 0:
+                break
+            jobs = engine.search_export_jobs(want)
+            out[used:used + len(jobs), 0] = thief + 1
+            out[used:used + len(jobs), 1:] = jobs
+            used += len(jobs)
+        outbox.copy_(torch.from_numpy(out.reshape(-1)))
+        dist.all_gather_into_tensor(inbox, outbox, group=group)
+        if rank in idle:
+            got = inbox.cpu().numpy().reshape(-1, num_taxa + 1)
+            jobs = got[got[:, 0] == rank + 1][:, 1:]
+            if len(jobs):
+                engine.search_import_jobs(np.ascontiguousarray(jobs))
+                done = False
     score, n, paths = engine.search_result()
     tot = _t([n], device)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
