@@ -34,10 +34,13 @@ struct Layout {
 	unsigned n;        // taxa in the problem
 	unsigned W;        // 128-bit blocks per state set
 	unsigned HB;       // header bytes (multiple of 16)
-	unsigned off_par, off_k0, off_k1;   // byte offsets of the topology arrays inside a header
+	unsigned off_par, off_sib, off_pos, off_size;   // byte arrays over edge ids inside a header
+	unsigned off_prog;                               // u32 per pre-order position: edge | sibling << 8 | depth << 16
 	unsigned trec;     // bytes per emitted tree record: score + path
 };
-// Header: [0,4) score | [4,4+n) path (byte 0 of it = the root's child) | par[] | kid0[] | kid1[]
+// Header: [0,4) score | [4,4+n) path (byte 0 of it = the root's child) | par[] sib[] pos[] size[] | prog[]
+// The "walk program" prog[] is the tree in pre-order with everything a top-down pass needs per step, so
+// that the kernels below run one uniform loop per child instead of chasing parent / child links.
 #define HDR_PATH 4u
 
 struct PoolView {
@@ -102,13 +105,104 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	}
 }
 
+// ---- walking a child tree ----------------------------------------------------------------------------
+// The child of parent node P obtained by inserting the next taxon on edge v, visited in pre-order without
+// ever materialising its topology: step j of the child is step j (before v), j - 2 (after v) of the
+// parent's walk program, with three spliced steps at v's position (new internal node b, new leaf a, v one
+// level deeper) -- branch-free selects, the same trip count for every lane of a level.
+//
+// Per-lane state with dynamic indexing lives in shared memory, element k of thread t at [k * blockDim.x + t]
+// (16-byte accesses are then bank-conflict free whatever k each lane uses; local memory would serialise
+// into one wavefront per distinct index):
+//   upath[k]   UP sets recomputed along the path from b (k = 0) up to the root's child; every other UP
+//              set is the parent tree's, read from its record (L1 hits: lanes of a warp share parents);
+//   dstack[d]  DOWN set of the current ancestor at depth d.
+struct ChildWalk {
+	const uint8_t *par, *sib;
+	const unsigned *prog;
+	const uint4 *PU;              // parent's UP sets for this lane's column
+	unsigned E, W, a, b, v, P, dv, sv, szv, last;
+	unsigned on0, on1, on2, on3, on4, on5, on6;   // edges on the root path (ids < 224)
+	uint4 rt;
+
+	__device__ __forceinline__ bool on_path(unsigned e) const {
+		const unsigned w = e < 96 ? (e < 32 ? on0 : (e < 64 ? on1 : on2)) : (e < 160 ? (e < 128 ? on3 : on4) : (e < 192 ? on5 : on6));
+		return (w >> (e & 31u)) & 1u;
+	}
+	__device__ __forceinline__ void mark(unsigned e) {
+		const unsigned bit = 1u << (e & 31u);
+		if (e < 32) on0 |= bit; else if (e < 64) on1 |= bit; else if (e < 96) on2 |= bit; else if (e < 128) on3 |= bit;
+		else if (e < 160) on4 |= bit; else if (e < 192) on5 |= bit; else on6 |= bit;
+	}
+	// Decodes the parent's header for the insertion on edge v and recomputes UP along the root path.
+	__device__ __forceinline__ unsigned init(const uint8_t *ph, const Layout &L, unsigned m, unsigned v_, const uint4 *parent_up,
+	                                         const uint4 &row_new, uint4 *upath, unsigned T) {
+		par = ph + L.off_par;
+		sib = ph + L.off_sib;
+		prog = (const unsigned *) (ph + L.off_prog);
+		PU = parent_up;
+		E = 2 * m - 3;
+		W = L.W;
+		a = E;
+		b = E + 1;
+		v = v_;
+		rt = row_new;
+		P = ph[L.off_pos + v];
+		szv = ph[L.off_size + v];
+		const unsigned pw = prog[P];
+		sv = (pw >> 8) & 0xFFu;
+		dv = pw >> 16;
+		on0 = on1 = on2 = on3 = on4 = on5 = on6 = 0;
+		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W));
+		upath[0] = u;
+		mark(b);
+		unsigned k = 1;
+		unsigned p = par[v], other = sv;
+		while (p != 0xFFu) {
+			u = fitch_block(u, __ldg(PU + (size_t) other * W));     // `other` hangs off the path: unchanged
+			upath[(size_t) k * T] = u;
+			mark(p);
+			++k;
+			other = sib[p];
+			p = par[p];
+		}
+		last = k - 1;       // depth of b
+		return k;           // merges done
+	}
+	// Step j of the child's pre-order: edge, sibling, depth.
+	__device__ __forceinline__ void step(unsigned j, unsigned &x, unsigned &s, unsigned &d) const {
+		const unsigned i = j <= P ? j : j - 2;
+		const unsigned w = prog[i < E ? i : E - 1];
+		x = w & 0xFFu;
+		s = (w >> 8) & 0xFFu;
+		d = w >> 16;
+		if (j > P + 2 && i < P + szv) d += 1;      // inside v's subtree: one level deeper
+		if (s == v) s = b;                         // v's sibling now hangs next to b
+		if (j == P) { x = b; s = sv; d = dv; }
+		if (j == P + 1) { x = a; s = v; d = dv + 1; }
+		if (j == P + 2) { x = v; s = a; d = dv + 1; }
+	}
+	__device__ __forceinline__ uint4 up_of(unsigned y, unsigned depth, const uint4 *upath, unsigned T) const {
+		if (on_path(y)) return upath[(size_t) (last - depth) * T];
+		if (y == a) return rt;
+		return __ldg(PU + (size_t) y * W);
+	}
+};
+
 // ---- child construction ------------------------------------------------------------------------------
+// One thread per (survivor, 128-bit column): UP (copied, then the path entries), DOWN and MIDPOINT of the
+// child are written to its record; the column-0 thread also writes the child's header, walk program
+// included.
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned long long child_first, const uint4 *__restrict__ rows,
-                 unsigned long long *merges) {
+                 unsigned long long *merges, unsigned D) {
+	extern __shared__ uint4 smem[];
+	const unsigned T = blockDim.x;
+	uint4 *upath = smem + threadIdx.x;
+	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
 	const unsigned n_surv = *n_surv_ptr;
-	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, a = E, b = E + 1;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2;
 	const unsigned long long total = (unsigned long long) n_surv * W;
 	unsigned my_merges = 0;
 	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -117,94 +211,44 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint4 sv = surv[s];
 		const unsigned pnode = sv.x, v = sv.y;
 		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
-		const uint8_t *ppar = ph + L.off_par, *pk0 = ph + L.off_k0, *pk1 = ph + L.off_k1;
-		const unsigned pv = ppar[v];
-		// The child's topology = the parent's with leaf a and internal node b spliced in above v.
-		auto par_of = [&](unsigned x) -> unsigned { return (x == a || x == v) ? b : (x == b ? pv : (unsigned) ppar[x]); };
-		auto kid0_of = [&](unsigned x) -> unsigned {
-			if (x == b) return a;
-			unsigned k = pk0[x];
-			return (x == pv && k == v) ? b : k;
-		};
-		auto kid1_of = [&](unsigned x) -> unsigned {
-			if (x == b) return v;
-			unsigned k = pk1[x];
-			return (x == pv && k == v) ? b : k;
-		};
-		const unsigned top = (pv == 0xFFu) ? b : (unsigned) ph[HDR_PATH];
-
-		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W;
-		uint4 *CM = child.sets + (child_first + s) * child.rec;
+		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
+		uint4 *CM = child.sets + (child_first + s) * child.rec + col;
 		uint4 *CU = CM + (unsigned long long) Ec * W, *CD = CU + (unsigned long long) Ec * W;
-
-		// UP: unchanged off the root path; recomputed from the new leaf up to the root's child.
-#pragma unroll 4
-		for (unsigned e = 0; e < E; ++e) CU[(size_t) e * W + col] = __ldg(PU + (size_t) e * W + col);
-		const uint4 rt = __ldg(rows + (size_t) m * W + col);
-		CU[(size_t) a * W + col] = rt;
-		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W + col));
-		CU[(size_t) b * W + col] = u;
-		unsigned n_up = 1;
-		for (unsigned x = b;;) {
-			const unsigned p = par_of(x);
-			if (p == 0xFFu) break;
-			const unsigned k0 = kid0_of(p);
-			const unsigned other = (k0 == x) ? kid1_of(p) : k0;   // off the path: its UP is the parent tree's
-			u = fitch_block(u, __ldg(PU + (size_t) other * W + col));
-			CU[(size_t) p * W + col] = u;
-			x = p;
-			++n_up;
-		}
-
-		// DOWN and MIDPOINT for every edge, stackless pre-order walk.
 		const uint4 r0 = __ldg(rows + col);
-		uint4 dpar = r0;
-		bool have_dpar = false;
-		for (unsigned x = top;;) {
-			const unsigned p = par_of(x);
-			uint4 d;
-			if (p == 0xFFu) {
-				d = r0;
-			} else {
-				const unsigned k0 = kid0_of(p);
-				const unsigned sib = (k0 == x) ? kid1_of(p) : k0;
-				const uint4 dp = have_dpar ? dpar : CD[(size_t) p * W + col];
-				d = fitch_block(dp, CU[(size_t) sib * W + col]);
-			}
-			CD[(size_t) x * W + col] = d;
-			CM[(size_t) x * W + col] = fitch_block(CU[(size_t) x * W + col], d);
-			if (!edge_is_leaf(x)) {
-				dpar = d;
-				have_dpar = true;
-				x = kid0_of(x);
-				continue;
-			}
-			have_dpar = false;
-			bool finished = false;
-			for (;;) {
-				const unsigned q = par_of(x);
-				if (q == 0xFFu) { finished = true; break; }
-				if (kid0_of(q) == x) { x = kid1_of(q); break; }
-				x = q;
-			}
-			if (finished) break;
+		ChildWalk cw;
+		const unsigned n_up = cw.init(ph, L, m, v, PU, __ldg(rows + (size_t) m * W + col), upath, T);
+		for (unsigned j = 0; j < Ec; ++j) {
+			unsigned x, sb, d;
+			cw.step(j, x, sb, d);
+			const uint4 ux = cw.up_of(x, d, upath, T);
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], cw.up_of(sb, d, upath, T));
+			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
+			CU[(size_t) x * W] = ux;
+			CD[(size_t) x * W] = dn;
+			CM[(size_t) x * W] = fitch_block(ux, dn);
 		}
-
 		if (col == 0) {
+			// header: copy, then re-derive everything the insertion changed
 			uint8_t *ch = child.hdr + (size_t) (child_first + s) * L.HB;
 			for (unsigned i = 0; i < L.HB / 16; ++i) ((uint4 *) ch)[i] = ((const uint4 *) ph)[i];
 			*(unsigned *) ch = sv.z;
-			ch[HDR_PATH] = (uint8_t) top;
 			ch[HDR_PATH + m] = (uint8_t) v;
-			uint8_t *cpar = ch + L.off_par, *ck0 = ch + L.off_k0, *ck1 = ch + L.off_k1;
-			cpar[a] = cpar[v] = (uint8_t) b;
-			cpar[b] = (uint8_t) pv;
-			ck0[b] = (uint8_t) a;
-			ck1[b] = (uint8_t) v;
-			ck0[a] = ck1[a] = 0xFF;
-			if (pv != 0xFFu) {
-				if (pk0[pv] == v) ck0[pv] = (uint8_t) b; else ck1[pv] = (uint8_t) b;
+			uint8_t *cpar = ch + L.off_par, *csib = ch + L.off_sib, *cpos = ch + L.off_pos, *csize = ch + L.off_size;
+			unsigned *cprog = (unsigned *) (ch + L.off_prog);
+			for (unsigned j = 0; j < Ec; ++j) {
+				unsigned x, sb, d;
+				cw.step(j, x, sb, d);
+				cprog[j] = x | (sb << 8) | (d << 16);
+				cpos[x] = (uint8_t) j;
+				csib[x] = (uint8_t) sb;
 			}
+			const unsigned pv = cw.par[v];
+			cpar[cw.a] = cpar[v] = (uint8_t) cw.b;
+			cpar[cw.b] = (uint8_t) pv;
+			csize[cw.a] = 1;
+			csize[cw.b] = (uint8_t) (cw.szv + 2);
+			for (unsigned q = pv; q != 0xFFu; q = cw.par[q]) csize[q] = (uint8_t) (ph[L.off_size + q] + 2);
+			ch[HDR_PATH] = (uint8_t) (cprog[0] & 0xFFu);
 			my_merges += n_up + 2 * Ec;
 		}
 	}
@@ -213,21 +257,12 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	if ((threadIdx.x & 31u) == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
 }
 
-
 // ---- last two levels fused ---------------------------------------------------------------------------
 // Parents have n-2 taxa.  A surviving child (n-1 taxa) is only ever scored once more, against the last
-// taxon, so it is never written to HBM: G lanes per child (one per 128-bit column) walk the child's
-// topology, form each edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the
-// columns), apply the acceptance test and emit complete trees.  This replaces k_build_children for the
-// deepest pool and the whole k_expand_score pass over it -- where almost all nodes of a search live.
-//
-// Per-lane state that needs dynamic indexing lives in shared memory, element k of thread t at
-// [k * blockDim.x + t]: 16-byte accesses are then bank-conflict free whatever k each lane uses (local
-// memory would serialise into one wavefront per distinct index).  Only two small stacks are needed:
-//   upath[k]   UP sets recomputed along the path from the new internal node (k = 0) to the root's child;
-//              every other UP set is the parent tree's and is read from its record (L1/L2 hits: the lanes
-//              of a warp mostly share a parent);
-//   dstack[d]  DOWN set of the current ancestor at depth d.
+// taxon, so it is never written to HBM: G lanes per child (one per 128-bit column) walk it, form each
+// edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the columns), apply the
+// acceptance test and emit complete trees.  This replaces k_build_children for the deepest pool and the
+// whole k_expand_score pass over it -- where almost all nodes of a search live.
 template <int G>
 __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
@@ -238,7 +273,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
 	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
-	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, a = E, b = E + 1;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2;
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
 	const unsigned lane = threadIdx.x & 31u, sub = lane % G;
 	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - sub));
@@ -254,53 +289,9 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		const uint4 sv = surv[s];
 		const unsigned pnode = sv.x, v = sv.y, score = sv.z;
 		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
-		const uint8_t *ppar = ph + L.off_par, *pk0 = ph + L.off_k0, *pk1 = ph + L.off_k1;
-		const unsigned pv = ppar[v];
-		auto par_of = [&](unsigned x) -> unsigned { return (x == a || x == v) ? b : (x == b ? pv : (unsigned) ppar[x]); };
-		auto kid0_of = [&](unsigned x) -> unsigned {
-			if (x == b) return a;
-			unsigned k = pk0[x];
-			return (x == pv && k == v) ? b : k;
-		};
-		auto kid1_of = [&](unsigned x) -> unsigned {
-			if (x == b) return v;
-			unsigned k = pk1[x];
-			return (x == pv && k == v) ? b : k;
-		};
-		const unsigned top = (pv == 0xFFu) ? b : (unsigned) ph[HDR_PATH];
 		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
-
-		// UP along the root path, remembering which edges are on it.
-		unsigned on0 = 0, on1 = 0, on2 = 0;
-		auto mark = [&](unsigned e) {
-			if (e < 32) on0 |= 1u << e; else if (e < 64) on1 |= 1u << (e - 32); else on2 |= 1u << (e - 64);
-		};
-		auto on_path = [&](unsigned e) -> bool {
-			const unsigned w = e < 32 ? on0 : (e < 64 ? on1 : on2);
-			return (w >> (e & 31u)) & 1u;
-		};
-		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W));
-		upath[0] = u;
-		mark(b);
-		unsigned k = 1;
-		for (unsigned x = b;;) {
-			const unsigned p = par_of(x);
-			if (p == 0xFFu) break;
-			const unsigned k0 = kid0_of(p);
-			const unsigned other = (k0 == x) ? kid1_of(p) : k0;      // hangs off the path: unchanged
-			u = fitch_block(u, __ldg(PU + (size_t) other * W));
-			upath[(size_t) k * T] = u;
-			mark(p);
-			++k;
-			x = p;
-		}
-		const unsigned last = k - 1;      // depth of b
-		auto up_of = [&](unsigned y, unsigned depth) -> uint4 {
-			if (on_path(y)) return upath[(size_t) (last - depth) * T];
-			if (y == a) return rt;
-			return __ldg(PU + (size_t) y * W);
-		};
-
+		ChildWalk cw;
+		const unsigned n_up = cw.init(ph, L, m, v, PU, rt, upath, T);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
 		unsigned bound = 0;
 		{
@@ -309,19 +300,13 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
 			bound = __shfl_sync(active, bound, leader);
 		}
-		unsigned depth = 0;
-		for (unsigned x = top;;) {
-			const unsigned p = par_of(x);
-			uint4 d;
-			if (p == 0xFFu) {
-				d = r0;
-			} else {
-				const unsigned k0 = kid0_of(p);
-				const unsigned sib = (k0 == x) ? kid1_of(p) : k0;
-				d = fitch_block(dstack[(size_t) (depth - 1) * T], up_of(sib, depth));
-			}
-			const uint4 mid = fitch_block(up_of(x, depth), d);
-			unsigned c = col_ok ? cost_block(mid, rl, col, wp) : 0u;
+		for (unsigned j = 0; j < Ec; ++j) {
+			unsigned x, sb, d;
+			cw.step(j, x, sb, d);
+			const uint4 ux = cw.up_of(x, d, upath, T);
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], cw.up_of(sb, d, upath, T));
+			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
+			unsigned c = col_ok ? cost_block(fitch_block(ux, dn), rl, col, wp) : 0u;
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
 			if (sub == 0 && accept_insertion(c, bound, score, rest_last)) {
@@ -335,23 +320,8 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 					rec[4 + m + 1] = (uint8_t) x;
 				}
 			}
-			if (!edge_is_leaf(x)) {
-				dstack[(size_t) depth * T] = d;
-				x = kid0_of(x);
-				++depth;
-				continue;
-			}
-			bool finished = false;
-			for (;;) {
-				const unsigned q = par_of(x);
-				if (q == 0xFFu) { finished = true; break; }
-				if (kid0_of(q) == x) { x = kid1_of(q); break; }
-				x = q;
-				--depth;
-			}
-			if (finished) break;
 		}
-		if (sub == 0) my_merges += k + 2 * Ec;
+		if (sub == 0) my_merges += n_up + 2 * Ec;
 	}
 	my_merges = warp_sum(my_merges);
 	if (lane == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
@@ -368,12 +338,26 @@ __global__ void k_write_headers(PoolView pool, Layout L, unsigned m, unsigned lo
 	for (unsigned i = 4; i < L.HB; ++i) h[i] = 0xFF;
 	*(unsigned *) h = tree_len[j];
 	const uint8_t *t = topo + (size_t) j * 4 * topo_stride;
+	const uint8_t *par = t, *k0 = t + topo_stride, *k1 = t + 2 * topo_stride, *pre = t + 3 * topo_stride;
 	for (unsigned k = 0; k < L.n; ++k) h[HDR_PATH + k] = paths[(size_t) j * L.n + k];
-	h[HDR_PATH] = t[3 * topo_stride];   // first edge in pre-order = the root's child
-	for (unsigned e = 0; e < E; ++e) {
-		h[L.off_par + e] = t[e];
-		h[L.off_k0 + e] = t[topo_stride + e];
-		h[L.off_k1 + e] = t[2 * topo_stride + e];
+	h[HDR_PATH] = pre[0];   // first edge in pre-order = the root's child
+	uint8_t *hpar = h + L.off_par, *hsib = h + L.off_sib, *hpos = h + L.off_pos, *hsize = h + L.off_size;
+	unsigned *hprog = (unsigned *) (h + L.off_prog);
+	// depth is kept in the size array until the program is written, then sizes are accumulated bottom-up
+	for (unsigned i = 0; i < E; ++i) {
+		const unsigned e = pre[i], p = par[e];
+		const unsigned d = p == 0xFFu ? 0u : (unsigned) hsize[p] + 1u;      // parents precede children in pre-order
+		const unsigned sb = p == 0xFFu ? 0xFFu : (unsigned) (k0[p] == e ? k1[p] : k0[p]);
+		hpar[e] = (uint8_t) p;
+		hsib[e] = (uint8_t) sb;
+		hpos[e] = (uint8_t) i;
+		hsize[e] = (uint8_t) d;
+		hprog[i] = e | (sb << 8) | (d << 16);
+	}
+	for (unsigned i = 0; i < E; ++i) hsize[pre[i]] = 1;
+	for (int i = (int) E - 1; i >= 0; --i) {
+		const unsigned e = pre[i], p = par[e];
+		if (p != 0xFFu) hsize[p] = (uint8_t) (hsize[p] + hsize[e]);
 	}
 }
 
@@ -467,9 +451,11 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	L.n = n;
 	L.W = W;
 	L.off_par = HDR_PATH + n;
-	L.off_k0 = L.off_par + Emax;
-	L.off_k1 = L.off_k0 + Emax;
-	L.HB = (L.off_k1 + Emax + 15u) & ~15u;
+	L.off_sib = L.off_par + Emax;
+	L.off_pos = L.off_sib + Emax;
+	L.off_size = L.off_pos + Emax;
+	L.off_prog = (L.off_size + Emax + 3u) & ~3u;
+	L.HB = (L.off_prog + 4u * Emax + 15u) & ~15u;
 	L.trec = 4 + ((n + 3u) & ~3u);
 
 	size_t free_b = 0, total_b = 0;
@@ -482,7 +468,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 
 	// The deepest pool is skipped when the last two levels are fused (narrow state sets): it then only
 	// ever holds imported jobs.
-	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 32 && n >= 5 && n <= 41;
+	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 32 && n >= 5;
 	const double last_cap = S->fused_last ? 1024.0 : 1e300;
 	// Largest per-level capacity C such that all pools fit; a level never needs more than (2m-5)!! nodes.
 	auto bytes_for = [&](double C) {
@@ -600,10 +586,23 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	return XMP_OK;
 }
 
+// Shared memory of the child-walk kernels: two stacks of D = m + 1 blocks per thread.
+static unsigned walk_threads(unsigned D, size_t *smem) {
+	unsigned threads = 128;
+	while (threads > 32 && (size_t) 2 * D * 16 * threads > ((size_t) 96 << 10)) threads >>= 1;
+	*smem = (size_t) 2 * D * 16 * threads;
+	return threads;
+}
+
 static int launch_children(xmp_ctx *ctx, Search *S, unsigned m) {
 	Pool &P = S->pool[m], &C = S->pool[m + 1];
-	const unsigned blocks = (unsigned) ctx->sm_count * 8;
-	k_build_children<<<blocks, 128, 0, ctx->stream>>>(P.view(), C.view(), S->L, m, S->d_surv, S->d_nsurv, C.count, ctx->d_rows, S->d_merges);
+	const unsigned D = m + 1;
+	size_t smem = 0;
+	const unsigned threads = walk_threads(D, &smem);
+	const unsigned blocks = (unsigned) ctx->sm_count * 16;
+	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, S->d_surv, S->d_nsurv, C.count, ctx->d_rows,
+	                                                         S->d_merges, D);
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -613,9 +612,8 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	const Layout &L = S->L;
 	Pool &P = S->pool[m];
 	const unsigned D = m + 1;                        // a tree on m + 1 taxa is at most m edges deep
-	unsigned threads = 128;
-	if ((size_t) 2 * D * 16 * threads > (size_t) 96 << 10) threads = 64;
-	const size_t smem = (size_t) 2 * D * 16 * threads;
+	size_t smem = 0;
+	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 #define XMP_FUSED(G)                                                                                                          \
 	do {                                                                                                                      \
