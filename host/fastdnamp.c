@@ -270,7 +270,7 @@ typedef struct {
 	xmp_search_stats stats;
 } worker;
 
-#define SLICE_BATCHES 64
+#define SLICE_BATCHES 8
 #define STEAL_NODES 256
 
 static void worker_fail(worker *w, const char *what) {

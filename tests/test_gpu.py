@@ -260,6 +260,13 @@ def test_search_is_independent_of_scheduling(xc, alignment_dir, goldens):
                {"flags": xc.SEARCH_NO_FUSE | xc.SEARCH_NO_DIVE, "mem_budget": 400 << 20}):
         score, n, trees, stats = run_search(xc, p, **kw)
         check_against_golden("mh6", g, p, score, n, trees)
+    # the one-level-per-synchronisation scheduler (kept for A/B measurements) instead of the sweep
+    os.environ["XMP_SWEEP"] = "0"
+    try:
+        score, n, trees, stats = run_search(xc, p)
+        check_against_golden("mh6", g, p, score, n, trees)
+    finally:
+        del os.environ["XMP_SWEEP"]
     ctx = xc.Context(0)
     ctx.load_problem(p)
     ctx.search_begin(bound=p.bound)

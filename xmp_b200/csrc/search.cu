@@ -394,6 +394,11 @@ struct Search {
 	unsigned long long *d_merges = nullptr;
 	uint4 *d_surv = nullptr;
 	unsigned long long surv_cap = 0;
+	uint4 *d_surv_lvl[XMP_MAX_TAXA + 2] = {nullptr};            // per-level survivor lists used by the sweep
+	unsigned long long surv_cap_lvl[XMP_MAX_TAXA + 2] = {0};
+	uint4 *d_surv_arena = nullptr;
+	unsigned *d_nsurv_lvl = nullptr;                           // [XMP_MAX_TAXA + 1] counters, one per level
+	bool sweep = true;
 	uint8_t *d_trees[2] = {nullptr, nullptr};
 	int cur = 0;
 	unsigned trees_cap = 0, ntrees_dev = 0;
@@ -402,7 +407,7 @@ struct Search {
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
-	unsigned min_batch = 32768, beam = 512, policy = 1;
+	unsigned min_batch = 4096, beam = 512, policy = 1;
 	xmp_search_stats st;
 	Scratch topo, pathbuf;
 };
@@ -435,6 +440,7 @@ void search_destroy(xmp_ctx *ctx) {
 	}
 	if (S->d_bound) cudaFree(S->d_bound);
 	if (S->d_surv) cudaFree(S->d_surv);
+	if (S->d_surv_arena) cudaFree(S->d_surv_arena);
 	if (S->d_trees[0]) cudaFree(S->d_trees[0]);
 	if (S->d_trees[1]) cudaFree(S->d_trees[1]);
 	if (S->d_len) cudaFree(S->d_len);
@@ -476,9 +482,9 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		for (unsigned m = 3; m < n; ++m) {
 			double c = std::min(C, odd_factorial(m));
 			if (m + 1 == n) c = std::min(c, last_cap);
-			tot += c * ((double) 3 * (2 * m - 3) * W * 16 + L.HB);
+			tot += c * ((double) 3 * (2 * m - 3) * W * 16 + L.HB + 16);   // + its slot in a survivor list
 		}
-		return tot + C * 16;   // survivors
+		return tot + 2 * C * 16;   // survivors of the single-batch path and of the fused level
 	};
 	double lo = 256, hi = 4194304.0;
 	if (bytes_for(lo) > (double) budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
@@ -501,13 +507,29 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	XMP_CUDA(cudaMalloc(&S->d_surv, (size_t) S->surv_cap * 16));
 	XMP_CUDA(cudaMalloc(&S->d_trees[0], (size_t) S->trees_cap * L.trec));
 	XMP_CUDA(cudaMalloc(&S->d_trees[1], (size_t) S->trees_cap * L.trec));
-	XMP_CUDA(cudaMalloc(&S->d_bound, 64));
+	{
+		// one survivor list per level: as many entries as the pool its children go to (the fused level
+		// keeps them only until the fused kernel has consumed them)
+		unsigned long long total = 0;
+		for (unsigned m = 3; m + 1 < n; ++m) {
+			S->surv_cap_lvl[m] = (S->fused_last && m + 2 == n) ? S->surv_cap : S->pool[m + 1].cap;
+			total += S->surv_cap_lvl[m];
+		}
+		XMP_CUDA(cudaMalloc(&S->d_surv_arena, (size_t) std::max<unsigned long long>(total, 1) * 16));
+		unsigned long long off = 0;
+		for (unsigned m = 3; m + 1 < n; ++m) {
+			S->d_surv_lvl[m] = S->d_surv_arena + off;
+			off += S->surv_cap_lvl[m];
+		}
+	}
+	XMP_CUDA(cudaMalloc(&S->d_bound, 1024));
 	S->d_nsurv = S->d_bound + 1;
 	S->d_ntrees = S->d_bound + 2;
 	S->d_merges = (unsigned long long *) (S->d_bound + 4);
-	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 64, ctx->stream));
+	S->d_nsurv_lvl = S->d_bound + 8;
+	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 1024, ctx->stream));
 	XMP_CUDA(cudaMalloc(&S->d_len, 65536 * sizeof(unsigned)));
-	XMP_CUDA(cudaMallocHost(&S->h_pin, 64));
+	XMP_CUDA(cudaMallocHost(&S->h_pin, 1024));
 	return XMP_OK;
 }
 
@@ -559,7 +581,8 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 	return XMP_OK;
 }
 
-static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long first, unsigned long long chunk, bool shard) {
+static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long first, unsigned long long chunk, bool shard,
+                         uint4 *surv, unsigned *nsurv) {
 	const Layout &L = S->L;
 	Pool &P = S->pool[m];
 	const int last = (m + 1 == S->n);
@@ -571,7 +594,7 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	const unsigned room = S->trees_cap;
 #define XMP_EXPAND(G)                                                                                                   \
 	k_expand_score<G><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
-	                                                                              S->d_bound, last, S->d_surv, S->d_nsurv, trees,   \
+	                                                                              S->d_bound, last, surv, nsurv, trees,             \
 	                                                                              S->d_ntrees, room, sc, si)
 	const unsigned W = L.W;
 	if (W > 16) XMP_EXPAND(32);
@@ -594,21 +617,21 @@ static unsigned walk_threads(unsigned D, size_t *smem) {
 	return threads;
 }
 
-static int launch_children(xmp_ctx *ctx, Search *S, unsigned m) {
+static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *surv, const unsigned *nsurv, unsigned long long child_first) {
 	Pool &P = S->pool[m], &C = S->pool[m + 1];
 	const unsigned D = m + 1;
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, S->d_surv, S->d_nsurv, C.count, ctx->d_rows,
+	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, child_first, ctx->d_rows,
 	                                                         S->d_merges, D);
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
 }
 
-static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, unsigned s_end) {
+static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, unsigned s_end, const uint4 *surv, const unsigned *nsurv) {
 	const Layout &L = S->L;
 	Pool &P = S->pool[m];
 	const unsigned D = m + 1;                        // a tree on m + 1 taxa is at most m edges deep
@@ -618,7 +641,7 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 #define XMP_FUSED(G)                                                                                                          \
 	do {                                                                                                                      \
 		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
-		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, S->d_surv, S->d_nsurv, s_begin, s_end,     \
+		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
 		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
 		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D); \
 	} while (0)
@@ -636,7 +659,7 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 
 // Reads back n_surv, n_trees, bound and the merge counter (one small pinned copy, one sync).
 static int fetch_counters(xmp_ctx *ctx, Search *S) {
-	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 32, cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 32 + 4 * (XMP_MAX_TAXA + 1), cudaMemcpyDeviceToHost, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	S->bound = S->h_pin[0];
 	return XMP_OK;
@@ -690,7 +713,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 	const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level && keep_best == 0;
 	const unsigned long long first = P.count - chunk;
 	if (!last) XMP_CUDA(cudaMemsetAsync(S->d_nsurv, 0, sizeof(unsigned), ctx->stream));
-	int rc = launch_expand(ctx, S, m, first, chunk, shard);
+	int rc = launch_expand(ctx, S, m, first, chunk, shard, S->d_surv, S->d_nsurv);
 	if (rc) return rc;
 	S->st.nodes += chunk;
 	S->st.score_calls += chunk * P.E;
@@ -725,7 +748,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 	if (S->fused_last && m + 2 == S->n) {
 		// Children of this level are scored against the last taxon without ever being stored.
 		const unsigned before = S->ntrees_dev;
-		rc = launch_fused(ctx, S, m, 0, 0xffffffffu);
+		rc = launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv, S->d_nsurv);
 		if (rc) return rc;
 		rc = fetch_counters(ctx, S);
 		if (rc) return rc;
@@ -742,7 +765,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 				todo.pop_back();
 				rc = drain_trees(ctx, S);
 				if (rc) return rc;
-				rc = launch_fused(ctx, S, m, r.lo, r.hi);
+				rc = launch_fused(ctx, S, m, r.lo, r.hi, S->d_surv, S->d_nsurv);
 				if (rc) return rc;
 				rc = fetch_counters(ctx, S);
 				if (rc) return rc;
@@ -768,7 +791,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		P.count -= chunk;
 		return tidy_trees(ctx, S);
 	}
-	rc = launch_children(ctx, S, m);
+	rc = launch_children(ctx, S, m, S->d_surv, S->d_nsurv, S->pool[m + 1].count);
 	if (rc) return rc;
 	rc = fetch_counters(ctx, S);
 	if (rc) return rc;
@@ -777,6 +800,111 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 	S->st.children += ns;
 	P.count -= chunk;
 	return XMP_OK;
+}
+
+// One sweep over the frontier: every level that holds open trees is expanded in the same pass, deepest
+// first, on one stream and with ONE host synchronisation at the end (per-level survivor lists and counters).
+// Going deepest-first lets level m's children land exactly where level m + 1's batch was just consumed, so
+// the pools stay plain stacks.  Compared with one level per synchronisation this cuts the number of host
+// round trips on deep, narrow searches (20 taxa: 17 levels) by an order of magnitude.
+static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
+	const unsigned n = S->n;
+	*any = false;
+	// Open trees on the last level only exist when the last two levels are not fused (or were imported):
+	// they emit complete trees into the shared buffer, so they go alone, as a classic single batch.
+	if (S->pool[n - 1].count) {
+		Pool &P = S->pool[n - 1];
+		unsigned long long room = (S->trees_cap - S->ntrees_dev) / P.E;
+		if (room == 0) {
+			int rc = drain_trees(ctx, S);
+			if (rc) return rc;
+			room = S->trees_cap / P.E;
+		}
+		*any = true;
+		return run_batch(ctx, S, n - 1, std::min(P.count, room), 0);
+	}
+	struct Item { unsigned m; unsigned long long chunk; bool fused; };
+	Item items[XMP_MAX_TAXA + 2];
+	unsigned n_items = 0;
+	unsigned long long taken[XMP_MAX_TAXA + 2] = {0};
+	const unsigned before = S->ntrees_dev;
+	XMP_CUDA(cudaMemsetAsync(S->d_nsurv_lvl, 0, 4 * (XMP_MAX_TAXA + 1), ctx->stream));
+	// A level joins the sweep only if it brings a worthwhile batch: every launch costs tens of microseconds
+	// whatever its size, so a handful of open trees is better left to accumulate.  If nothing qualifies
+	// (the tail of a search), everything goes.
+	for (unsigned threshold = S->min_batch; n_items == 0; threshold = 1) {
+		for (unsigned m = n - 2; m >= 3; --m) {
+			Pool &P = S->pool[m];
+			if (P.count == 0) continue;
+			const bool fused = S->fused_last && m + 2 == n;
+			const unsigned long long base_next = fused ? 0 : S->pool[m + 1].count - taken[m + 1];
+			unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - base_next);
+			const unsigned long long chunk = std::min(P.count, room / P.E);
+			if (chunk == 0 || chunk < std::min<unsigned long long>(threshold, P.cap)) continue;
+			const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level;
+			int rc = launch_expand(ctx, S, m, P.count - chunk, chunk, shard, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
+			if (rc) return rc;
+			rc = fused ? launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv_lvl[m], S->d_nsurv_lvl + m)
+			           : launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, base_next);
+			if (rc) return rc;
+			taken[m] = chunk;
+			items[n_items++] = Item{m, chunk, fused};
+		}
+		if (threshold == 1) break;
+	}
+	if (n_items == 0) return XMP_OK;
+	*any = true;
+	int rc = fetch_counters(ctx, S);
+	if (rc) return rc;
+	for (unsigned i = 0; i < n_items; ++i) S->pool[items[i].m].count -= items[i].chunk;
+	for (unsigned i = 0; i < n_items; ++i) {
+		const unsigned m = items[i].m;
+		const unsigned ns = S->h_pin[8 + m];
+		Pool &P = S->pool[m];
+		S->st.nodes += items[i].chunk;
+		S->st.score_calls += items[i].chunk * P.E;
+		S->st.children += ns;
+		if (items[i].fused) {
+			S->st.nodes += ns;
+			S->st.score_calls += (unsigned long long) ns * (P.E + 2);
+			if (S->h_pin[2] > S->trees_cap) {
+				// The tree buffer overflowed inside the fused kernel: restore the counter, make room and redo
+				// this level's survivors in halves (emission is idempotent: records carry their own length).
+				struct Range { unsigned lo, hi; };
+				std::vector<Range> todo;
+				todo.push_back(Range{0, ns});
+				S->ntrees_dev = before;
+				while (!todo.empty()) {
+					Range r = todo.back();
+					todo.pop_back();
+					rc = drain_trees(ctx, S);
+					if (rc) return rc;
+					rc = launch_fused(ctx, S, m, r.lo, r.hi, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
+					if (rc) return rc;
+					rc = fetch_counters(ctx, S);
+					if (rc) return rc;
+					if (S->h_pin[2] > S->trees_cap) {
+						if (r.hi - r.lo < 2) return set_error(XMP_ERR_NOMEM, "tree buffer too small for a single partial tree's completions");
+						const unsigned mid = r.lo + (r.hi - r.lo) / 2;
+						todo.push_back(Range{mid, r.hi});
+						todo.push_back(Range{r.lo, mid});
+						S->ntrees_dev = 0;
+						XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+						continue;
+					}
+					S->st.full_trees += S->h_pin[2];
+					S->ntrees_dev = S->h_pin[2];
+				}
+			} else {
+				S->st.full_trees += S->h_pin[2] - before;
+				S->ntrees_dev = S->h_pin[2];
+			}
+		} else {
+			S->pool[m + 1].count += ns;
+		}
+	}
+	S->st.iterations += 1;
+	return tidy_trees(ctx, S);
 }
 
 static int push_root(xmp_ctx *ctx, Search *S) {
@@ -819,9 +947,10 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
 	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
 	S->n = ctx->num_taxa;
-	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
+	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 4096), 1u);
 	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
 	S->policy = env_unsigned("XMP_POLICY", 1);
+	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	memset(&S->st, 0, sizeof S->st);
 	int rc = alloc_search(ctx, S);
 	if (rc) { search_destroy(ctx); return rc; }
@@ -863,7 +992,25 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 	XMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
 	unsigned batches = 0;
 	int rc = XMP_OK;
-	while (!S->done && (max_batches == 0 || batches < max_batches)) {
+	while (S->sweep && !S->done && (max_batches == 0 || batches < max_batches)) {
+		bool any = false;
+		rc = run_sweep(ctx, S, &any);
+		if (rc) break;
+		if (!any) {
+			bool open = false;
+			for (unsigned m = 3; m < S->n; ++m) open |= S->pool[m].count != 0;
+			if (open) {
+				// every open level is blocked by a full pool below it, which can only be the tree buffer
+				rc = drain_trees(ctx, S);
+				if (rc) break;
+				continue;
+			}
+			S->done = true;
+			break;
+		}
+		++batches;
+	}
+	while (!S->sweep && !S->done && (max_batches == 0 || batches < max_batches)) {
 		// Deepest level holding a worthwhile batch; otherwise the fullest one (policy 1, default).
 		// Policy 0 falls back to the deepest non-empty level, policy 2 always takes the fullest.
 		int pick = -1, fallback = -1;

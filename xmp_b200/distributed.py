@@ -24,7 +24,7 @@ def _t(x, device, dtype=torch.int64):
     return torch.tensor(x, dtype=dtype, device=device)
 
 
-def sharded_search(engine, num_taxa, device="cpu", slice_batches=64, steal_nodes=256, group=None, on_round=None):
+def sharded_search(engine, num_taxa, device="cpu", slice_batches=8, steal_nodes=256, group=None, on_round=None):
     """Runs engine (already search_begin()'ed with this rank's shard_index / shard_count) to completion
     together with the other ranks.  Returns (score, total number of optimal trees, this rank's optimal
     paths, number of rounds).  Every rank returns the same score and total.
