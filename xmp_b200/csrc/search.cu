@@ -217,15 +217,24 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
 		const unsigned n_up = cw.init(ph, L, m, v, PU, __ldg(rows + (size_t) m * W + col), upath, T);
+		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
+		unsigned x, sb, d;
+		cw.step(0, x, sb, d);
+		uint4 ux = cw.up_of(x, d, upath, T), us = r0;
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned x, sb, d;
-			cw.step(j, x, sb, d);
-			const uint4 ux = cw.up_of(x, d, upath, T);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], cw.up_of(sb, d, upath, T));
+			unsigned xn = x, sbn = sb, dnx = d;
+			uint4 uxn = ux, usn = us;
+			if (j + 1 < Ec) {
+				cw.step(j + 1, xn, sbn, dnx);
+				uxn = cw.up_of(xn, dnx, upath, T);
+				usn = cw.up_of(sbn, dnx, upath, T);     // depth >= 1 from the second step on
+			}
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
 			CU[(size_t) x * W] = ux;
 			CD[(size_t) x * W] = dn;
 			CM[(size_t) x * W] = fitch_block(ux, dn);
+			x = xn; sb = sbn; d = dnx; ux = uxn; us = usn;
 		}
 		if (col == 0) {
 			// header: copy, then re-derive everything the insertion changed
@@ -300,11 +309,19 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
 			bound = __shfl_sync(active, bound, leader);
 		}
+		unsigned x, sb, d;
+		cw.step(0, x, sb, d);
+		uint4 ux = cw.up_of(x, d, upath, T), us = r0;
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned x, sb, d;
-			cw.step(j, x, sb, d);
-			const uint4 ux = cw.up_of(x, d, upath, T);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], cw.up_of(sb, d, upath, T));
+			// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
+			unsigned xn = x, sbn = sb, dnx = d;
+			uint4 uxn = ux, usn = us;
+			if (j + 1 < Ec) {
+				cw.step(j + 1, xn, sbn, dnx);
+				uxn = cw.up_of(xn, dnx, upath, T);
+				usn = cw.up_of(sbn, dnx, upath, T);
+			}
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
 			unsigned c = col_ok ? cost_block(fitch_block(ux, dn), rl, col, wp) : 0u;
 #pragma unroll
@@ -320,6 +337,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 					rec[4 + m + 1] = (uint8_t) x;
 				}
 			}
+			x = xn; sb = sbn; d = dnx; ux = uxn; us = usn;
 		}
 		if (sub == 0) my_merges += n_up + 2 * Ec;
 	}
