@@ -8,6 +8,7 @@
 // This is HBM-bound bitwise integer work: 0.5 B per site-merge for scoring.
 // No tensor cores; the design points are coalesced 128-bit loads, enough independent loads in flight
 // per SM to cover HBM latency, and one reduction per (pair, tile).
+#include <stdlib.h>
 #include "ctx.h"
 
 namespace xmp {
@@ -154,6 +155,103 @@ static void launch_wide(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tr
 	k_score_wide<K><<<grid, 256, 0, ctx->stream>>>(d_sets, tree_stride, ppt, row, ctx->wp, W, n_pairs, ppw, d_cost);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same scorer with the edge sets staged through shared memory by TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), no register staging.  Every warp runs its
+// own S-deep ring of 32*K-block tiles: lane 0 arms a stage's mbarrier with the byte count and issues the
+// copy of the warp's pair i + S - 1 while the warp scores pair i out of the stage that has just landed.
+// Selected with XMP_SCORE_TMA=1; profiles/r01_tma_vs_ldg.md has the measured comparison that decides the
+// default.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+template <int K, int S>
+__global__ void __launch_bounds__(256, S <= 3 ? 2 : 1)
+k_score_wide_tma(const uint4 *__restrict__ sets, unsigned long long tree_stride, unsigned pairs_per_tree,
+                 const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned n_blocks,
+                 unsigned long long n_pairs, unsigned pairs_per_warp, unsigned *__restrict__ cost) {
+	extern __shared__ __align__(128) unsigned char dyn[];
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	constexpr unsigned TILE = 32u * K;                         // blocks per tile
+	uint4 *ring = (uint4 *) dyn + (size_t) warp * S * TILE;     // this warp's stages
+	unsigned long long *bars = (unsigned long long *) ((uint4 *) dyn + (size_t) 8 * S * TILE) + warp * S;
+	const unsigned tile0 = blockIdx.x * TILE;
+	const unsigned tile_blocks = min(TILE, n_blocks - tile0);
+	const unsigned tile_bytes = tile_blocks * 16u;
+	const unsigned col0 = tile0 + lane;
+	const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+	uint4 t[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) t[k] = (col0 + 32u * k < n_blocks) ? __ldg(taxon_row + col0 + 32u * k) : ones;
+	const bool heavy = 4u * tile0 < wp.heavy_words;
+
+	const unsigned long long p0 = ((unsigned long long) blockIdx.y * 8u + warp) * pairs_per_warp;
+	const unsigned long long p_end = min(p0 + pairs_per_warp, n_pairs);
+	const unsigned count = p0 < p_end ? (unsigned) (p_end - p0) : 0u;
+	auto src_of = [&](unsigned long long pair) {
+		return sets + (pair / pairs_per_tree) * tree_stride + (pair % pairs_per_tree) * (unsigned long long) n_blocks + tile0;
+	};
+	if (lane == 0) {
+		for (int s = 0; s < S; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	auto issue = [&](unsigned i) {      // lane 0 only: start the copy of this warp's i-th pair into stage i % S
+		const unsigned s = i % S;
+		const unsigned bar = smem_u32(bars + s);
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		             ::"r"(smem_u32(ring + (size_t) s * TILE)), "l"(src_of(p0 + i)), "r"(tile_bytes), "r"(bar) : "memory");
+	};
+	if (lane == 0) {
+		for (unsigned i = 0; i < (unsigned) (S - 1) && i < count; ++i) issue(i);
+	}
+	for (unsigned i = 0; i < count; ++i) {
+		if (lane == 0 && i + S - 1 < count) issue(i + S - 1);      // its stage was drained in iteration i - 1
+		const unsigned s = i % S, parity = (i / S) & 1u;
+		const unsigned bar = smem_u32(bars + s);
+		unsigned done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+			             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+		}
+		const uint4 *st = ring + (size_t) s * TILE + lane;
+		unsigned c = 0;
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			const uint4 v = (32u * k + lane < tile_blocks) ? st[32 * k] : ones;
+			if (!heavy) {
+				c += __popc(empty_mask(v.x, t[k].x)) + __popc(empty_mask(v.y, t[k].y)) + __popc(empty_mask(v.z, t[k].z)) + __popc(empty_mask(v.w, t[k].w));
+			} else {
+				c += cost_block(v, t[k], col0 + 32u * k, wp);
+			}
+		}
+		c = warp_sum(c);
+		if (lane == 0) atomicAdd(cost + p0 + i, c);
+		__syncwarp();        // every lane has read the stage before lane 0 refills it
+	}
+}
+
+template <int K, int S>
+static int launch_wide_tma(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree_stride, unsigned ppt, const uint4 *row,
+                           unsigned long long n_pairs, unsigned *d_cost) {
+	const unsigned W = ctx->n_blocks;
+	const unsigned tiles = (W + 32 * K - 1) / (32 * K);
+	unsigned ppw = 64;
+	while (ppw > 4 && (unsigned long long) tiles * ((n_pairs + 8ull * ppw - 1) / (8ull * ppw)) < 4ull * ctx->sm_count) ppw >>= 1;
+	unsigned long long groups = (n_pairs + 8ull * ppw - 1) / (8ull * ppw);
+	if (groups > 65535ull) {
+		ppw = (unsigned) ((n_pairs + 8ull * 65535ull - 1) / (8ull * 65535ull));
+		groups = (n_pairs + 8ull * ppw - 1) / (8ull * ppw);
+	}
+	const size_t smem = (size_t) 8 * S * 32 * K * 16 + 8 * S * sizeof(unsigned long long);
+	XMP_CUDA(cudaFuncSetAttribute(k_score_wide_tma<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	dim3 grid(tiles, (unsigned) groups);
+	k_score_wide_tma<K, S><<<grid, 256, smem, ctx->stream>>>(d_sets, tree_stride, ppt, row, ctx->wp, W, n_pairs, ppw, d_cost);
+	return XMP_OK;
+}
+
 int launch_score_sets(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree_stride, size_t n_pairs, unsigned ppt,
                       unsigned taxon, const unsigned *d_base, unsigned bound, unsigned *d_cost, unsigned *d_surv,
                       unsigned *d_nsurv) {
@@ -164,7 +262,14 @@ int launch_score_sets(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree
 	if (d_nsurv) XMP_CUDA(cudaMemsetAsync(d_nsurv, 0, sizeof(unsigned), ctx->stream));
 	if (W >= 64) {
 		XMP_CUDA(cudaMemsetAsync(d_cost, 0, n_pairs * sizeof(unsigned), ctx->stream));
-		if (W >= 256) launch_wide<8>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
+		static const bool use_tma = getenv("XMP_SCORE_TMA") && atoi(getenv("XMP_SCORE_TMA")) != 0;
+		static const int tma_variant = getenv("XMP_SCORE_TMA") ? atoi(getenv("XMP_SCORE_TMA")) : 0;
+		if (W >= 256 && use_tma) {
+			// 1: three stages, two CTAs per SM (the best TMA configuration measured); 2: four stages, one CTA per SM
+			int rc = tma_variant == 2 ? launch_wide_tma<8, 4>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost)
+			                          : launch_wide_tma<8, 3>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
+			if (rc) return rc;
+		} else if (W >= 256) launch_wide<8>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
 		else if (W >= 128) launch_wide<4>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
 		else launch_wide<2>(ctx, d_sets, tree_stride, ppt, row, n_pairs, d_cost);
 		if (d_surv) {
