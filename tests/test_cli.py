@@ -1,0 +1,76 @@
+"""The fastdnamp_b200 command line where no GPU is needed: option handling, settings report, lower-bound
+only runs (restBound.txt), reader errors, and the loud failure when a search is requested without a
+device.  The search itself is covered by tests/test_gpu.py."""
+import os
+import subprocess
+
+import pytest
+
+from tests.conftest import ROOT
+
+EXE = os.path.join(ROOT, "fastdnamp_b200")
+
+
+def run(args, cwd):
+    return subprocess.run([EXE] + args, cwd=cwd, capture_output=True, text=True)
+
+
+def test_usage_and_bad_options(tmp_path):
+    r = run([], tmp_path)
+    assert r.returncode == 0 and "Syntax: fastDNAmp [<options>] <phylipfile>" in r.stderr and "--gpus=<nn>" in r.stderr
+    r = run(["-h"], tmp_path)
+    assert r.returncode == 0 and "-m <nn>      Maximum number of trees to save" in r.stderr
+    r = run(["--nosuchoption=3", "x.phy"], tmp_path)
+    assert r.returncode == 1 and "Unrecognised option '--nosuchoption=3', aborting." in r.stderr
+    r = run(["-Z"], tmp_path)
+    assert r.returncode == 1 and "Unrecognised option '-Z', aborting." in r.stderr
+    r = run(["missing.phy"], tmp_path)
+    assert r.returncode == 1 and "File 'missing.phy' could not be opened for input, aborting." in r.stderr
+    r = run(["-Bx", "missing.phy"], tmp_path)
+    assert r.returncode == 1 and "Unknown bound type 'x'." in r.stderr
+
+
+@pytest.mark.parametrize("name", ["mt-10", "h3", "EukaryotesrDNA"])
+def test_lower_bound_only_run_matches_reference(alignment_dir, goldens, tmp_path, name):
+    """--onlycomputelowerbound=Y: everything up to the search, which is all host C: the settings report,
+    the preprocessing report, the MST upper bound line and restBound.txt must be the reference's."""
+    g = goldens[name]
+    r = run(["--tbr=N", "--seed=1", "--displaynewtrees=n", "--updatesecs=0", "--onlycomputelowerbound=Y", "--savereordereddataset=Y",
+             str(alignment_dir / g["alignment"])], tmp_path)
+    assert r.returncode == 0, r.stderr
+    e = r.stderr
+    assert e.startswith("fastDNAmp: Exact Maximum Parsimony Phylogenetic Tree Search v1.1\n\n")
+    for line in ("No initial bound specified.", "All optimal trees will be saved.", "All sites will be processed.",
+                 "Sites containing gaps or ambiguous characters will be retained.", "Trees will be output in NEXUS format.",
+                 "New trees will not be reported as they occur.", "The distinct-bases-per-site bound will be used.",
+                 "The program will exit after computing lower bounds.",
+                 "Using random number seed 1.  First 3 random numbers: 1804289383, 846930886, 1681692777.",
+                 "%d constant sites." % g["constant_sites"],
+                 "%d non-parsimoniously-informative sites, having a total weight of %d." % (g["nonpi_sites"], g["constant_weight"]),
+                 "%d parsimoniously-informative sites." % g["pi_sites"],
+                 "Improving initial upper bound to %d, based on minimum spanning tree weight." % g["initial_upper_bound"]):
+        assert line in e, line
+    rb = [[int(x) for x in l.split()] for l in (tmp_path / "restBound.txt").read_text().splitlines()[1:]]
+    assert rb == g["rest_bound"]
+    order = [int(l[1:10]) for l in (tmp_path / "reordered.phy").read_text().splitlines()[1:]]
+    assert order == g["taxon_order"]
+
+
+def test_reader_errors_reach_the_user(alignment_dir, tmp_path):
+    r = run([str(alignment_dir / "phylip_format_testing" / "bad1_T3_missing_1_base.phy")], tmp_path)
+    assert r.returncode == 1 and "contains 1 fewer sites than the first line in this group, aborting." in r.stderr
+    f = tmp_path / "three.phy"
+    f.write_text("3 4\nA         ACGT\nB         ACGT\nC         ACGT\n")
+    r = run([str(f)], tmp_path)
+    assert r.returncode == 1 and "You must have four or more taxa to perform this analysis." in r.stderr
+    r = run(["-Bp", str(alignment_dir / "h3.phy")], tmp_path)
+    assert r.returncode == 1 and "-Bf" in r.stderr
+
+
+def test_search_without_a_device_fails_loudly(alignment_dir, tmp_path):
+    import xmp_b200.cuda as xc
+    if xc.lib().xmp_cuda_device_count() > 0:
+        pytest.skip("this check is for machines without a GPU")
+    r = run(["-q", str(alignment_dir / "h3.phy")], tmp_path)
+    assert r.returncode == 1 and "No CUDA device found.  This program has no CPU search path, aborting." in r.stderr
+    assert r.stdout == ""

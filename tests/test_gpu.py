@@ -130,6 +130,17 @@ def test_score_batch_matches_oracle(ctx, torch, n_blocks, weighted):
     assert (d_cost.cpu().numpy().astype(np.uint32) == want).all()
 
 
+def test_tma_staged_scorer_gives_the_same_costs():
+    """XMP_SCORE_TMA selects the TMA bulk-copy version of the wide scorer (read once per process, hence a
+    child process): same parity tests, both ring configurations."""
+    import sys
+    for variant in ("1", "2"):
+        env = dict(os.environ, XMP_SCORE_TMA=variant)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu.py"), "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                            "-k", "score_batch_matches_oracle and (300 or 513)"], env=env, capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-2000:]
+
+
 def test_score_batch_empty_and_single(ctx, torch):
     rng = np.random.default_rng(1)
     rows = np.stack([ol.random_sets(rng, 32) for _ in range(4)])
@@ -218,6 +229,36 @@ def test_search_matches_reference(xc, alignment_dir, goldens, name):
     check_against_golden(name, g, p, score, n, trees)
     print("\n%s: %.3f s device, %d nodes (reference %d, %.2f s CPU), %d batches" %
           (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
+
+
+def test_search_random_alignments_with_ambiguity_codes(xc, tmp_path):
+    """Seeded random alignments (IUPAC ambiguity codes, gaps, repeated columns so that weights exceed 1, few
+    taxa so that the oracle is instant): host preprocessing + device search against the oracle search."""
+    from xmp_b200 import hostlib as xh
+    rng = np.random.default_rng(2026)
+    alphabet = np.array(list("ACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    checked = 0
+    for case in range(24):
+        n, sites = int(rng.integers(4, 10)), int(rng.integers(8, 60))
+        base = rng.integers(0, len(alphabet), (n, sites))
+        # evolve columns a little so that they are informative, then repeat some of them
+        for t in range(1, n):
+            keep = rng.random(sites) < 0.6
+            base[t, keep] = base[rng.integers(0, t), keep]
+        cols = rng.integers(0, sites, sites * 2)
+        text = "%d %d\n" % (n, len(cols)) + "".join("T%-9d%s\n" % (t, "".join(alphabet[base[t, cols]])) for t in range(n))
+        f = tmp_path / ("rand%d.phy" % case)
+        f.write_text(text)
+        a = xh.Alignment(str(f))
+        p = xh.Problem(a, options=xh.OPT_USEDISTBASESBOUNDREST | xh.OPT_IMPROVEINITUPPERBOUND | (xh.OPT_USEMSTBOUNDREST if case % 3 == 0 else 0))
+        if p.num_sites == 0:
+            continue
+        want_score, want_n, want_trees, _, _ = ol.search(p)
+        score, n_trees, paths, _ = xc.search(p, flags=(xc.SEARCH_NO_FUSE if case % 4 == 1 else 0))
+        assert (score, n_trees) == (want_score, want_n), case
+        assert p.newick_list(paths) == want_trees, case       # same trees, and in the reference's DFS order
+        checked += 1
+    assert checked >= 15
 
 
 def test_search_its36_with_loaded_partition_bound(xc, alignment_dir, goldens, tmp_path):

@@ -103,6 +103,7 @@ k_score_group(const uint4 *__restrict__ sets, unsigned long long tree_stride, un
               const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned n_blocks, unsigned long long n_pairs,
               const unsigned *__restrict__ base_score, unsigned bound, unsigned rest,
               unsigned *__restrict__ cost, unsigned *__restrict__ survivors, unsigned *n_survivors) {
+	__shared__ unsigned s_warp[9];
 	const unsigned long long gthread = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned long long pair = gthread / G;
 	const unsigned sub = (unsigned) (gthread % G);
@@ -122,8 +123,8 @@ k_score_group(const uint4 *__restrict__ sets, unsigned long long tree_stride, un
 			keep = accept_insertion(s, bound, base, rest);
 		}
 	}
-	if (survivors) {
-		unsigned slot = warp_append(keep, n_survivors);
+	if (survivors) {      // uniform over the grid
+		unsigned slot = block_append(keep, n_survivors, s_warp);
 		if (keep) survivors[slot] = (unsigned) pair;
 	}
 }
