@@ -344,10 +344,7 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 			}
 			down[e] = d;
 			rec[(size_t) e * n_blocks + col] = fitch_block(up[e], d);
-			if (store_all) {
-				rec[((size_t) E + e) * n_blocks + col] = up[e];
-				rec[((size_t) 2 * E + e) * n_blocks + col] = d;
-			}
+			if (store_all) rec[((size_t) E + e) * n_blocks + col] = up[e];
 		}
 	}
 	if (tree_len) {

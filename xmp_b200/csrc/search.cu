@@ -16,8 +16,8 @@
 //                    MIDPOINT in pre-order).
 //
 // Frontier layout in HBM: one pool per tree size m.  A node is a header (score, insertion path,
-// topology as three byte arrays over edge ids) plus a record of 3 * (2m-3) state sets laid out
-// [MIDPOINT | UP | DOWN][edge][block], so the scoring kernel streams a contiguous MIDPOINT array per
+// topology as three byte arrays over edge ids) plus a record of 2 * (2m-3) state sets laid out
+// [MIDPOINT | UP][edge][block] (DOWN sets are transient), so the scoring kernel streams a contiguous MIDPOINT array per
 // node.  Pools are stacks: the scheduler always expands the deepest level that holds a worthwhile
 // batch, which bounds memory like a depth-first search while keeping launches wide.
 //
@@ -213,7 +213,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
 		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
 		uint4 *CM = child.sets + (child_first + s) * child.rec + col;
-		uint4 *CU = CM + (unsigned long long) Ec * W, *CD = CU + (unsigned long long) Ec * W;
+		uint4 *CU = CM + (unsigned long long) Ec * W;      // DOWN sets are not kept: no later step reads them
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
 		const unsigned n_up = cw.init(ph, L, m, v, PU, __ldg(rows + (size_t) m * W + col), upath, T);
@@ -232,7 +232,6 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
 			CU[(size_t) x * W] = ux;
-			CD[(size_t) x * W] = dn;
 			CM[(size_t) x * W] = fitch_block(ux, dn);
 			x = xn; sb = sbn; d = dnx; ux = uxn; us = usn;
 		}
@@ -417,6 +416,7 @@ struct Search {
 	uint4 *d_surv_arena = nullptr;
 	unsigned *d_nsurv_lvl = nullptr;                           // [XMP_MAX_TAXA + 1] counters, one per level
 	bool sweep = true;
+	unsigned sweep_fallback = 1;
 	uint8_t *d_trees[2] = {nullptr, nullptr};
 	int cur = 0;
 	unsigned trees_cap = 0, ntrees_dev = 0;
@@ -425,7 +425,7 @@ struct Search {
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
-	unsigned min_batch = 4096, beam = 512, policy = 1;
+	unsigned min_batch = 32768, beam = 512, policy = 1;
 	xmp_search_stats st;
 	Scratch topo, pathbuf;
 };
@@ -484,7 +484,11 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 
 	size_t free_b = 0, total_b = 0;
 	XMP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>(free_b / 2, (size_t) 16 << 30);
+	// Default frontier budget: deep searches (many tree sizes in flight at once) profit from large pools --
+	// batches stay big -- while allocating tens of GiB costs tens of milliseconds, which short searches on
+	// few taxa would notice (profiles/r01_search_tuning.md).
+	const size_t dflt = n >= 17 ? ((size_t) 48 << 30) : ((size_t) 12 << 30);
+	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>(free_b / 2, dflt);
 	S->trees_cap = 1u << 20;
 	const size_t fixed = 2 * (size_t) S->trees_cap * L.trec + ((size_t) 64 << 20);
 	if (budget < fixed + ((size_t) 64 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
@@ -500,11 +504,11 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		for (unsigned m = 3; m < n; ++m) {
 			double c = std::min(C, odd_factorial(m));
 			if (m + 1 == n) c = std::min(c, last_cap);
-			tot += c * ((double) 3 * (2 * m - 3) * W * 16 + L.HB + 16);   // + its slot in a survivor list
+			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + L.HB + 16);   // + its slot in a survivor list
 		}
 		return tot + 2 * C * 16;   // survivors of the single-batch path and of the fused level
 	};
-	double lo = 256, hi = 4194304.0;
+	double lo = 256, hi = 16777216.0;
 	if (bytes_for(lo) > (double) budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
 	while (hi - lo > 1) {
 		double mid = (lo + hi) / 2;
@@ -514,7 +518,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	for (unsigned m = 3; m < n; ++m) {
 		Pool &P = S->pool[m];
 		P.E = 2 * m - 3;
-		P.rec = 3ull * P.E * W;
+		P.rec = 2ull * P.E * W;       // [MIDPOINT | UP][edge][block]
 		P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
 		if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
 		P.count = 0;
@@ -850,25 +854,41 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 	// A level joins the sweep only if it brings a worthwhile batch: every launch costs tens of microseconds
 	// whatever its size, so a handful of open trees is better left to accumulate.  If nothing qualifies
 	// (the tail of a search), everything goes.
-	for (unsigned threshold = S->min_batch; n_items == 0; threshold = 1) {
-		for (unsigned m = n - 2; m >= 3; --m) {
-			Pool &P = S->pool[m];
-			if (P.count == 0) continue;
-			const bool fused = S->fused_last && m + 2 == n;
-			const unsigned long long base_next = fused ? 0 : S->pool[m + 1].count - taken[m + 1];
-			unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - base_next);
-			const unsigned long long chunk = std::min(P.count, room / P.E);
-			if (chunk == 0 || chunk < std::min<unsigned long long>(threshold, P.cap)) continue;
-			const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level;
-			int rc = launch_expand(ctx, S, m, P.count - chunk, chunk, shard, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
-			if (rc) return rc;
-			rc = fused ? launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv_lvl[m], S->d_nsurv_lvl + m)
-			           : launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, base_next);
-			if (rc) return rc;
-			taken[m] = chunk;
-			items[n_items++] = Item{m, chunk, fused};
+	// chunk each level could take right now (deepest first, so that room below reflects this sweep's removals
+	// is decided while launching); first find out whether any level brings a worthwhile batch
+	unsigned long long best_chunk = 0;
+	unsigned best_level = 0;
+	bool worthwhile = false;
+	for (unsigned m = n - 2; m >= 3; --m) {
+		Pool &P = S->pool[m];
+		if (P.count == 0) continue;
+		const bool fused = S->fused_last && m + 2 == n;
+		const unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - S->pool[m + 1].count);
+		const unsigned long long chunk = std::min(P.count, room / P.E);
+		if (chunk >= std::min<unsigned long long>(S->min_batch, P.cap)) worthwhile = true;
+		if (chunk > best_chunk) { best_chunk = chunk; best_level = m; }
+	}
+	for (unsigned m = n - 2; m >= 3; --m) {
+		Pool &P = S->pool[m];
+		if (P.count == 0) continue;
+		const bool fused = S->fused_last && m + 2 == n;
+		const unsigned long long base_next = fused ? 0 : S->pool[m + 1].count - taken[m + 1];
+		unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - base_next);
+		const unsigned long long chunk = std::min(P.count, room / P.E);
+		if (chunk == 0) continue;
+		if (worthwhile) {
+			if (chunk < std::min<unsigned long long>(S->min_batch, P.cap)) continue;
+		} else if (S->sweep_fallback == 1 && m != best_level) {
+			continue;        // nothing worthwhile: grow the frontier from its fullest level only
 		}
-		if (threshold == 1) break;
+		const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level;
+		int rc = launch_expand(ctx, S, m, P.count - chunk, chunk, shard, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
+		if (rc) return rc;
+		rc = fused ? launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv_lvl[m], S->d_nsurv_lvl + m)
+		           : launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, base_next);
+		if (rc) return rc;
+		taken[m] = chunk;
+		items[n_items++] = Item{m, chunk, fused};
 	}
 	if (n_items == 0) return XMP_OK;
 	*any = true;
@@ -965,10 +985,11 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
 	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
 	S->n = ctx->num_taxa;
-	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 4096), 1u);
+	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
 	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
 	S->policy = env_unsigned("XMP_POLICY", 1);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
+	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
 	memset(&S->st, 0, sizeof S->st);
 	int rc = alloc_search(ctx, S);
 	if (rc) { search_destroy(ctx); return rc; }
