@@ -15,7 +15,7 @@ for rep in range(2):
         t0 = time.perf_counter(); p = xh.Problem(a); t1 = time.perf_counter()
         ctx = xc.Context(0); t2 = time.perf_counter()
         ctx.load_problem(p); t3 = time.perf_counter()
-        ctx.search_begin(bound=p.bound); t4 = time.perf_counter()
+        ctx.search_begin(bound=p.bound, mem_budget=int(float(os.environ.get('XMP_BUDGET_GB', '0')) * 2**30)); t4 = time.perf_counter()
         while not ctx.search_run(0): pass
         t5 = time.perf_counter()
         score, n, paths = ctx.search_result(); st = ctx.search_stats(); t6 = time.perf_counter()

@@ -47,6 +47,7 @@ struct PoolView {
 	uint8_t *hdr;
 	uint4 *sets;
 	unsigned long long rec;   // uint4 per node
+	unsigned long long cap;   // slots; pools are rings: slot = index modulo cap
 };
 
 __device__ __forceinline__ unsigned path_hash(const uint8_t *path, unsigned m, unsigned e) {
@@ -70,7 +71,8 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	const unsigned long long pair = gthread / G;
 	const unsigned sub = (unsigned) (gthread % G);
 	const bool valid = pair < n_nodes * E;
-	const unsigned long long node = first + pair / E;
+	unsigned long long node = first + pair / E;
+	if (node >= pool.cap) node -= pool.cap;              // the batch may wrap around the end of the ring
 	const unsigned e = (unsigned) (pair % E);
 	unsigned s = 0;
 	__syncthreads();
@@ -195,24 +197,28 @@ struct ChildWalk {
 // included.
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
-                 const unsigned *n_surv_ptr, unsigned long long child_first, const uint4 *__restrict__ rows,
-                 unsigned long long *merges, unsigned D) {
+                 const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
+                 const uint4 *__restrict__ rows, unsigned long long *merges, unsigned D) {
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
 	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
-	const unsigned n_surv = *n_surv_ptr;
+	// survivors s_begin .. min(*n_surv_ptr, s_end) - 1 become children child_first, child_first + 1, ...
+	const unsigned n_surv = min(*n_surv_ptr, s_end);
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2;
-	const unsigned long long total = (unsigned long long) n_surv * W;
+	const unsigned long long total = n_surv > s_begin ? (unsigned long long) (n_surv - s_begin) * W : 0ull;
 	unsigned my_merges = 0;
 	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
 	     idx += (unsigned long long) gridDim.x * blockDim.x) {
-		const unsigned s = (unsigned) (idx / W), col = (unsigned) (idx % W);
+		const unsigned k = (unsigned) (idx / W), col = (unsigned) (idx % W);
+		const unsigned s = s_begin + k;
+		unsigned long long cslot = child_first + k;
+		if (cslot >= child.cap) cslot -= child.cap;
 		const uint4 sv = surv[s];
 		const unsigned pnode = sv.x, v = sv.y;
 		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
 		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
-		uint4 *CM = child.sets + (child_first + s) * child.rec + col;
+		uint4 *CM = child.sets + cslot * child.rec + col;
 		uint4 *CU = CM + (unsigned long long) Ec * W;      // DOWN sets are not kept: no later step reads them
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
@@ -237,7 +243,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		}
 		if (col == 0) {
 			// header: copy, then re-derive everything the insertion changed
-			uint8_t *ch = child.hdr + (size_t) (child_first + s) * L.HB;
+			uint8_t *ch = child.hdr + (size_t) cslot * L.HB;
 			for (unsigned i = 0; i < L.HB / 16; ++i) ((uint4 *) ch)[i] = ((const uint4 *) ph)[i];
 			*(unsigned *) ch = sv.z;
 			ch[HDR_PATH + m] = (uint8_t) v;
@@ -398,8 +404,10 @@ struct Pool {
 	uint8_t *hdr = nullptr;
 	uint4 *sets = nullptr;
 	unsigned long long cap = 0, count = 0, rec = 0;
+	unsigned long long head = 0;          // ring: open nodes occupy slots head .. head + count - 1 (modulo cap)
 	unsigned E = 0;
-	PoolView view() const { return PoolView{hdr, sets, rec}; }
+	PoolView view() const { return PoolView{hdr, sets, rec, cap}; }
+	unsigned long long slot(unsigned long long i) const { return (head + i) % cap; }
 };
 
 struct Search {
@@ -417,6 +425,11 @@ struct Search {
 	unsigned *d_nsurv_lvl = nullptr;                           // [XMP_MAX_TAXA + 1] counters, one per level
 	bool sweep = true;
 	unsigned sweep_fallback = 1;
+	// A level whose batch produced more children than the next pool could take keeps the batch at the head
+	// of its ring and builds the remaining survivors in later sweeps.
+	struct Pending { bool active = false; unsigned long long chunk = 0; unsigned head = 0, ns = 0; };
+	Pending pend[XMP_MAX_TAXA + 2];
+	double rate[XMP_MAX_TAXA + 2];        // survivors per scored pair seen so far, per level (sizes the batches)
 	uint8_t *d_trees[2] = {nullptr, nullptr};
 	int cur = 0;
 	unsigned trees_cap = 0, ntrees_dev = 0;
@@ -504,9 +517,9 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		for (unsigned m = 3; m < n; ++m) {
 			double c = std::min(C, odd_factorial(m));
 			if (m + 1 == n) c = std::min(c, last_cap);
-			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + L.HB + 16);   // + its slot in a survivor list
+			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + L.HB + 64);   // + four slots in a survivor list
 		}
-		return tot + 2 * C * 16;   // survivors of the single-batch path and of the fused level
+		return tot + 5 * C * 16;   // survivors of the single-batch path and of the fused level
 	};
 	double lo = 256, hi = 16777216.0;
 	if (bytes_for(lo) > (double) budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
@@ -534,7 +547,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		// keeps them only until the fused kernel has consumed them)
 		unsigned long long total = 0;
 		for (unsigned m = 3; m + 1 < n; ++m) {
-			S->surv_cap_lvl[m] = (S->fused_last && m + 2 == n) ? S->surv_cap : S->pool[m + 1].cap;
+			S->surv_cap_lvl[m] = (S->fused_last && m + 2 == n) ? 4 * S->surv_cap : 4 * S->pool[m + 1].cap;
 			total += S->surv_cap_lvl[m];
 		}
 		XMP_CUDA(cudaMalloc(&S->d_surv_arena, (size_t) std::max<unsigned long long>(total, 1) * 16));
@@ -571,6 +584,8 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			unsigned part = (unsigned) std::min<size_t>(k - done, 65536);
 			Pool &P = S->pool[m];
 			if (P.count + part > P.cap) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m, P.cap);
+			const unsigned long long tail = P.slot(P.count);
+			part = (unsigned) std::min<unsigned long long>(part, P.cap - tail);      // up to the end of the ring, the rest next time
 			const unsigned E = 2 * m - 3, stride = (E + 15u) & ~15u;
 			std::vector<uint8_t> h((size_t) part * 4 * stride, 0xFF);
 			HostTopo t;
@@ -589,9 +604,9 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			if (rc) return rc;
 			XMP_CUDA(cudaMemcpyAsync(S->topo.ptr, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
 			XMP_CUDA(cudaMemcpyAsync(S->pathbuf.ptr, sel.data() + done * L.n, (size_t) part * L.n, cudaMemcpyHostToDevice, ctx->stream));
-			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, P.sets + P.count * P.rec, (size_t) P.rec, true, S->d_len);
+			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, P.sets + tail * P.rec, (size_t) P.rec, true, S->d_len);
 			if (rc) return rc;
-			k_write_headers<<<(part + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, P.count, part, (const uint8_t *) S->topo.ptr, stride,
+			k_write_headers<<<(part + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
 			                                                            (const uint8_t *) S->pathbuf.ptr, S->d_len);
 			XMP_CUDA(cudaGetLastError());
 			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -639,15 +654,16 @@ static unsigned walk_threads(unsigned D, size_t *smem) {
 	return threads;
 }
 
-static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *surv, const unsigned *nsurv, unsigned long long child_first) {
+static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *surv, const unsigned *nsurv, unsigned long long child_first,
+                           unsigned s_begin = 0, unsigned s_end = 0xffffffffu) {
 	Pool &P = S->pool[m], &C = S->pool[m + 1];
 	const unsigned D = m + 1;
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, child_first, ctx->d_rows,
-	                                                         S->d_merges, D);
+	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+	                                                         ctx->d_rows, S->d_merges, D);
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -733,7 +749,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 	Pool &P = S->pool[m];
 	const bool last = (m + 1 == S->n);
 	const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level && keep_best == 0;
-	const unsigned long long first = P.count - chunk;
+	const unsigned long long first = P.slot(P.count - chunk);      // most recent nodes first (stack order)
 	if (!last) XMP_CUDA(cudaMemsetAsync(S->d_nsurv, 0, sizeof(unsigned), ctx->stream));
 	int rc = launch_expand(ctx, S, m, first, chunk, shard, S->d_surv, S->d_nsurv);
 	if (rc) return rc;
@@ -813,7 +829,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		P.count -= chunk;
 		return tidy_trees(ctx, S);
 	}
-	rc = launch_children(ctx, S, m, S->d_surv, S->d_nsurv, S->pool[m + 1].count);
+	rc = launch_children(ctx, S, m, S->d_surv, S->d_nsurv, S->pool[m + 1].slot(S->pool[m + 1].count));
 	if (rc) return rc;
 	rc = fetch_counters(ctx, S);
 	if (rc) return rc;
@@ -845,64 +861,104 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 		*any = true;
 		return run_batch(ctx, S, n - 1, std::min(P.count, room), 0);
 	}
-	struct Item { unsigned m; unsigned long long chunk; bool fused; };
+	struct Item { unsigned m; unsigned long long chunk, room; bool fused, cont; };
 	Item items[XMP_MAX_TAXA + 2];
 	unsigned n_items = 0;
-	unsigned long long taken[XMP_MAX_TAXA + 2] = {0};
 	const unsigned before = S->ntrees_dev;
-	XMP_CUDA(cudaMemsetAsync(S->d_nsurv_lvl, 0, 4 * (XMP_MAX_TAXA + 1), ctx->stream));
+	// Batch of level m: as many of its oldest open trees as the next pool can be EXPECTED to absorb, going by
+	// the survival rate seen so far (a worst-case bound of 2m-3 children per tree would keep batches an order
+	// of magnitude smaller).  If more children survive than fit, the batch stays put and the rest of its
+	// survivor list is built in later sweeps (Pending).
+	auto plan = [&](unsigned m, unsigned long long room_next) -> unsigned long long {
+		Pool &P = S->pool[m];
+		const bool fused = S->fused_last && m + 2 == n;
+		if (P.count == 0 || S->pend[m].active) return 0;
+		const double per_tree = fused ? (double) P.E : std::max(1.0, P.E * std::min(1.0, S->rate[m] * 1.25));
+		unsigned long long chunk = fused ? P.count : (unsigned long long) ((double) room_next / per_tree);
+		chunk = std::min(chunk, S->surv_cap_lvl[m] / P.E);        // the survivor list itself must never overflow
+		return std::min(chunk, P.count);
+	};
 	// A level joins the sweep only if it brings a worthwhile batch: every launch costs tens of microseconds
-	// whatever its size, so a handful of open trees is better left to accumulate.  If nothing qualifies
-	// (the tail of a search), everything goes.
-	// chunk each level could take right now (deepest first, so that room below reflects this sweep's removals
-	// is decided while launching); first find out whether any level brings a worthwhile batch
+	// whatever its size.  If nothing qualifies (the start and the tail of a search) only the fullest level
+	// goes, which grows the frontier (XMP_SWEEP_FALLBACK=0: every level goes).
 	unsigned long long best_chunk = 0;
 	unsigned best_level = 0;
 	bool worthwhile = false;
 	for (unsigned m = n - 2; m >= 3; --m) {
-		Pool &P = S->pool[m];
-		if (P.count == 0) continue;
 		const bool fused = S->fused_last && m + 2 == n;
-		const unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - S->pool[m + 1].count);
-		const unsigned long long chunk = std::min(P.count, room / P.E);
-		if (chunk >= std::min<unsigned long long>(S->min_batch, P.cap)) worthwhile = true;
+		const unsigned long long room_next = fused ? 0 : S->pool[m + 1].cap - S->pool[m + 1].count;
+		if (S->pend[m].active) {
+			if (room_next) worthwhile = true;      // it can move on
+			continue;
+		}
+		const unsigned long long chunk = plan(m, room_next);
+		if (chunk >= std::min<unsigned long long>(S->min_batch, S->pool[m].cap)) worthwhile = true;
 		if (chunk > best_chunk) { best_chunk = chunk; best_level = m; }
 	}
-	for (unsigned m = n - 2; m >= 3; --m) {
-		Pool &P = S->pool[m];
-		if (P.count == 0) continue;
-		const bool fused = S->fused_last && m + 2 == n;
-		const unsigned long long base_next = fused ? 0 : S->pool[m + 1].count - taken[m + 1];
-		unsigned long long room = fused ? S->surv_cap_lvl[m] : std::min(S->surv_cap_lvl[m], S->pool[m + 1].cap - base_next);
-		const unsigned long long chunk = std::min(P.count, room / P.E);
-		if (chunk == 0) continue;
-		if (worthwhile) {
-			if (chunk < std::min<unsigned long long>(S->min_batch, P.cap)) continue;
-		} else if (S->sweep_fallback == 1 && m != best_level) {
-			continue;        // nothing worthwhile: grow the frontier from its fullest level only
+	// pass 0 applies the selection above; pass 1 (only if pass 0 launched nothing) lets every level go that can
+	for (int pass = 0; pass < 2 && n_items == 0; ++pass) {
+		for (unsigned m = n - 2; m >= 3; --m) {
+			Pool &P = S->pool[m];
+			const bool fused = S->fused_last && m + 2 == n;
+			const unsigned long long room_next = fused ? 0 : S->pool[m + 1].cap - S->pool[m + 1].count;
+			if (!fused && S->pend[m].active) {
+				Search::Pending &pd = S->pend[m];
+				const unsigned long long take = std::min<unsigned long long>(pd.ns - pd.head, room_next);
+				if (take == 0) continue;
+				// the level's counter still holds the length of the list written by its last scoring pass
+				int rc = launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, S->pool[m + 1].slot(S->pool[m + 1].count),
+				                         pd.head, pd.head + (unsigned) take);
+				if (rc) return rc;
+				items[n_items++] = Item{m, take, 0, false, true};
+				continue;
+			}
+			const unsigned long long chunk = plan(m, room_next);
+			if (chunk == 0) continue;
+			if (pass == 0) {
+				if (worthwhile) {
+					if (chunk < std::min<unsigned long long>(S->min_batch, P.cap)) continue;
+				} else if (S->sweep_fallback == 1 && m != best_level) {
+					continue;
+				}
+			}
+			const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level;
+			XMP_CUDA(cudaMemsetAsync(S->d_nsurv_lvl + m, 0, sizeof(unsigned), ctx->stream));
+			int rc = launch_expand(ctx, S, m, P.slot(0), chunk, shard, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
+			if (rc) return rc;
+			const unsigned s_end = (unsigned) std::min<unsigned long long>(room_next, 0xffffffffull);
+			rc = fused ? launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv_lvl[m], S->d_nsurv_lvl + m)
+			           : launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, S->pool[m + 1].slot(S->pool[m + 1].count), 0, s_end);
+			if (rc) return rc;
+			items[n_items++] = Item{m, chunk, room_next, fused, false};
 		}
-		const bool shard = S->prm.shard_count > 1 && m + 1 == S->split_level;
-		int rc = launch_expand(ctx, S, m, P.count - chunk, chunk, shard, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
-		if (rc) return rc;
-		rc = fused ? launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv_lvl[m], S->d_nsurv_lvl + m)
-		           : launch_children(ctx, S, m, S->d_surv_lvl[m], S->d_nsurv_lvl + m, base_next);
-		if (rc) return rc;
-		taken[m] = chunk;
-		items[n_items++] = Item{m, chunk, fused};
 	}
 	if (n_items == 0) return XMP_OK;
 	*any = true;
 	int rc = fetch_counters(ctx, S);
 	if (rc) return rc;
-	for (unsigned i = 0; i < n_items; ++i) S->pool[items[i].m].count -= items[i].chunk;
 	for (unsigned i = 0; i < n_items; ++i) {
 		const unsigned m = items[i].m;
-		const unsigned ns = S->h_pin[8 + m];
 		Pool &P = S->pool[m];
+		if (items[i].cont) {
+			Search::Pending &pd = S->pend[m];
+			pd.head += (unsigned) items[i].chunk;
+			S->pool[m + 1].count += items[i].chunk;
+			S->st.children += items[i].chunk;
+			if (pd.head == pd.ns) {
+				P.head = P.slot(pd.chunk);
+				P.count -= pd.chunk;
+				pd.active = false;
+			}
+			continue;
+		}
+		const unsigned ns = S->h_pin[8 + m];
 		S->st.nodes += items[i].chunk;
 		S->st.score_calls += items[i].chunk * P.E;
-		S->st.children += ns;
+		S->rate[m] = std::max((double) ns / ((double) items[i].chunk * P.E), 0.5 * S->rate[m]);
 		if (items[i].fused) {
+			P.head = P.slot(items[i].chunk);
+			P.count -= items[i].chunk;
+			S->st.children += ns;
 			S->st.nodes += ns;
 			S->st.score_calls += (unsigned long long) ns * (P.E + 2);
 			if (S->h_pin[2] > S->trees_cap) {
@@ -937,8 +993,19 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 				S->st.full_trees += S->h_pin[2] - before;
 				S->ntrees_dev = S->h_pin[2];
 			}
+			continue;
+		}
+		const unsigned long long built = std::min<unsigned long long>(ns, items[i].room);
+		S->pool[m + 1].count += built;
+		S->st.children += built;
+		if (ns > built) {
+			S->pend[m].active = true;
+			S->pend[m].chunk = items[i].chunk;
+			S->pend[m].head = (unsigned) built;
+			S->pend[m].ns = ns;
 		} else {
-			S->pool[m + 1].count += ns;
+			P.head = P.slot(items[i].chunk);
+			P.count -= items[i].chunk;
 		}
 	}
 	S->st.iterations += 1;
@@ -962,7 +1029,7 @@ static int dive(xmp_ctx *ctx, Search *S) {
 		rc = run_batch(ctx, S, m, S->pool[m].count, S->beam);
 		if (rc) return rc;
 	}
-	for (unsigned m = 3; m < S->n; ++m) S->pool[m].count = 0;
+	for (unsigned m = 3; m < S->n; ++m) S->pool[m].count = S->pool[m].head = 0;
 	// Trees found by the dive will be found again by the search proper.
 	S->ntrees_dev = 0;
 	S->host_trees.clear();
@@ -990,6 +1057,7 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	S->policy = env_unsigned("XMP_POLICY", 1);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
+	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
 	int rc = alloc_search(ctx, S);
 	if (rc) { search_destroy(ctx); return rc; }
@@ -1039,10 +1107,9 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 			bool open = false;
 			for (unsigned m = 3; m < S->n; ++m) open |= S->pool[m].count != 0;
 			if (open) {
-				// every open level is blocked by a full pool below it, which can only be the tree buffer
-				rc = drain_trees(ctx, S);
-				if (rc) break;
-				continue;
+				// cannot happen: the deepest open level can always be expanded
+				rc = set_error(XMP_ERR_NOMEM, "the frontier is blocked: no level can be expanded (internal error)");
+				break;
 			}
 			S->done = true;
 			break;
@@ -1135,9 +1202,13 @@ extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uin
 		Pool &P = S->pool[m];
 		if (P.count == 0) continue;
 		// Like the reference's thief (src/mpiworker.c:169-181): take from the shallowest open level.
+		if (S->pend[m].active) continue;      // its oldest nodes are half expanded; newer ones sit behind them in the ring
 		unsigned k = (unsigned) std::min<unsigned long long>(P.count, max_nodes);
+		const unsigned long long tail = P.slot(P.count);         // one past the newest node
+		if (tail != 0) k = (unsigned) std::min<unsigned long long>(k, tail);   // stay on this side of the wrap
+		const unsigned long long from = (tail == 0 ? P.cap : tail) - k;
 		std::vector<uint8_t> h((size_t) k * L.HB);
-		XMP_CUDA(cudaMemcpyAsync(h.data(), P.hdr + (size_t) (P.count - k) * L.HB, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		XMP_CUDA(cudaMemcpyAsync(h.data(), P.hdr + (size_t) from * L.HB, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 		for (unsigned i = 0; i < k; ++i) {
 			uint8_t *job = jobs + (size_t) i * L.n;
