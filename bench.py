@@ -241,7 +241,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------- exact search (second half of the metric)
-BANDB_DATASETS = ["mt-10", "h1", "h4", "mh1", "mh3", "rbc14x759", "Metazoan"]
+BANDB_DATASETS = ["mt-10", "h1", "h4", "mh1", "mh3", "rbc14x759", "Metazoan", "its36"]
 
 
 def run_bandb(torch, xc, dist, rank, world, local, names):
@@ -262,7 +262,16 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
             f.write(bundle[g["alignment"]].encode("latin-1"))
         a = xh.Alignment(f.name)
         os.unlink(f.name)
-        p = xh.Problem(a)          # default options: -Bd bound, MST upper bound, like the reference run
+        if "-Bp" in g["flags"]:
+            # the author's its36 setting (-Bp -b 233 -m 100000): the partition bound is CPU precomputation in the
+            # reference; its restBound[] comes from the golden run through the -Bf mechanism
+            with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as rb:
+                rb.write("i\tbound\n" + "".join("%d\t%d\n" % (i, b) for i, b in g["rest_bound"]))
+            p = xh.Problem(a, options=xh.OPT_USELOADRESTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=int(g["flags"][g["flags"].index("-b") + 1]),
+                           rest_bound_file=rb.name)
+            os.unlink(rb.name)
+        else:
+            p = xh.Problem(a)          # default options: -Bd bound, MST upper bound, like the reference run
         ctx = xc.Context(local)
         ctx.load_problem(p)
         if dist:
