@@ -301,7 +301,10 @@ static void *worker_main(void *arg) {
 
 	for (;;) {
 		unsigned mine = 0, global;
-		if (!done && xmp_cuda_search_run(w->ctx, sh->n_workers > 1 ? SLICE_BATCHES : 0, &done)) { worker_fail(w, "searching"); break; }
+		/* slices give the other GPUs (and --displaynewbounds) a chance to see a new bound; a single GPU with
+		 * nothing to report runs straight through */
+		const unsigned slice = (sh->n_workers > 1 || sh->display_bounds) ? SLICE_BATCHES : 0;
+		if (!done && xmp_cuda_search_run(w->ctx, slice, &done)) { worker_fail(w, "searching"); break; }
 		if (xmp_cuda_search_get_bound(w->ctx, &mine)) { worker_fail(w, "reading the bound"); break; }
 
 		pthread_mutex_lock(&sh->mu);

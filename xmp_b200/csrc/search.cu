@@ -7,19 +7,21 @@
 // child tree's UP / DOWN / MIDPOINT sets and recurse; complete trees lower the bound and are recorded
 // (:195-213).  Here the same search tree is explored a batch of partial trees at a time:
 //
-//   k_expand_score   every (partial tree, edge) pair of the batch in one launch: weighted Fitch cost
-//                    (AND / empty-nibble mask / POPC), group-shuffle reduction, the reference's signed
-//                    acceptance test, ballot compaction of survivors; on the last level survivors are
-//                    complete trees: atomicMin on the bound and a tree record.
-//   k_build_children one thread per (survivor, 128-bit column): splices the new leaf into the parent's
-//                    topology and recomputes the child's state sets (UP along the root path, DOWN and
-//                    MIDPOINT in pre-order).
+//   k_expand_score      every (partial tree, edge) pair of the batch in one launch: weighted Fitch cost
+//                       (AND / empty-nibble mask / POPC), group-shuffle reduction, the reference's signed
+//                       acceptance test, ballot compaction of survivors (one counter atomic per CTA); on
+//                       the last level survivors are complete trees: atomicMin on the bound, a tree record.
+//   k_build_children    one thread per (survivor, 128-bit column): walks the child in pre-order through the
+//                       parent's walk program with the insertion spliced in, recomputes UP along the root
+//                       path and DOWN / MIDPOINT everywhere, writes the child's record and header.
+//   k_expand_last_fused the same walk for parents with n-2 taxa, but each MIDPOINT is scored against the
+//                       last taxon on the spot: the deepest level is never stored.
 //
-// Frontier layout in HBM: one pool per tree size m.  A node is a header (score, insertion path,
-// topology as three byte arrays over edge ids) plus a record of 2 * (2m-3) state sets laid out
-// [MIDPOINT | UP][edge][block] (DOWN sets are transient), so the scoring kernel streams a contiguous MIDPOINT array per
-// node.  Pools are stacks: the scheduler always expands the deepest level that holds a worthwhile
-// batch, which bounds memory like a depth-first search while keeping launches wide.
+// Frontier layout in HBM: one ring-buffer pool per tree size m.  A node is a header (length, insertion
+// path, byte arrays over edge ids, walk program) plus a record of 2 * (2m-3) state sets laid out
+// [MIDPOINT | UP][edge][block] (DOWN sets are transient), so the scoring kernel streams a contiguous
+// MIDPOINT array per node.  The scheduler (run_sweep) expands every level that holds a worthwhile batch in
+// one pass, deepest first, with a single host synchronisation per pass; pool capacities bound the memory.
 //
 // Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
 // recorded carries its length and the final filter keeps those equal to the final bound.
@@ -438,14 +440,14 @@ struct Search {
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
-	unsigned min_batch = 32768, beam = 512, policy = 1;
+	unsigned min_batch = 32768, beam = 512;
 	xmp_search_stats st;
 	Scratch topo, pathbuf;
 };
 
-// Scheduler knobs (defaults chosen on B200, see profiles/r01_search_tuning.md; overridable for tuning
-// through XMP_MIN_BATCH / XMP_BEAM): prefer levels holding at least min_batch open trees; width of the
-// initial greedy dive.
+// Scheduler knobs (defaults chosen on B200, see profiles/r01_search_tuning.md; overridable for tuning):
+// XMP_MIN_BATCH  open trees a level must offer to join a sweep, XMP_BEAM  width of the initial greedy dive,
+// XMP_SWEEP=0  one level per synchronisation, XMP_SWEEP_FALLBACK=0  every level goes when none qualifies.
 static unsigned env_unsigned(const char *name, unsigned dflt) {
 	const char *v = getenv(name);
 	if (!v || !*v) return dflt;
@@ -1054,7 +1056,6 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	S->n = ctx->num_taxa;
 	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
 	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
-	S->policy = env_unsigned("XMP_POLICY", 1);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
@@ -1117,8 +1118,9 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		++batches;
 	}
 	while (!S->sweep && !S->done && (max_batches == 0 || batches < max_batches)) {
-		// Deepest level holding a worthwhile batch; otherwise the fullest one (policy 1, default).
-		// Policy 0 falls back to the deepest non-empty level, policy 2 always takes the fullest.
+		// XMP_SWEEP=0 (kept for A/B measurements, profiles/r01_search_tuning.md): one level per host
+		// synchronisation, worst-case batch sizing; the deepest level holding a worthwhile batch, otherwise
+		// the fullest one.
 		int pick = -1, fallback = -1;
 		unsigned long long pick_chunk = 0, fallback_chunk = 0;
 		for (unsigned m = S->n - 1; m >= 3; --m) {
@@ -1130,13 +1132,11 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 			else room = (S->pool[m + 1].cap - S->pool[m + 1].count) / P.E;
 			unsigned long long chunk = std::min(P.count, room);
 			if (chunk == 0) continue;
-			if (S->policy == 0) {
-				if (fallback < 0) { fallback = (int) m; fallback_chunk = chunk; }
-			} else if (chunk > fallback_chunk) {
+			if (chunk > fallback_chunk) {
 				fallback = (int) m;
 				fallback_chunk = chunk;
 			}
-			if (S->policy != 2 && chunk >= S->min_batch) { pick = (int) m; pick_chunk = chunk; break; }
+			if (chunk >= S->min_batch) { pick = (int) m; pick_chunk = chunk; break; }
 		}
 		if (pick < 0) { pick = fallback; pick_chunk = fallback_chunk; }
 		if (pick < 0) {
