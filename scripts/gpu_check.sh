@@ -26,6 +26,6 @@ PY
   (cd /tmp/xw && $CMD > $GRAFT_REPO_ROOT/gpurun_out/h4_plain.log 2>&1 &&
    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $GRAFT_REPO_ROOT/gpurun_out/search_launches_h4.csv $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_search_h4.log 2>&1)
   (cd /tmp/xw && $CMD > /dev/null 2>&1 &&
-   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_last_fused -s 60 -c 1 -f -o $GRAFT_REPO_ROOT/gpurun_out/prof_fused_h4 $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_fused_h4.log 2>&1)
+   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_last_fused -s 12 -c 1 -f -o $GRAFT_REPO_ROOT/gpurun_out/prof_fused_h4 $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_fused_h4.log 2>&1)
 fi
 tail -6 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log; cat gpurun_out/bench.log | cut -c1-600; tail -3 gpurun_out/bench.err; cat gpurun_out/bench_ref.log | cut -c1-300
