@@ -2,6 +2,12 @@
 # Scaling run on one node: bench.py (ours and the reference arm) at N = 1, 2, 4, 8, launched the way the driver does.
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
+rm -f gpurun_out/scale_status.txt
+if [ $NG -ge 2 ]; then
+  timeout 900 python -m pytest tests/test_gpu.py -m gpu -q -k "two_gpus" --timeout=600 -p no:cacheprovider > gpurun_out/pytest_multi.log 2>&1
+  echo "two-GPU tests exit $?" >> gpurun_out/scale_status.txt
+  tail -3 gpurun_out/pytest_multi.log
+fi
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && break
   if [ $N -eq 1 ]; then

@@ -9,8 +9,10 @@ from tests import oracle_lib as ol
 
 
 class OracleEngine:
-    def __init__(self, problem):
+    def __init__(self, problem, lazy_done=True):
         self.p = problem
+        self.lazy_done = lazy_done      # like the CUDA engine before it learnt to report an empty frontier at once
+        self.wrapped_up = False
         self.n = problem.num_taxa
         self.jobs = []          # (m, path) open subtrees
         self.found = []         # (score, path)
@@ -38,6 +40,9 @@ class OracleEngine:
                 self.bound = score
             self.found.extend((score, q) for q in paths)
             done += 1
+        if self.lazy_done and done:
+            return False          # an engine may notice that it ran dry only on the next call
+        self.wrapped_up = not self.jobs
         return not self.jobs
 
     def search_get_bound(self):
@@ -67,8 +72,10 @@ class OracleEngine:
             m = int(path[0])
             path[0] = 0
             self.jobs.append((m, path))
+        self.wrapped_up = False
 
     def search_result(self):
+        assert self.wrapped_up and not self.jobs, "search_result before search_run reported done"
         paths = [q for s, q in self.found if s == self.bound]
         arr = np.stack(paths) if paths else np.zeros((0, self.n), np.uint8)
         return self.bound, len(paths), arr

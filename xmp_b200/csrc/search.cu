@@ -1155,6 +1155,14 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		if (rc) break;
 		++batches;
 	}
+	if (rc == XMP_OK && !S->done) {
+		// A slice that stopped on max_batches may have emptied the frontier with its last sweep: report it
+		// now, so that "nothing pending" and "done" never disagree (the multi-GPU hosts terminate on the former
+		// and fetch results on the latter).
+		bool open = false;
+		for (unsigned m = 3; m < S->n; ++m) open |= S->pool[m].count != 0;
+		if (!open) S->done = true;
+	}
 	if (rc == XMP_OK && S->done && !S->finished) {
 		rc = drain_trees(ctx, S);
 		if (rc == XMP_OK) rc = fetch_counters(ctx, S);

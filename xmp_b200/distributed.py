@@ -80,6 +80,8 @@ def sharded_search(engine, num_taxa, device="cpu", slice_batches=8, steal_nodes=
             if len(jobs):
                 engine.search_import_jobs(np.ascontiguousarray(jobs))
                 done = False
+    if not done:
+        engine.search_run(0)      # nothing is pending anywhere; lets an engine that had not noticed yet wrap up
     score, n, paths = engine.search_result()
     tot = _t([n], device)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
