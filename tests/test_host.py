@@ -153,3 +153,13 @@ def test_base_tree_newick(alignment_dir, goldens):
     assert out[0] == "(%d,((%d,%d),%d))" % (t[0], t[3], t[1], t[2])     # above leaf 1: new leaf LEFT
     assert out[1] == "(%d,(%d,(%d,%d)))" % (t[0], t[1], t[3], t[2])     # above leaf 2
     assert out[2] == "(%d,(%d,(%d,%d)))" % (t[0], t[3], t[1], t[2])     # above the internal node
+
+
+def test_walk_program_derivation(tmp_path):
+    """xmp_b200/csrc/walk_prog.h (shared with the CUDA kernels): a child's walk program derived from its
+    parent's equals the program built from the child's topology, up to 100 taxa."""
+    import subprocess
+    exe = str(tmp_path / "walk_check")
+    subprocess.run(["g++", "-O2", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(os.path.dirname(os.path.abspath(__file__)), "walk_check.cpp")], check=True)
+    r = subprocess.run([exe, "100", "120"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr

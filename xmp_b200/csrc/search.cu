@@ -29,37 +29,58 @@
 #include <stdlib.h>
 #include <string.h>
 #include "ctx.h"
+#include "walk_prog.h"
 
 namespace xmp {
 
 struct Layout {
-	unsigned n;        // taxa in the problem
-	unsigned W;        // 128-bit blocks per state set
-	unsigned HB;       // header bytes (multiple of 16)
-	unsigned off_par, off_sib, off_pos, off_size;   // byte arrays over edge ids inside a header
-	unsigned off_prog;                               // u32 per pre-order position: edge | sibling << 8 | depth << 16
-	unsigned trec;     // bytes per emitted tree record: score + path
+	unsigned n;         // taxa in the problem
+	unsigned W;         // 128-bit blocks per state set
+	unsigned NW;        // header words per node: score | insertion path (packed bytes) | walk program
+	unsigned off_prog;  // index of the first program word
+	unsigned ts_shift;  // records are tiled: 1 << ts_shift consecutive slots interleave their rows
+	unsigned trec;      // bytes per emitted tree record: score + path
 };
-// Header: [0,4) score | [4,4+n) path (byte 0 of it = the root's child) | par[] sib[] pos[] size[] | prog[]
-// The "walk program" prog[] is the tree in pre-order with everything a top-down pass needs per step, so
-// that the kernels below run one uniform loop per child instead of chasing parent / child links.
-#define HDR_PATH 4u
+// Header words: [0] tree length so far | [1, 1 + ceil(n/4)) insertion path, one byte per taxon (byte 0 = the
+// root's child) | [off_prog, off_prog + 2n-3) walk program (walk_prog.h), one word per pre-order position.
+#define HDR_PATH_W 1u
 
+// Both arrays of a pool are tiled so that threads working on CONSECUTIVE slots touch consecutive addresses
+// when they access the same row -- and every row is indexed by pre-order position, which all lanes of a
+// warp reach at the same step of their walks:
+//   header word w of slot s:        hdr [((s / 32) * NW + w) * 32 + s % 32]                     (128-byte lines)
+//   block c of row k of slot s:     sets[(((s / TS) * nsets + k) * TS + s % TS) * W + c]        TS = 1 << ts_shift
+// with TS * W * 16 B = one 128-byte line for narrow sets (W = 1: 8 slots, W = 2: 4, W <= 4: 2) and TS = 1,
+// i.e. plain records, from W = 5 up.  Rows of a node: MIDPOINT at [0, E), UP at [E, 2E); DOWN sets are transient.
 struct PoolView {
-	uint8_t *hdr;
+	unsigned *hdr;
 	uint4 *sets;
-	unsigned long long rec;   // uint4 per node
-	unsigned long long cap;   // slots; pools are rings: slot = index modulo cap
+	unsigned nsets;           // rows per node = 2 * (2m-3)
+	unsigned long long cap;   // slots (a multiple of 32); pools are rings: slot = index modulo cap
 };
 
-__device__ __forceinline__ unsigned path_hash(const uint8_t *path, unsigned m, unsigned e) {
-	unsigned h = 2166136261u;
-	for (unsigned t = 3; t < m; ++t) h = (h ^ path[t]) * 16777619u;
-	h = (h ^ e) * 16777619u;
-	return h ^ (h >> 15);
+__device__ __forceinline__ unsigned *hdr_of(const PoolView &p, const Layout &L, unsigned long long slot) {
+	return p.hdr + (slot >> 5) * L.NW * 32ull + (slot & 31ull);               // word w at [w * 32]
+}
+__device__ __forceinline__ uint4 *sets_of(const PoolView &p, const Layout &L, unsigned long long slot) {
+	const unsigned ts = L.ts_shift;
+	return p.sets + ((((slot >> ts) * p.nsets) << ts) + (slot & ((1ull << ts) - 1ull))) * L.W;   // row k at [(k << ts) * W]
+}
+__device__ __forceinline__ unsigned path_byte(const unsigned *h, unsigned t) {
+	return (h[(HDR_PATH_W + (t >> 2)) * 32u] >> (8u * (t & 3u))) & 0xFFu;
+}
+
+__device__ __forceinline__ unsigned path_hash(const unsigned *h, unsigned m, unsigned e) {
+	unsigned x = 2166136261u;
+	for (unsigned t = 3; t < m; ++t) x = (x ^ path_byte(h, t)) * 16777619u;
+	x = (x ^ e) * 16777619u;
+	return x ^ (x >> 15);
 }
 
 // ---- scoring + pruning of a batch of partial trees --------------------------------------------------
+// Pairs are enumerated tile by tile, position by position, slot-minor: a warp reads whole 128-byte lines of
+// MIDPOINT rows, and the survivors of one tile (<= 8 parents) stay together in the survivor list, so that
+// the child kernels find their parents' data in L1.
 template <int G>
 __global__ void __launch_bounds__(256)
 k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes,
@@ -68,18 +89,22 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
                unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
 	__shared__ unsigned s_bound, s_warp[9];
 	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
-	const unsigned E = 2 * m - 3;
+	const unsigned E = 2 * m - 3, ts = L.ts_shift, tmask = (1u << ts) - 1u;
 	const unsigned long long gthread = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned long long pair = gthread / G;
 	const unsigned sub = (unsigned) (gthread % G);
-	const bool valid = pair < n_nodes * E;
-	unsigned long long node = first + pair / E;
+	const unsigned tile_pairs = E << ts;
+	const unsigned long long tile = pair / tile_pairs;
+	const unsigned r = (unsigned) (pair - tile * tile_pairs);
+	const unsigned pos = r >> ts;
+	const long long lin = (long long) ((tile << ts) + (r & tmask)) - (long long) (first & tmask);   // index inside the batch
+	const bool valid = lin >= 0 && (unsigned long long) lin < n_nodes;
+	unsigned long long node = first + (valid ? (unsigned long long) lin : 0ull);
 	if (node >= pool.cap) node -= pool.cap;              // the batch may wrap around the end of the ring
-	const unsigned e = (unsigned) (pair % E);
 	unsigned s = 0;
 	__syncthreads();
 	if (valid) {
-		const uint4 *src = pool.sets + node * pool.rec + (unsigned long long) e * L.W;
+		const uint4 *src = sets_of(pool, L, node) + ((size_t) pos << ts) * L.W;
 		for (unsigned b = sub; b < L.W; b += G) s += cost_block(src[b], __ldg(taxon_row + b), b, wp);
 	}
 #pragma unroll
@@ -87,12 +112,12 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 
 	bool keep = false;
 	unsigned new_score = 0;
-	const uint8_t *hdr = pool.hdr + node * L.HB;
+	const unsigned *hdr = hdr_of(pool, L, node);
 	if (valid && sub == 0) {
-		const unsigned score = *(const unsigned *) hdr;
+		const unsigned score = hdr[0];
 		keep = accept_insertion(s, s_bound, score, rest);
 		new_score = score + s;
-		if (keep && shard_count > 1) keep = (path_hash(hdr + HDR_PATH, m, e) % shard_count) == shard_index;
+		if (keep && shard_count > 1) keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos) * 32u])) % shard_count) == shard_index;
 	}
 	if (last) {
 		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
@@ -100,33 +125,34 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 		if (keep && slot < trees_cap) {
 			uint8_t *rec = trees + (size_t) slot * L.trec;
 			*(unsigned *) rec = new_score;
-			for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = hdr[HDR_PATH + t];
-			rec[4 + m] = (uint8_t) e;
+			for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = (uint8_t) path_byte(hdr, t);
+			rec[4 + m] = (uint8_t) prog_edge(hdr[(L.off_prog + pos) * 32u]);
 		}
 	} else {
 		unsigned slot = block_append(keep, n_surv, s_warp);
-		if (keep) surv[slot] = make_uint4((unsigned) node, e, new_score, 0u);
+		if (keep) surv[slot] = make_uint4((unsigned) node, pos, new_score, 0u);
 	}
 }
 
 // ---- walking a child tree ----------------------------------------------------------------------------
-// The child of parent node P obtained by inserting the next taxon on edge v, visited in pre-order without
-// ever materialising its topology: step j of the child is step j (before v), j - 2 (after v) of the
-// parent's walk program, with three spliced steps at v's position (new internal node b, new leaf a, v one
-// level deeper) -- branch-free selects, the same trip count for every lane of a level.
+// The child of parent node N obtained by inserting the next taxon on the edge at position P, visited in
+// pre-order without ever materialising its topology: step j of the child is step j (before P) or j - 2 (after)
+// of the parent's walk program with three spliced steps at P (walk_prog.h) -- selects, the same trip count
+// for every lane of a level, and every lane is at the same position j at the same time.
 //
 // Per-lane state with dynamic indexing lives in shared memory, element k of thread t at [k * blockDim.x + t]
 // (16-byte accesses are then bank-conflict free whatever k each lane uses; local memory would serialise
 // into one wavefront per distinct index):
-//   upath[k]   UP sets recomputed along the path from b (k = 0) up to the root's child; every other UP
-//              set is the parent tree's, read from its record (L1 hits: lanes of a warp share parents);
+//   upath[k]   UP sets recomputed along the root path: k = 0 the new internal node, k = dv - d the ancestor at
+//              depth d; every other UP set is the parent tree's, read from its record (L1 hits: the lanes of a
+//              warp share a handful of parents);
 //   dstack[d]  DOWN set of the current ancestor at depth d.
 struct ChildWalk {
-	const uint8_t *par, *sib;
-	const unsigned *prog;
-	const uint4 *PU;              // parent's UP sets for this lane's column
-	unsigned E, W, a, b, v, P, dv, sv, szv, last;
-	unsigned on0, on1, on2, on3, on4, on5, on6;   // edges on the root path (ids < 224)
+	const unsigned *prog;         // parent's program: word i at prog[i * 32]
+	const uint4 *PU;              // parent's UP rows for this lane's column: row i at PU[i * rs]
+	unsigned rs, E;
+	Splice sp;
+	unsigned on0, on1, on2, on3, on4, on5, on6;   // parent positions that are proper ancestors of P (positions < 224)
 	uint4 rt;
 
 	__device__ __forceinline__ bool on_path(unsigned e) const {
@@ -138,65 +164,60 @@ struct ChildWalk {
 		if (e < 32) on0 |= bit; else if (e < 64) on1 |= bit; else if (e < 96) on2 |= bit; else if (e < 128) on3 |= bit;
 		else if (e < 160) on4 |= bit; else if (e < 192) on5 |= bit; else on6 |= bit;
 	}
-	// Decodes the parent's header for the insertion on edge v and recomputes UP along the root path.
-	__device__ __forceinline__ unsigned init(const uint8_t *ph, const Layout &L, unsigned m, unsigned v_, const uint4 *parent_up,
+	// Decodes the insertion at position P of the parent and recomputes UP along the root path.
+	__device__ __forceinline__ unsigned init(const unsigned *ph, const Layout &L, unsigned m, unsigned P, const uint4 *parent_up,
 	                                         const uint4 &row_new, uint4 *upath, unsigned T) {
-		par = ph + L.off_par;
-		sib = ph + L.off_sib;
-		prog = (const unsigned *) (ph + L.off_prog);
+		prog = ph + L.off_prog * 32u;
 		PU = parent_up;
+		rs = L.W << L.ts_shift;
 		E = 2 * m - 3;
-		W = L.W;
-		a = E;
-		b = E + 1;
-		v = v_;
 		rt = row_new;
-		P = ph[L.off_pos + v];
-		szv = ph[L.off_size + v];
-		const unsigned pw = prog[P];
-		sv = (pw >> 8) & 0xFFu;
-		dv = pw >> 16;
+		sp = make_splice(P, prog[P * 32u], E);
 		on0 = on1 = on2 = on3 = on4 = on5 = on6 = 0;
-		uint4 u = fitch_block(rt, __ldg(PU + (size_t) v * W));
+		uint4 u = fitch_block(rt, __ldg(PU + (size_t) P * rs));
 		upath[0] = u;
-		mark(b);
-		unsigned k = 1;
-		unsigned p = par[v], other = sv;
-		while (p != 0xFFu) {
-			u = fitch_block(u, __ldg(PU + (size_t) other * W));     // `other` hangs off the path: unchanged
+		unsigned k = 1, cur = P, other = sp.sv;
+		for (unsigned depth = sp.dv; depth > 0; --depth) {
+			u = fitch_block(u, __ldg(PU + (size_t) other * rs));     // `other` hangs off the path: unchanged
 			upath[(size_t) k * T] = u;
-			mark(p);
+			cur = parent_pos(cur, other);
+			mark(cur);
+			other = prog_sib(prog[cur * 32u]);
 			++k;
-			other = sib[p];
-			p = par[p];
 		}
-		last = k - 1;       // depth of b
 		return k;           // merges done
 	}
-	// Step j of the child's pre-order: edge, sibling, depth.
-	__device__ __forceinline__ void step(unsigned j, unsigned &x, unsigned &s, unsigned &d) const {
-		const unsigned i = j <= P ? j : j - 2;
-		const unsigned w = prog[i < E ? i : E - 1];
-		x = w & 0xFFu;
-		s = (w >> 8) & 0xFFu;
-		d = w >> 16;
-		if (j > P + 2 && i < P + szv) d += 1;      // inside v's subtree: one level deeper
-		if (s == v) s = b;                         // v's sibling now hangs next to b
-		if (j == P) { x = b; s = sv; d = dv; }
-		if (j == P + 1) { x = a; s = v; d = dv + 1; }
-		if (j == P + 2) { x = v; s = a; d = dv + 1; }
-	}
-	__device__ __forceinline__ uint4 up_of(unsigned y, unsigned depth, const uint4 *upath, unsigned T) const {
-		if (on_path(y)) return upath[(size_t) (last - depth) * T];
-		if (y == a) return rt;
-		return __ldg(PU + (size_t) y * W);
+	// Step j of the child's pre-order: its program word, its UP set and its sibling's.
+	__device__ __forceinline__ void step(unsigned j, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) const {
+		const unsigned P = sp.P;
+		unsigned i = parent_index(j, P);
+		if (i >= E) i = E - 1;
+		const unsigned w = prog[i * 32u];
+		const bool anc = on_path(i);
+		word = child_word(j, w, anc, sp);
+		const unsigned d = prog_depth(w);
+		// where the two UP sets come from: 0 = the parent's record (row), 1 = upath[k], 2 = the new taxon's row, 3 = none
+		unsigned src_u = anc ? 1u : 0u, row_u = i, k_u = sp.dv - d;
+		unsigned s = prog_sib(w);
+		unsigned src_s = 0u, row_s = s, k_s = sp.dv - d;
+		if (s == XMP_NO_POS) src_s = 3u;
+		else if (s == P) { src_s = 1u; k_s = 0u; }              // the sibling was the insertion edge: now the new internal node
+		else if (on_path(s)) src_s = 1u;
+		if (j == P) {
+			src_u = 1u; k_u = 0u;
+			row_s = sp.sv; src_s = sp.sv == XMP_NO_POS ? 3u : 0u;
+		}
+		if (j == P + 1u) { src_u = 2u; src_s = 0u; row_s = P; }
+		if (j == P + 2u) { src_u = 0u; row_u = P; src_s = 2u; }
+		ux = src_u == 0u ? __ldg(PU + (size_t) row_u * rs) : (src_u == 1u ? upath[(size_t) k_u * T] : rt);
+		us = src_s == 0u ? __ldg(PU + (size_t) row_s * rs) : (src_s == 1u ? upath[(size_t) k_s * T] : (src_s == 2u ? rt : r0));
 	}
 };
 
 // ---- child construction ------------------------------------------------------------------------------
-// One thread per (survivor, 128-bit column): UP (copied, then the path entries), DOWN and MIDPOINT of the
-// child are written to its record; the column-0 thread also writes the child's header, walk program
-// included.
+// One thread per (survivor, 128-bit column): at step j the UP and MIDPOINT sets of the child's position j go
+// to row j of its record, the column-0 thread adds the program word -- consecutive threads build consecutive
+// slots, so with the tiled layout every such store fills whole 128-byte lines.
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
@@ -207,7 +228,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
 	// survivors s_begin .. min(*n_surv_ptr, s_end) - 1 become children child_first, child_first + 1, ...
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
-	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned long long total = n_surv > s_begin ? (unsigned long long) (n_surv - s_begin) * W : 0ull;
 	unsigned my_merges = 0;
 	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -217,54 +238,44 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		unsigned long long cslot = child_first + k;
 		if (cslot >= child.cap) cslot -= child.cap;
 		const uint4 sv = surv[s];
-		const unsigned pnode = sv.x, v = sv.y;
-		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
-		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
-		uint4 *CM = child.sets + cslot * child.rec + col;
-		uint4 *CU = CM + (unsigned long long) Ec * W;      // DOWN sets are not kept: no later step reads them
+		const unsigned pnode = sv.x, P = sv.y;
+		const unsigned *ph = hdr_of(parent, L, pnode);
+		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;
+		uint4 *CM = sets_of(child, L, cslot) + col;
+		uint4 *CU = CM + (size_t) Ec * rs;                  // DOWN sets are not kept: no later step reads them
+		unsigned *ch = hdr_of(child, L, cslot);
+		unsigned *cprog = ch + L.off_prog * 32u;
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, v, PU, __ldg(rows + (size_t) m * W + col), upath, T);
+		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T);
 		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
-		unsigned x, sb, d;
-		cw.step(0, x, sb, d);
-		uint4 ux = cw.up_of(x, d, upath, T), us = r0;
+		unsigned wj, first_edge = 0;
+		uint4 ux, us;
+		cw.step(0, wj, ux, us, upath, T, r0);
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned xn = x, sbn = sb, dnx = d;
+			unsigned wn = wj;
 			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) {
-				cw.step(j + 1, xn, sbn, dnx);
-				uxn = cw.up_of(xn, dnx, upath, T);
-				usn = cw.up_of(sbn, dnx, upath, T);     // depth >= 1 from the second step on
-			}
+			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
-			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
-			CU[(size_t) x * W] = ux;
-			CM[(size_t) x * W] = fitch_block(ux, dn);
-			x = xn; sb = sbn; d = dnx; ux = uxn; us = usn;
+			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
+			CU[(size_t) j * rs] = ux;
+			CM[(size_t) j * rs] = fitch_block(ux, dn);
+			if (col == 0) {
+				cprog[j * 32u] = wj;
+				if (j == 0) first_edge = prog_edge(wj);
+			}
+			wj = wn; ux = uxn; us = usn;
 		}
 		if (col == 0) {
-			// header: copy, then re-derive everything the insertion changed
-			uint8_t *ch = child.hdr + (size_t) cslot * L.HB;
-			for (unsigned i = 0; i < L.HB / 16; ++i) ((uint4 *) ch)[i] = ((const uint4 *) ph)[i];
-			*(unsigned *) ch = sv.z;
-			ch[HDR_PATH + m] = (uint8_t) v;
-			uint8_t *cpar = ch + L.off_par, *csib = ch + L.off_sib, *cpos = ch + L.off_pos, *csize = ch + L.off_size;
-			unsigned *cprog = (unsigned *) (ch + L.off_prog);
-			for (unsigned j = 0; j < Ec; ++j) {
-				unsigned x, sb, d;
-				cw.step(j, x, sb, d);
-				cprog[j] = x | (sb << 8) | (d << 16);
-				cpos[x] = (uint8_t) j;
-				csib[x] = (uint8_t) sb;
+			ch[0] = sv.z;
+			const unsigned pw = (L.n + 3u) >> 2;
+			for (unsigned q = 0; q < pw; ++q) {
+				unsigned w = ph[(HDR_PATH_W + q) * 32u];
+				if (q == (m >> 2)) w = (w & ~(0xFFu << (8u * (m & 3u)))) | (cw.sp.xv << (8u * (m & 3u)));
+				if (q == 0) w = (w & ~0xFFu) | first_edge;
+				ch[(HDR_PATH_W + q) * 32u] = w;
 			}
-			const unsigned pv = cw.par[v];
-			cpar[cw.a] = cpar[v] = (uint8_t) cw.b;
-			cpar[cw.b] = (uint8_t) pv;
-			csize[cw.a] = 1;
-			csize[cw.b] = (uint8_t) (cw.szv + 2);
-			for (unsigned q = pv; q != 0xFFu; q = cw.par[q]) csize[q] = (uint8_t) (ph[L.off_size + q] + 2);
-			ch[HDR_PATH] = (uint8_t) (cprog[0] & 0xFFu);
 			my_merges += n_up + 2 * Ec;
 		}
 	}
@@ -289,7 +300,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
 	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
-	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2;
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
 	const unsigned lane = threadIdx.x & 31u, sub = lane % G;
 	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - sub));
@@ -303,11 +314,11 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	for (unsigned long long s = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + threadIdx.x / G; s < n_surv;
 	     s += (unsigned long long) gridDim.x * groups_per_block) {
 		const uint4 sv = surv[s];
-		const unsigned pnode = sv.x, v = sv.y, score = sv.z;
-		const uint8_t *ph = parent.hdr + (size_t) pnode * L.HB;
-		const uint4 *PU = parent.sets + (unsigned long long) pnode * parent.rec + (unsigned long long) E * W + col;
+		const unsigned pnode = sv.x, P = sv.y, score = sv.z;
+		const unsigned *ph = hdr_of(parent, L, pnode);
+		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, v, PU, rt, upath, T);
+		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
 		unsigned bound = 0;
 		{
@@ -316,20 +327,17 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
 			bound = __shfl_sync(active, bound, leader);
 		}
-		unsigned x, sb, d;
-		cw.step(0, x, sb, d);
-		uint4 ux = cw.up_of(x, d, upath, T), us = r0;
+		unsigned wj;
+		uint4 ux, us;
+		cw.step(0, wj, ux, us, upath, T, r0);
 		for (unsigned j = 0; j < Ec; ++j) {
 			// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
-			unsigned xn = x, sbn = sb, dnx = d;
+			unsigned wn = wj;
 			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) {
-				cw.step(j + 1, xn, sbn, dnx);
-				uxn = cw.up_of(xn, dnx, upath, T);
-				usn = cw.up_of(sbn, dnx, upath, T);
-			}
+			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
-			if (!edge_is_leaf(x)) dstack[(size_t) d * T] = dn;
+			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
 			unsigned c = col_ok ? cost_block(fitch_block(ux, dn), rl, col, wp) : 0u;
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
@@ -339,12 +347,12 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 				if (slot < trees_cap) {
 					uint8_t *rec = trees + (size_t) slot * L.trec;
 					*(unsigned *) rec = score + c;
-					for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = ph[HDR_PATH + t];
-					rec[4 + m] = (uint8_t) v;
-					rec[4 + m + 1] = (uint8_t) x;
+					for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = (uint8_t) path_byte(ph, t);
+					rec[4 + m] = (uint8_t) cw.sp.xv;
+					rec[4 + m + 1] = (uint8_t) prog_edge(wj);
 				}
 			}
-			x = xn; sb = sbn; d = dnx; ux = uxn; us = usn;
+			wj = wn; ux = uxn; us = usn;
 		}
 		if (sub == 0) my_merges += n_up + 2 * Ec;
 	}
@@ -359,31 +367,51 @@ __global__ void k_write_headers(PoolView pool, Layout L, unsigned m, unsigned lo
 	const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n_jobs) return;
 	const unsigned E = 2 * m - 3;
-	uint8_t *h = pool.hdr + (size_t) (first + j) * L.HB;
-	for (unsigned i = 4; i < L.HB; ++i) h[i] = 0xFF;
-	*(unsigned *) h = tree_len[j];
+	unsigned *h = hdr_of(pool, L, first + j);
 	const uint8_t *t = topo + (size_t) j * 4 * topo_stride;
 	const uint8_t *par = t, *k0 = t + topo_stride, *k1 = t + 2 * topo_stride, *pre = t + 3 * topo_stride;
-	for (unsigned k = 0; k < L.n; ++k) h[HDR_PATH + k] = paths[(size_t) j * L.n + k];
-	h[HDR_PATH] = pre[0];   // first edge in pre-order = the root's child
-	uint8_t *hpar = h + L.off_par, *hsib = h + L.off_sib, *hpos = h + L.off_pos, *hsize = h + L.off_size;
-	unsigned *hprog = (unsigned *) (h + L.off_prog);
-	// depth is kept in the size array until the program is written, then sizes are accumulated bottom-up
-	for (unsigned i = 0; i < E; ++i) {
-		const unsigned e = pre[i], p = par[e];
-		const unsigned d = p == 0xFFu ? 0u : (unsigned) hsize[p] + 1u;      // parents precede children in pre-order
-		const unsigned sb = p == 0xFFu ? 0xFFu : (unsigned) (k0[p] == e ? k1[p] : k0[p]);
-		hpar[e] = (uint8_t) p;
-		hsib[e] = (uint8_t) sb;
-		hpos[e] = (uint8_t) i;
-		hsize[e] = (uint8_t) d;
-		hprog[i] = e | (sb << 8) | (d << 16);
+	unsigned prog[2 * XMP_MAX_TAXA];
+	unsigned char pos[2 * XMP_MAX_TAXA], size[2 * XMP_MAX_TAXA];
+	prog_from_topology(par, k0, k1, pre, E, prog, pos, size);
+	h[0] = tree_len[j];
+	const unsigned pw = (L.n + 3u) >> 2;
+	for (unsigned q = 0; q < pw; ++q) {
+		unsigned w = 0;
+		for (unsigned b = 0; b < 4; ++b) {
+			const unsigned k = 4 * q + b;
+			unsigned byte = k < L.n ? paths[(size_t) j * L.n + k] : 0u;
+			if (k == 0) byte = pre[0];                // first edge in pre-order = the root's child
+			w |= byte << (8u * b);
+		}
+		h[(HDR_PATH_W + q) * 32u] = w;
 	}
-	for (unsigned i = 0; i < E; ++i) hsize[pre[i]] = 1;
-	for (int i = (int) E - 1; i >= 0; --i) {
-		const unsigned e = pre[i], p = par[e];
-		if (p != 0xFFu) hsize[p] = (uint8_t) (hsize[p] + hsize[e]);
-	}
+	for (unsigned i = 0; i < E; ++i) h[(L.off_prog + i) * 32u] = prog[i];
+}
+
+// Sets built from topologies (k_build_sets: plain records indexed by edge id, MIDPOINT then UP) -> the pool's
+// tiled, position-indexed rows.  One thread per (job, position, column).
+__global__ void k_scatter_sets(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n_jobs,
+                               const uint8_t *__restrict__ topo, unsigned topo_stride, const uint4 *__restrict__ src) {
+	const unsigned E = 2 * m - 3, W = L.W;
+	const unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (unsigned long long) n_jobs * E * W) return;
+	const unsigned col = (unsigned) (idx % W);
+	const unsigned i = (unsigned) ((idx / W) % E);
+	const unsigned j = (unsigned) (idx / ((unsigned long long) W * E));
+	const unsigned e = topo[(size_t) j * 4 * topo_stride + 3 * topo_stride + i];
+	const uint4 *rec = src + (size_t) j * 2 * E * W;
+	uint4 *dst = sets_of(pool, L, first + j) + col;
+	const size_t rs = (size_t) W << L.ts_shift;
+	dst[(size_t) i * rs] = rec[(size_t) e * W + col];
+	dst[(size_t) (E + i) * rs] = rec[((size_t) E + e) * W + col];
+}
+
+// Insertion paths of nodes first .. first + n - 1 as plain byte records (job descriptors for export).
+__global__ void k_read_paths(PoolView pool, Layout L, unsigned long long first, unsigned n, uint8_t *__restrict__ out) {
+	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const unsigned *h = hdr_of(pool, L, first + i);
+	for (unsigned t = 0; t < L.n; ++t) out[(size_t) i * L.n + t] = (uint8_t) path_byte(h, t);
 }
 
 __global__ void k_filter_trees(const uint8_t *__restrict__ src, unsigned n_src, unsigned trec, const unsigned *bound_ptr,
@@ -403,12 +431,12 @@ __global__ void k_lower_bound(unsigned *bound_ptr, unsigned value) { atomicMin(b
 
 // ---- host side ----------------------------------------------------------------------------------------
 struct Pool {
-	uint8_t *hdr = nullptr;
+	unsigned *hdr = nullptr;
 	uint4 *sets = nullptr;
-	unsigned long long cap = 0, count = 0, rec = 0;
+	unsigned long long cap = 0, count = 0, rec = 0;   // rec = uint4 per node
 	unsigned long long head = 0;          // ring: open nodes occupy slots head .. head + count - 1 (modulo cap)
 	unsigned E = 0;
-	PoolView view() const { return PoolView{hdr, sets, rec, cap}; }
+	PoolView view() const { return PoolView{hdr, sets, 2 * E, cap}; }
 	unsigned long long slot(unsigned long long i) const { return (head + i) % cap; }
 };
 
@@ -442,7 +470,7 @@ struct Search {
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	unsigned min_batch = 32768, beam = 512;
 	xmp_search_stats st;
-	Scratch topo, pathbuf;
+	Scratch topo, pathbuf, stage;
 };
 
 // Scheduler knobs (defaults chosen on B200, see profiles/r01_search_tuning.md; overridable for tuning):
@@ -480,6 +508,7 @@ void search_destroy(xmp_ctx *ctx) {
 	if (S->h_pin) cudaFreeHost(S->h_pin);
 	S->topo.release();
 	S->pathbuf.release();
+	S->stage.release();
 	delete S;
 	ctx->search = nullptr;
 }
@@ -489,12 +518,9 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	Layout &L = S->L;
 	L.n = n;
 	L.W = W;
-	L.off_par = HDR_PATH + n;
-	L.off_sib = L.off_par + Emax;
-	L.off_pos = L.off_sib + Emax;
-	L.off_size = L.off_pos + Emax;
-	L.off_prog = (L.off_size + Emax + 3u) & ~3u;
-	L.HB = (L.off_prog + 4u * Emax + 15u) & ~15u;
+	L.off_prog = HDR_PATH_W + ((n + 3u) >> 2);
+	L.NW = L.off_prog + Emax;
+	L.ts_shift = W == 1 ? 3u : (W == 2 ? 2u : (W <= 4 ? 1u : 0u));     // one 128-byte line per row of a tile
 	L.trec = 4 + ((n + 3u) & ~3u);
 
 	size_t free_b = 0, total_b = 0;
@@ -519,7 +545,8 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		for (unsigned m = 3; m < n; ++m) {
 			double c = std::min(C, odd_factorial(m));
 			if (m + 1 == n) c = std::min(c, last_cap);
-			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + L.HB + 64);   // + four slots in a survivor list
+			c = 32.0 * std::ceil(c / 32.0);                                // whole tiles
+			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + 4.0 * L.NW + 64);   // + four slots in a survivor list
 		}
 		return tot + 5 * C * 16;   // survivors of the single-batch path and of the fused level
 	};
@@ -536,8 +563,9 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 		P.rec = 2ull * P.E * W;       // [MIDPOINT | UP][edge][block]
 		P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
 		if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
+		P.cap = (P.cap + 31ull) & ~31ull;                                 // whole tiles (headers: 32 slots, sets: <= 8)
 		P.count = 0;
-		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.HB));
+		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.NW * 4));
 		XMP_CUDA(cudaMalloc(&P.sets, (size_t) P.cap * P.rec * 16));
 	}
 	S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) S->beam * Emax);
@@ -583,8 +611,9 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 		unsigned k = (unsigned) (sel.size() / L.n);
 		size_t done = 0;
 		while (done < k) {
-			unsigned part = (unsigned) std::min<size_t>(k - done, 65536);
 			Pool &P = S->pool[m];
+			// at most 65536 nodes and 256 MiB of staging per round
+			unsigned part = (unsigned) std::min<size_t>(k - done, std::max<size_t>(1, std::min<size_t>(65536, ((size_t) 256 << 20) / ((size_t) P.rec * 16))));
 			if (P.count + part > P.cap) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m, P.cap);
 			const unsigned long long tail = P.slot(P.count);
 			part = (unsigned) std::min<unsigned long long>(part, P.cap - tail);      // up to the end of the ring, the rest next time
@@ -606,13 +635,21 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			if (rc) return rc;
 			XMP_CUDA(cudaMemcpyAsync(S->topo.ptr, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
 			XMP_CUDA(cudaMemcpyAsync(S->pathbuf.ptr, sel.data() + done * L.n, (size_t) part * L.n, cudaMemcpyHostToDevice, ctx->stream));
-			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, P.sets + tail * P.rec, (size_t) P.rec, true, S->d_len);
+			rc = S->stage.reserve((size_t) part * P.rec * 16);
 			if (rc) return rc;
+			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, (uint4 *) S->stage.ptr, (size_t) P.rec, true, S->d_len);
+			if (rc) return rc;
+			{
+				const unsigned long long threads = (unsigned long long) part * E * L.W;
+				k_scatter_sets<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr,
+				                                                                          stride, (const uint4 *) S->stage.ptr);
+				XMP_CUDA(cudaGetLastError());
+			}
 			k_write_headers<<<(part + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
 			                                                            (const uint8_t *) S->pathbuf.ptr, S->d_len);
 			XMP_CUDA(cudaGetLastError());
 			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-			S->st.launches += 2;
+			S->st.launches += 3;
 			P.count += part;
 			done += part;
 		}
@@ -628,7 +665,9 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	const uint4 *row = ctx->d_rows + (size_t) m * L.W;
 	const unsigned rest = ctx->rest_bound[m];
 	const unsigned sc = shard ? S->prm.shard_count : 1u, si = shard ? S->prm.shard_index : 0u;
-	const unsigned long long pairs = chunk * P.E;
+	// whole tiles of the pool's record layout are enumerated; slots outside the batch are masked in the kernel
+	const unsigned long long tiles = ((first & ((1ull << L.ts_shift) - 1ull)) + chunk + (1ull << L.ts_shift) - 1ull) >> L.ts_shift;
+	const unsigned long long pairs = (tiles << L.ts_shift) * P.E;
 	uint8_t *trees = S->d_trees[S->cur];   // slots are absolute: d_ntrees already counts the records present
 	const unsigned room = S->trees_cap;
 #define XMP_EXPAND(G)                                                                                                   \
@@ -1215,12 +1254,14 @@ extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uin
 		const unsigned long long tail = P.slot(P.count);         // one past the newest node
 		if (tail != 0) k = (unsigned) std::min<unsigned long long>(k, tail);   // stay on this side of the wrap
 		const unsigned long long from = (tail == 0 ? P.cap : tail) - k;
-		std::vector<uint8_t> h((size_t) k * L.HB);
-		XMP_CUDA(cudaMemcpyAsync(h.data(), P.hdr + (size_t) from * L.HB, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+		int rc = S->pathbuf.reserve((size_t) k * L.n);
+		if (rc) return rc;
+		k_read_paths<<<(k + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, from, k, (uint8_t *) S->pathbuf.ptr);
+		XMP_CUDA(cudaGetLastError());
+		XMP_CUDA(cudaMemcpyAsync(jobs, S->pathbuf.ptr, (size_t) k * L.n, cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 		for (unsigned i = 0; i < k; ++i) {
 			uint8_t *job = jobs + (size_t) i * L.n;
-			memcpy(job, h.data() + (size_t) i * L.HB + HDR_PATH, L.n);
 			job[0] = (uint8_t) m;
 			job[1] = job[2] = 0;
 		}
