@@ -8,14 +8,14 @@ CFLAGS    := -O2 -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
 
 CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu xmp_b200/csrc/microbench.cu
 CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh include/xmp_cuda.h
-HOST_SRCS := host/phylip.c host/prep.c host/trees.c
+HOST_SRCS := host/phylip.c host/prep.c host/trees.c host/partbound.c
 
 .PHONY: all host cuda cli oracle ref clean
 all: host cuda cli oracle
 
 host: host/libxmp_host.so
 host/libxmp_host.so: $(HOST_SRCS) host/xmp_host.h
-	$(CC) $(CFLAGS) -shared -o $@ $(HOST_SRCS)
+	$(CC) $(CFLAGS) -shared -o $@ $(HOST_SRCS) -lpthread
 
 cuda: xmp_b200/libxmp_b200.so
 xmp_b200/libxmp_b200.so: $(CUDA_SRCS) $(CUDA_HDRS)

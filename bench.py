@@ -263,13 +263,9 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
         a = xh.Alignment(f.name)
         os.unlink(f.name)
         if "-Bp" in g["flags"]:
-            # the author's its36 setting (-Bp -b 233 -m 100000): the partition bound is CPU precomputation in the
-            # reference; its restBound[] comes from the golden run through the -Bf mechanism
-            with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as rb:
-                rb.write("i\tbound\n" + "".join("%d\t%d\n" % (i, b) for i, b in g["rest_bound"]))
-            p = xh.Problem(a, options=xh.OPT_USELOADRESTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=int(g["flags"][g["flags"].index("-b") + 1]),
-                           rest_bound_file=rb.name)
-            os.unlink(rb.name)
+            # the author's its36 setting (-Bp -b 233 -m 100000); the partition bound is host precomputation
+            # (host/partbound.c), outside the timed search like the reference's "Time to determine lower bounds"
+            p = xh.Problem(a, options=xh.OPT_USEPARTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=int(g["flags"][g["flags"].index("-b") + 1]))
         else:
             p = xh.Problem(a)          # default options: -Bd bound, MST upper bound, like the reference run
         ctx = xc.Context(local)

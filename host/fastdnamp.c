@@ -84,7 +84,7 @@ static int unsigned_option(const char *arg, const char *name, unsigned *out) {
 }
 
 static int parse_args(int argc, char **argv, cli *c) {
-	unsigned ignored = 0, mb = 0;
+	unsigned mb = 0;
 	if (argc < 2) { usage(); return 0; }
 	for (int i = 1; i < argc; ++i) {
 		const char *a = argv[i];
@@ -140,6 +140,7 @@ static int parse_args(int argc, char **argv, cli *c) {
 						fprintf(stderr, "To specify the '%c' option, you must have previously specified -Bp.\n", *p);
 						exit(1);
 					}
+					c->s.part_strategy = *p == 'C' ? 1 : 2;
 					break;
 				case 'f':
 					if (i + 1 >= argc) die("Option -Bf needs a file name, aborting.");
@@ -165,7 +166,7 @@ static int parse_args(int argc, char **argv, cli *c) {
 			if (unsigned_option(x, "seed", &c->seed)) break;
 			if (bool_option(x, "onlycomputelowerbound", &c->s.options, XMPH_OPT_ONLYCOMPUTELOWERBOUND)) break;
 			if (bool_option(x, "keeptempfiles", &c->s.options, XMPH_OPT_KEEPTEMPFILES)) break;
-			if (unsigned_option(x, "pbmaxiters", &ignored)) break;
+			if (unsigned_option(x, "pbmaxiters", &c->s.part_max_stale)) break;
 			if (bool_option(x, "savereordereddataset", &c->s.options, XMPH_OPT_SAVEREORDEREDDATASET)) break;
 			if (bool_option(x, "tbr", &c->s.options, XMPH_OPT_TBR)) break;
 			if (unsigned_option(x, "gpus", &c->n_gpus)) break;
@@ -211,6 +212,11 @@ static void report_settings(const cli *c) {
 	if (o & XMPH_OPT_USELOADRESTBOUND) fprintf(stderr, "The restBound[] array will be loaded from the file '%s'.\n", c->s.rest_bound_file);
 	if (o & XMPH_OPT_USEDISTBASESBOUNDREST) fprintf(stderr, "The distinct-bases-per-site bound will be used.\n");
 	if (o & XMPH_OPT_USEMSTBOUNDREST) fprintf(stderr, "The minimum spanning tree bound will be used.\n");
+	if (o & XMPH_OPT_USEPARTBOUND) {
+		fprintf(stderr, "The PARTBOUND bound will be used.  %s will be maximised.\n",
+		        c->s.part_strategy == 0 ? "Final scores" : c->s.part_strategy == 1 ? "Clipped scores" : "Lower bounds");
+		if (c->s.part_max_stale) fprintf(stderr, "PARTBOUND iterations will stop after %u iterations with no improvement.\n", c->s.part_max_stale);
+	}
 	if (o & XMPH_OPT_ONLYCOMPUTELOWERBOUND) fprintf(stderr, "The program will exit after computing lower bounds.\n");
 	if (o & XMPH_OPT_SAVEREORDEREDDATASET) fprintf(stderr, "The dataset produced by reordering taxa and stripping constant and non-PI sites will be saved.\n");
 	if (o & XMPH_OPT_KEEPTEMPFILES) fprintf(stderr, "Temporary intermediate files will be kept.\n");

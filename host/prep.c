@@ -28,6 +28,9 @@ void xmph_default_settings(xmph_settings *s) {
 	s->start_col = 0;
 	s->end_col = XMPH_NO_LIMIT;
 	s->rest_bound_file = NULL;
+	s->part_strategy = 0;     /* PBS_CLIPPEDANDADDITIVE, src/common.c:64 */
+	s->part_max_stale = 2;    /* src/common.c:65 */
+	s->threads = 0;
 }
 
 /* IUPAC code -> set over {A=1, C=2, G=4, T=8}; gap and '?' are fully ambiguous (src/common.c:891-916). */
@@ -420,12 +423,12 @@ void xmph_free_problem(xmph_problem *p) {
 int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *p) {
 	columns c = { 0, 0, NULL, NULL };
 	const unsigned unsupported = XMPH_OPT_USEINCOMPATBOUNDREST | XMPH_OPT_USEKICKASSBOUNDREST | XMPH_OPT_USEKA2BOUNDREST |
-	                             XMPH_OPT_USEGREEDYHITTINGSETBOUND | XMPH_OPT_USEPARTBOUND;
+	                             XMPH_OPT_USEGREEDYHITTINGSETBOUND;
 	memset(p, 0, sizeof *p);
 	if (a->num_taxa < 4) return xmph_fail("You must have four or more taxa to perform this analysis.");
 	if (a->num_taxa > XMPH_MAXTAXA) return xmph_fail("At most %d taxa are supported.", XMPH_MAXTAXA);
 	if (s->options & unsupported) {
-		return xmph_fail("Only the -Bd, -Bm and -Bf lower bounds are built into this program; compute other bounds with the reference and load its restBound.txt with -Bf <file>.");
+		return xmph_fail("Only the -Bd, -Bm, -Bp and -Bf lower bounds are built into this program; compute other bounds with the reference and load its restBound.txt with -Bf <file>.");
 	}
 	if (recode(a, s, &c)) { free(c.col); return -1; }
 	sort_columns(&c, by_bytes);
@@ -456,6 +459,10 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 		return -1;
 	}
 	if (s->options & XMPH_OPT_USEMSTBOUNDREST) mst_bound(p);
+	if ((s->options & XMPH_OPT_USEPARTBOUND) && xmph_part_bound(p, (int) s->part_strategy, s->part_max_stale, s->threads)) {
+		xmph_free_problem(p);
+		return -1;
+	}
 	pack_rows(p);
 	return 0;
 }

@@ -3,7 +3,7 @@
  * This mirrors, behaviour for behaviour, the parts of the reference that surround the hot path
  * (reference file:line given at each function): the PHYLIP reader, column recoding / pattern
  * compression / removal of uninformative sites, the max-mini taxon order, the MST upper bound, the
- * distinct-bases and MST lower bounds, packing into 4-bit state sets, and the Newick / NEXUS writer.
+ * distinct-bases, MST and partition lower bounds, packing into 4-bit state sets, and the Newick / NEXUS writer.
  * Nothing here computes Fitch sets for the search: that is libxmp_b200.so (include/xmp_cuda.h).
  *
  * All functions return 0 on success and a negative value on failure, with a message retrievable
@@ -55,6 +55,9 @@ typedef struct {
 	unsigned max_trees;     /* XMPH_NO_LIMIT = keep all */
 	unsigned start_col, end_col;
 	const char *rest_bound_file;
+	unsigned part_strategy;   /* -Bp: 0 final scores (default), 1 clipped only (-BpC), 2 lower bounds only (-BpL); src/partbound.h:5-9 */
+	unsigned part_max_stale;  /* -Bp: stop after this many passes without improvement (--pbmaxiters, default 2; 0 = never) */
+	unsigned threads;         /* host threads for bound precomputation, 0 = all cores */
 } xmph_settings;
 
 typedef struct {
@@ -81,6 +84,11 @@ void xmph_free_alignment(xmph_alignment *a);
 int  xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *p); /* src/common.c:1113-1224 */
 void xmph_free_problem(xmph_problem *p);
 int  xmph_write_rest_bound(const xmph_problem *p, const char *path);           /* src/bound.c:47-56 */
+/* Partition lower bound, raising p->rest_bound[3 .. num_taxa-2] (src/partbound.c:1144-1164); called by xmph_prepare for -Bp. */
+int  xmph_part_bound(xmph_problem *p, int strategy, unsigned max_stale_passes, unsigned n_threads);
+/* Exact length of a pair of unambiguous sites holding the (state, state) pairs in the bit set `index`
+ * (bit 4a+b); the entry the reference keeps in its generated table src/sitepaircosts.c. */
+int  xmph_site_pair_cost(unsigned index);
 
 /* ---- trees ------------------------------------------------------------------------------- */
 /* A tree is its insertion path: path[t] (3 <= t < num_taxa) = edge id taxon t was inserted on, in the

@@ -69,6 +69,8 @@ DATASETS = {
     "53humans.16": ("data/from_minmaxsqueeze/53humans.16.phy", []),
 }
 PARSER_FIXTURES = "data/phylip_format_testing"
+# inputs of other golden files (partbound.json): bundled here, not run by this script
+EXTRA_ALIGNMENTS = ["measure/53humans.32.phy"] + ["measure/e%d.phy" % i for i in (1, 3, 4, 5, 6)]
 SMALL_SET = 2000  # full canonical tree list is committed when the set has at most this many trees
 
 
@@ -142,7 +144,7 @@ def run_one(name):
 
 def bundle_alignments():
     bundle = {}
-    for name, (rel, _) in DATASETS.items():
+    for rel in [rel for rel, _ in DATASETS.values()] + EXTRA_ALIGNMENTS:
         p = os.path.join(REF, rel)
         if os.path.exists(p):
             bundle[os.path.basename(rel)] = open(p, "rb").read().decode("latin-1")

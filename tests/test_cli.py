@@ -56,6 +56,22 @@ def test_lower_bound_only_run_matches_reference(alignment_dir, goldens, tmp_path
     assert order == g["taxon_order"]
 
 
+@pytest.mark.parametrize("name", ["its36", "h1.C", "Metazoan.it1", "its36.L"])
+def test_partition_bound_run_matches_reference(alignment_dir, tmp_path, name):
+    """-Bp and its variants from the command line: the settings lines and restBound.txt of the reference."""
+    import json
+    case = json.load(open(os.path.join(ROOT, "tests", "golden", "partbound.json")))["cases"][name]
+    r = run(["--tbr=N", "--seed=1", "--updatesecs=0", "--onlycomputelowerbound=Y"] + case["flags"] + [str(alignment_dir / case["alignment"])], tmp_path)
+    assert r.returncode == 0, r.stderr
+    kind = "Clipped scores" if name.endswith(".C") else "Lower bounds" if name.endswith(".L") else "Final scores"
+    assert "The PARTBOUND bound will be used.  %s will be maximised." % kind in r.stderr
+    stale = 1 if name.endswith(".it1") else 2
+    assert "PARTBOUND iterations will stop after %d iterations with no improvement." % stale in r.stderr
+    assert "The distinct-bases-per-site bound will be used." not in r.stderr
+    rb = [[int(x) for x in l.split()] for l in (tmp_path / "restBound.txt").read_text().splitlines()[1:]]
+    assert rb == case["rest_bound"]
+
+
 def test_reader_errors_reach_the_user(alignment_dir, tmp_path):
     r = run([str(alignment_dir / "phylip_format_testing" / "bad1_T3_missing_1_base.phy")], tmp_path)
     assert r.returncode == 1 and "contains 1 fewer sites than the first line in this group, aborting." in r.stderr
@@ -63,8 +79,10 @@ def test_reader_errors_reach_the_user(alignment_dir, tmp_path):
     f.write_text("3 4\nA         ACGT\nB         ACGT\nC         ACGT\n")
     r = run([str(f)], tmp_path)
     assert r.returncode == 1 and "You must have four or more taxa to perform this analysis." in r.stderr
-    r = run(["-Bp", str(alignment_dir / "h3.phy")], tmp_path)
+    r = run(["-Bi", str(alignment_dir / "h3.phy")], tmp_path)
     assert r.returncode == 1 and "-Bf" in r.stderr
+    r = run(["-BC", str(alignment_dir / "h3.phy")], tmp_path)
+    assert r.returncode == 1 and "you must have previously specified -Bp" in r.stderr
 
 
 def test_search_without_a_device_fails_loudly(alignment_dir, tmp_path):

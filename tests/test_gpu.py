@@ -274,6 +274,17 @@ def test_search_its36_with_loaded_partition_bound(xc, alignment_dir, goldens, tm
     check_against_golden("its36", g, p, score, n, trees)
 
 
+def test_search_its36_with_native_partition_bound(xc, alignment_dir, goldens):
+    """The same setting with restBound[] computed here (host/partbound.c), no file from the reference involved."""
+    from xmp_b200 import hostlib as xh
+    g = goldens["its36"]
+    a = xh.Alignment(str(alignment_dir / g["alignment"]))
+    p = xh.Problem(a, options=xh.OPT_USEPARTBOUND | xh.OPT_IMPROVEINITUPPERBOUND, bound=233, max_trees=100000)
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
+    score, n, trees, stats = run_search(xc, p)
+    check_against_golden("its36", g, p, score, n, trees)
+
+
 def test_search_mh3_large_tree_set(xc, alignment_dir, goldens):
     g = goldens["mh3"]
     a, p = prepare(alignment_dir, goldens, "mh3")

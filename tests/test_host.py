@@ -163,3 +163,55 @@ def test_walk_program_derivation(tmp_path):
     subprocess.run(["g++", "-O2", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(os.path.dirname(os.path.abspath(__file__)), "walk_check.cpp")], check=True)
     r = subprocess.run([exe, "100", "120"], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+
+
+# ---- partition lower bound (-Bp, reference src/partbound.c) --------------------------------------
+def _partbound_goldens():
+    import json
+    from tests.conftest import GOLDEN
+    return json.load(open(os.path.join(GOLDEN, "partbound.json")))
+
+
+PB = _partbound_goldens()
+
+
+def _partbound_problem(alignment_dir, case, threads=0):
+    a = xh.Alignment(str(alignment_dir / case["alignment"]))
+    opts = xh.OPT_NEXUSFMT
+    strategy, stale = 0, 2
+    for f in case["flags"]:
+        if f.startswith("-B"):
+            opts |= (xh.OPT_USEDISTBASESBOUNDREST if "d" in f else 0) | (xh.OPT_USEMSTBOUNDREST if "m" in f else 0)
+            opts |= xh.OPT_USEPARTBOUND if "p" in f else 0
+            strategy = 1 if "C" in f else 2 if "L" in f else 0
+        elif f.startswith("--pbmaxiters="):
+            stale = int(f.split("=")[1])
+        elif f == "-d":
+            opts |= xh.OPT_DISCARDMISSAMBIG
+    return xh.Problem(a, options=opts, part_strategy=strategy, part_max_stale=stale, threads=threads)
+
+
+@pytest.mark.parametrize("name", sorted(PB["cases"]))
+def test_partition_bound_matches_reference(alignment_dir, name):
+    """restBound.txt of `fastdnamp -Bp...` (all strategies, --pbmaxiters, mixed with -Bd / -Bm) is reproduced exactly."""
+    case = PB["cases"][name]
+    p = _partbound_problem(alignment_dir, case)
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == case["rest_bound"]
+
+
+def test_partition_bound_is_independent_of_thread_count(alignment_dir):
+    case = PB["cases"]["Metazoan"]
+    for threads in (1, 3):
+        p = _partbound_problem(alignment_dir, case, threads=threads)
+        assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == case["rest_bound"]
+
+
+def test_site_pair_costs_equal_the_reference_table():
+    """The reference ships a generated 65,535-entry table of two-site lengths (src/sitepaircosts.c); here the
+    same numbers come out of the general part bound on first use.  All entries, by hash and by sample."""
+    L = xh.lib()
+    table = bytes(L.xmph_site_pair_cost(i) for i in range(1, 65536))
+    assert hashlib.sha256(table).hexdigest() == PB["site_pair_table_sha256"]
+    for i, v in PB["site_pair_table_samples"].items():
+        assert table[int(i) - 1] == v
+    assert L.xmph_site_pair_cost(0) == -1 and L.xmph_site_pair_cost(65536) == -1

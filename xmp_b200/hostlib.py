@@ -21,6 +21,7 @@ OPT_USELOADRESTBOUND = 32
 OPT_USEDISTBASESBOUNDREST = 64
 OPT_USEMSTBOUNDREST = 256
 OPT_IMPROVEINITUPPERBOUND = 4096
+OPT_USEPARTBOUND = 8192
 OPT_TBR = 131072
 NO_LIMIT = 0x7FFFFFFF
 
@@ -32,7 +33,8 @@ class _Alignment(C.Structure):
 
 class _Settings(C.Structure):
     _fields_ = [("options", C.c_uint), ("bound", C.c_uint), ("max_trees", C.c_uint),
-                ("start_col", C.c_uint), ("end_col", C.c_uint), ("rest_bound_file", C.c_char_p)]
+                ("start_col", C.c_uint), ("end_col", C.c_uint), ("rest_bound_file", C.c_char_p),
+                ("part_strategy", C.c_uint), ("part_max_stale", C.c_uint), ("threads", C.c_uint)]
 
 
 class _Problem(C.Structure):
@@ -52,6 +54,7 @@ def lib():
             raise RuntimeError("host/libxmp_host.so is missing: run `make host` (or __graft_entry__.build())")
         L = C.CDLL(path)
         L.xmph_last_error.restype = C.c_char_p
+        L.xmph_site_pair_cost.argtypes = [C.c_uint]
         L.xmph_path_to_newick.restype = C.c_size_t
         L.xmph_path_to_newick.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_char_p]
         L.xmph_path_to_dfs.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
@@ -99,13 +102,14 @@ class Problem:
     """The packed search problem (reference: struct TreeData hot fields, src/common.h:152-237)."""
 
     def __init__(self, alignment, options=None, bound=NO_LIMIT, max_trees=NO_LIMIT, start_col=0,
-                 end_col=NO_LIMIT, rest_bound_file=None):
+                 end_col=NO_LIMIT, rest_bound_file=None, part_strategy=0, part_max_stale=2, threads=0):
         L = lib()
         s = _Settings()
         L.xmph_default_settings(C.byref(s))
         if options is not None:
             s.options = options
         s.bound, s.max_trees, s.start_col, s.end_col = bound, max_trees, start_col, end_col
+        s.part_strategy, s.part_max_stale, s.threads = part_strategy, part_max_stale, threads
         self._rbf = os.fsencode(rest_bound_file) if rest_bound_file else None
         s.rest_bound_file = self._rbf
         self.alignment = alignment
