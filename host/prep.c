@@ -14,8 +14,10 @@
  *   pack                  src/common.c:1034-1109, here with BYTESPERBLOCK 16
  */
 #include <ctype.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "xmp_host.h"
 
 int xmph_fail(const char *fmt, ...);
@@ -194,33 +196,77 @@ static void drop_uninformative(columns *c, xmph_problem *p) {
 }
 
 /* ---- unpacked (one set per byte) distances -------------------------------------------------- */
+/* Both distances are written branch-free so that the compiler vectorises them: at 64 taxa x 2^20 sites
+ * (BASELINE config 2 pushed through the CLI) the O(n^2) distances are the whole preprocessing time. */
 static unsigned fitch_distance(const unsigned char *a, const unsigned char *b, const unsigned *w, unsigned n) {
 	unsigned d = 0;
-	for (unsigned i = 0; i < n; ++i) {
-		if (!(a[i] & b[i])) d += w[i];
-	}
+	for (unsigned i = 0; i < n; ++i) d += w[i] & (0u - (unsigned) ((a[i] & b[i]) == 0));
 	return d;
 }
 
 static unsigned strict_distance(const unsigned char *a, const unsigned char *b, const unsigned *w, unsigned n) {
 	unsigned d = 0;
-	for (unsigned i = 0; i < n; ++i) {
-		if (a[i] != b[i]) d += w[i];
-	}
+	for (unsigned i = 0; i < n; ++i) d += w[i] & (0u - (unsigned) (a[i] != b[i]));
 	return d;
 }
 
-/* Weight of a minimum spanning tree of the complete graph on `height` rows (Prim). */
-static unsigned mst_weight(const unsigned char *rows, unsigned n_sites, unsigned height, const unsigned *w, int strict) {
-	unsigned *best = (unsigned *) malloc(height * sizeof(unsigned));
-	unsigned char *in = (unsigned char *) calloc(height, 1);
+/* A tiny parallel-for over independent items (pair distances); threads == 0 means all cores. */
+typedef struct { void (*fn)(void *, unsigned); void *arg; unsigned n, next; } par_for;
+
+static void *par_for_thread(void *x) {
+	par_for *pf = (par_for *) x;
+	for (;;) {
+		unsigned i = __atomic_fetch_add(&pf->next, 1u, __ATOMIC_RELAXED);
+		if (i >= pf->n) return NULL;
+		pf->fn(pf->arg, i);
+	}
+}
+
+static void parallel_for(unsigned n, void (*fn)(void *, unsigned), void *arg, unsigned threads, size_t work_per_item) {
+	par_for pf = { fn, arg, n, 0 };
+	pthread_t th[64];
+	unsigned started = 0;
+	if (!threads) {
+		long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		threads = cores > 0 ? (unsigned) cores : 1;
+	}
+	if (threads > 64) threads = 64;
+	if (threads > n) threads = n;
+	if ((double) work_per_item * n < 4e6) threads = 1;           /* not worth a thread start */
+	for (; started + 1 < threads; ++started) if (pthread_create(&th[started], NULL, par_for_thread, &pf)) break;
+	par_for_thread(&pf);
+	for (unsigned i = 0; i < started; ++i) pthread_join(th[i], NULL);
+}
+
+/* All pairwise distances between `height` rows: D[i * height + j], symmetric, zero diagonal. */
+typedef struct { const unsigned char *rows; const unsigned *w; unsigned *D; unsigned ns, height; int strict; } pair_job;
+
+static void pair_item(void *x, unsigned item) {
+	const pair_job *j = (const pair_job *) x;
+	/* item -> (a, b), a < b, row-major over the strict upper triangle */
+	unsigned a = 0, left = item;
+	while (left >= j->height - 1 - a) { left -= j->height - 1 - a; ++a; }
+	const unsigned b = a + 1 + left;
+	const unsigned char *ra = j->rows + (size_t) a * j->ns, *rb = j->rows + (size_t) b * j->ns;
+	unsigned d = j->strict ? strict_distance(ra, rb, j->w, j->ns) : fitch_distance(ra, rb, j->w, j->ns);
+	j->D[(size_t) a * j->height + b] = j->D[(size_t) b * j->height + a] = d;
+}
+
+static unsigned *pair_matrix(const unsigned char *rows, unsigned ns, unsigned height, const unsigned *w, int strict, unsigned threads) {
+	unsigned *D = (unsigned *) calloc((size_t) height * height + 1, sizeof(unsigned));
+	pair_job j = { rows, w, D, ns, height, strict };
+	if (D && height > 1) parallel_for(height * (height - 1) / 2, pair_item, &j, threads, ns);
+	return D;
+}
+
+/* Weight of a minimum spanning tree of the complete graph with distance matrix D over `height` vertices (Prim). */
+static unsigned mst_of_matrix(const unsigned *D, unsigned height) {
+	unsigned *best = (unsigned *) malloc((height + 1) * sizeof(unsigned));
+	unsigned char *in = (unsigned char *) calloc(height + 1, 1);
 	unsigned total = 0;
 	if (height < 2) { free(best); free(in); return 0; }
 	in[0] = 1;
-	for (unsigned j = 1; j < height; ++j) {
-		best[j] = strict ? strict_distance(rows, rows + (size_t) j * n_sites, w, n_sites)
-		                 : fitch_distance(rows, rows + (size_t) j * n_sites, w, n_sites);
-	}
+	for (unsigned j = 1; j < height; ++j) best[j] = D[j];
 	for (unsigned k = 1; k < height; ++k) {
 		unsigned pick = 0, d = 0xffffffffu;
 		for (unsigned j = 1; j < height; ++j) {
@@ -229,14 +275,18 @@ static unsigned mst_weight(const unsigned char *rows, unsigned n_sites, unsigned
 		in[pick] = 1;
 		total += d;
 		for (unsigned j = 1; j < height; ++j) {
-			if (in[j]) continue;
-			unsigned e = strict ? strict_distance(rows + (size_t) pick * n_sites, rows + (size_t) j * n_sites, w, n_sites)
-			                    : fitch_distance(rows + (size_t) pick * n_sites, rows + (size_t) j * n_sites, w, n_sites);
-			if (e < best[j]) best[j] = e;
+			if (!in[j] && D[(size_t) pick * height + j] < best[j]) best[j] = D[(size_t) pick * height + j];
 		}
 	}
 	free(best);
 	free(in);
+	return total;
+}
+
+static unsigned mst_weight(const unsigned char *rows, unsigned n_sites, unsigned height, const unsigned *w, int strict, unsigned threads) {
+	unsigned *D = pair_matrix(rows, n_sites, height, w, strict, threads);
+	unsigned total = D ? mst_of_matrix(D, height) : 0;
+	free(D);
 	return total;
 }
 
@@ -246,48 +296,34 @@ static int cmp_unsigned(const void *a, const void *b) {
 	return x < y ? -1 : x > y;
 }
 
-static void swap_rows(xmph_problem *p, unsigned a, unsigned b, unsigned char *tmp) {
-	size_t n = p->num_sites;
-	memcpy(tmp, p->sites + a * n, n);
-	memcpy(p->sites + a * n, p->sites + b * n, n);
-	memcpy(p->sites + b * n, tmp, n);
-}
-
 /* Max-mini order: the two most distant taxa first (first such pair in (i, j) order); then repeatedly
  * the remaining taxon whose ascending-sorted vector of distances to the taxa already placed is
- * lexicographically greatest (first such taxon on ties).  The last taxon is whatever is left. */
-static void order_taxa(xmph_problem *p) {
+ * lexicographically greatest (first such taxon, in current row order, on ties).  The last taxon is
+ * whatever is left.  Rows are exchanged exactly as the reference exchanges them (row order decides
+ * ties), but on a permutation: the distances come from one matrix computed up front, and the rows
+ * themselves move once, at the end. */
+static void order_taxa(xmph_problem *p, unsigned threads) {
 	const unsigned n = p->num_taxa, ns = p->num_sites;
-	unsigned char *tmp = (unsigned char *) malloc(ns + 1);
+	unsigned *D = pair_matrix(p->sites, ns, n, p->site_weights, 0, threads);
 	unsigned *dist = (unsigned *) malloc(n * sizeof(unsigned));
 	unsigned *best = (unsigned *) malloc(n * sizeof(unsigned));
+	unsigned *at = p->taxon_map;                  /* at[k] = original row now at position k */
 	unsigned fi = 0, fj = 1, fd = 0;
 
-	for (unsigned i = 0; i < n; ++i) p->taxon_map[i] = i;
+	for (unsigned i = 0; i < n; ++i) at[i] = i;
 	for (unsigned i = 0; i + 1 < n; ++i) {
 		for (unsigned j = i + 1; j < n; ++j) {
-			unsigned d = fitch_distance(p->sites + (size_t) i * ns, p->sites + (size_t) j * ns, p->site_weights, ns);
+			unsigned d = D[(size_t) i * n + j];
 			if (d > fd) { fi = i; fj = j; fd = d; }
 		}
 	}
-	if (fi != 0) {
-		swap_rows(p, 0, fi, tmp);
-		p->taxon_map[0] = fi;
-		p->taxon_map[fi] = 0;
-	}
-	if (fj != 1) {
-		swap_rows(p, 1, fj, tmp);
-		unsigned t = p->taxon_map[fj];
-		p->taxon_map[fj] = p->taxon_map[1];
-		p->taxon_map[1] = t;
-	}
+	if (fi != 0) { at[0] = fi; at[fi] = 0; }
+	if (fj != 1) { unsigned t = at[fj]; at[fj] = at[1]; at[1] = t; }
 	for (unsigned k = 2; k + 1 < n; ++k) {
 		unsigned pick = k;
 		memset(best, 0, n * sizeof(unsigned));
 		for (unsigned i = k; i < n; ++i) {
-			for (unsigned j = 0; j < k; ++j) {
-				dist[j] = fitch_distance(p->sites + (size_t) i * ns, p->sites + (size_t) j * ns, p->site_weights, ns);
-			}
+			for (unsigned j = 0; j < k; ++j) dist[j] = D[(size_t) at[i] * n + at[j]];
 			qsort(dist, k, sizeof(unsigned), cmp_unsigned);
 			for (unsigned j = 0; j < k; ++j) {
 				if (dist[j] > best[j]) {
@@ -298,16 +334,19 @@ static void order_taxa(xmph_problem *p) {
 				if (dist[j] < best[j]) break;
 			}
 		}
-		if (pick != k) {
-			swap_rows(p, k, pick, tmp);
-			unsigned t = p->taxon_map[pick];
-			p->taxon_map[pick] = p->taxon_map[k];
-			p->taxon_map[k] = t;
-		}
+		if (pick != k) { unsigned t = at[pick]; at[pick] = at[k]; at[k] = t; }
+	}
+	int moved = 0;
+	for (unsigned i = 0; i < n; ++i) moved |= at[i] != i;
+	if (moved) {
+		unsigned char *sorted = (unsigned char *) malloc((size_t) n * ns + 1);
+		for (unsigned i = 0; i < n; ++i) memcpy(sorted + (size_t) i * ns, p->sites + (size_t) at[i] * ns, ns);
+		free(p->sites);
+		p->sites = sorted;
 	}
 	free(best);
 	free(dist);
-	free(tmp);
+	free(D);
 }
 
 /* ---- lower bounds --------------------------------------------------------------------------- */
@@ -347,17 +386,28 @@ static void distinct_bases_bound(xmph_problem *p) {
 
 /* MST bound: half the MST weight (Fitch distances, so ambiguity never overestimates) over
  * { union of taxa 0..k, taxon k+1, ..., taxon n-1 }, rounded down. */
-static void mst_bound(xmph_problem *p) {
+static void mst_bound(xmph_problem *p, unsigned threads) {
 	const unsigned n = p->num_taxa, ns = p->num_sites;
-	unsigned char *rows = (unsigned char *) malloc((size_t) n * ns + 1);
-	memcpy(rows, p->sites, (size_t) n * ns);
+	unsigned *D = pair_matrix(p->sites, ns, n, p->site_weights, 0, threads);   /* taxon-to-taxon distances never change */
+	unsigned char *joined = (unsigned char *) malloc((size_t) ns + 1);          /* union of taxa 0..k */
+	unsigned *sub = (unsigned *) malloc((size_t) n * n * sizeof(unsigned) + 4);
+	memcpy(joined, p->sites, ns);
 	for (unsigned k = 0; k + 1 < n; ++k) {
-		unsigned char *cur = rows + (size_t) k * ns;
-		unsigned b = mst_weight(cur, ns, n - k, p->site_weights, 0) / 2;
+		/* vertices: the union, then taxa k+1 .. n-1 */
+		const unsigned h = n - k;
+		sub[0] = 0;
+		for (unsigned j = 1; j < h; ++j) {
+			sub[j] = sub[(size_t) j * h] = k == 0 ? D[k + j] : fitch_distance(joined, p->sites + (size_t) (k + j) * ns, p->site_weights, ns);
+			for (unsigned i = 1; i < h; ++i) sub[(size_t) j * h + i] = D[(size_t) (k + j) * n + k + i];
+		}
+		unsigned b = mst_of_matrix(sub, h) / 2;
 		if (b > p->rest_bound[k]) p->rest_bound[k] = b;
-		for (unsigned i = 0; i < ns; ++i) cur[ns + i] |= cur[i];
+		const unsigned char *next = p->sites + (size_t) (k + 1) * ns;
+		for (unsigned i = 0; i < ns; ++i) joined[i] |= next[i];
 	}
-	free(rows);
+	free(sub);
+	free(joined);
+	free(D);
 }
 
 /* Same text format as restBound.txt: a header line, then "<index> <bound>" lines. */
@@ -446,11 +496,11 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 	free(c.col);
 	p->taxon_map = (unsigned *) malloc(a->num_taxa * sizeof(unsigned));
 	p->rest_bound = (unsigned *) calloc(a->num_taxa, sizeof(unsigned));
-	order_taxa(p);
+	order_taxa(p, s->threads);
 
 	p->bound = s->bound;
 	if (s->options & XMPH_OPT_IMPROVEINITUPPERBOUND) {
-		p->mst_upper_bound = mst_weight(p->sites, p->num_sites, p->num_taxa, p->site_weights, 1) + p->constant_weight;
+		p->mst_upper_bound = mst_weight(p->sites, p->num_sites, p->num_taxa, p->site_weights, 1, s->threads) + p->constant_weight;
 		if (p->mst_upper_bound < p->bound) p->bound = p->mst_upper_bound;
 	}
 	if (s->options & XMPH_OPT_USEDISTBASESBOUNDREST) distinct_bases_bound(p);
@@ -458,7 +508,7 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 		xmph_free_problem(p);
 		return -1;
 	}
-	if (s->options & XMPH_OPT_USEMSTBOUNDREST) mst_bound(p);
+	if (s->options & XMPH_OPT_USEMSTBOUNDREST) mst_bound(p, s->threads);
 	if ((s->options & XMPH_OPT_USEPARTBOUND) && xmph_part_bound(p, (int) s->part_strategy, s->part_max_stale, s->threads)) {
 		xmph_free_problem(p);
 		return -1;

@@ -80,8 +80,8 @@ def test_rest_bound_file_round_trip(alignment_dir, goldens, tmp_path):
 
 def test_unsupported_bounds_say_so(alignment_dir, goldens):
     a = xh.Alignment(str(alignment_dir / "h3.phy"))
-    with pytest.raises(xh.HostError, match="-Bf"):
-        xh.Problem(a, options=8192)
+    with pytest.raises(xh.HostError, match="-Bf"):        # -Bi (incompatibility bound) is not built in
+        xh.Problem(a, options=128)
 
 
 # ---- PHYLIP reader fixtures (reference data/phylip_format_testing; names encode the outcome) ----
