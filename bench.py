@@ -270,6 +270,7 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
             p = xh.Problem(a)          # default options: -Bd bound, MST upper bound, like the reference run
         ctx = xc.Context(local)
         ctx.load_problem(p)
+        ctx.search_reserve(p.num_taxa, p.n_blocks)      # device memory set up before the clock, like the reference's arena
         if dist:
             dist.barrier()
         torch.cuda.synchronize()

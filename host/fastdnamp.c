@@ -426,14 +426,16 @@ int main(int argc, char **argv) {
 	worker *ws = (worker *) calloc(c.n_gpus, sizeof(worker));
 	pthread_t *th = (pthread_t *) calloc(c.n_gpus, sizeof(pthread_t));
 
-	/* Device contexts are created before the clock starts, like the rest of program start-up; the
-	 * upload of the problem and the frontier allocation are inside the timed search. */
+	/* Device contexts and the search's device memory are set up before the clock starts, like the
+	 * reference's arena (InitTreeData, src/common.c:1113-1224); the upload of the problem is inside the
+	 * timed search. */
 	for (unsigned g = 0; g < c.n_gpus; ++g) {
 		ws[g].sh = &sh;
 		ws[g].p = &p;
 		ws[g].c = &c;
 		ws[g].index = g;
 		if (xmp_cuda_init((int) g, &ws[g].ctx)) die(xmp_cuda_last_error());
+		if (xmp_cuda_search_reserve(ws[g].ctx, p.num_taxa, p.n_blocks, c.mem_budget)) die(xmp_cuda_last_error());
 	}
 	t_search = now_seconds();
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_create(&th[g], NULL, worker_main, &ws[g]);

@@ -144,6 +144,11 @@ typedef struct {
 	double   seconds;                  /* device time spent inside xmp_cuda_search_run */
 } xmp_search_stats;
 
+/* Optional: allocate the search's device memory for a problem of this shape now (mem_budget as in
+ * xmp_search_params, 0 = default), so that xmp_cuda_search_begin finds it in place -- the reference
+ * likewise sets up its arena in InitTreeData, before its branch-and-bound timer starts
+ * (src/common.c:1113-1224).  The memory stays with the context and is reused by later searches. */
+int xmp_cuda_search_reserve(xmp_ctx *ctx, unsigned num_taxa, unsigned n_blocks, size_t mem_budget);
 int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *params);
 /* Runs at most max_batches frontier batches (0 = until done).  *done = 1 once the frontier is empty. */
 int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done);

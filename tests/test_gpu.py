@@ -261,6 +261,28 @@ def test_search_random_alignments_with_ambiguity_codes(xc, tmp_path):
     assert checked >= 15
 
 
+def test_search_memory_is_reserved_ahead_and_reused(xc, alignment_dir, goldens):
+    """xmp_cuda_search_reserve sets up the device memory before the search; the context keeps it, and
+    searches of other shapes in the same context (smaller, larger, reserved or not) stay exact."""
+    ctx = xc.Context(0)
+    try:
+        for name, reserve in (("h3", True), ("mh6", False), ("its14", True), ("mt-10", False), ("h3", False)):
+            g = goldens[name]
+            a, p = prepare(alignment_dir, goldens, name)
+            if reserve:
+                ctx.search_reserve(p.num_taxa, p.n_blocks)
+            ctx.load_problem(p)
+            ctx.search_begin(bound=p.bound)
+            while not ctx.search_run(0):
+                pass
+            score, n, paths = ctx.search_result()
+            check_against_golden(name, g, p, score, n, p.newick_list(paths))
+        with pytest.raises(xc.XmpCudaError):
+            ctx.search_reserve(3, 1)
+    finally:
+        ctx.close()
+
+
 def test_search_its36_with_loaded_partition_bound(xc, alignment_dir, goldens, tmp_path):
     """The author's own its36 setting (-Bp -b 233 -m 100000): restBound[] comes from the reference's
     restBound.txt through -Bf, as INTEGRATION.md describes."""

@@ -150,6 +150,8 @@ extern "C" void xmp_cuda_destroy(xmp_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	search_destroy(ctx);
 	free_problem(ctx);
+	if (ctx->arena) cudaFree(ctx->arena);
+	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	ctx->scratch.release();
 	ctx->scratch2.release();
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -64,6 +64,9 @@ struct xmp_ctx {
 
 	xmp::Scratch scratch, scratch2;
 	xmp::Search *search = nullptr;
+	void *arena = nullptr;         // the search's device memory (frontier pools, survivor lists, tree buffers), kept between searches
+	size_t arena_bytes = 0;
+	unsigned *h_pin = nullptr;     // pinned scalars the search polls
 };
 
 namespace xmp {

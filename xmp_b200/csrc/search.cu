@@ -451,7 +451,6 @@ struct Search {
 	unsigned long long surv_cap = 0;
 	uint4 *d_surv_lvl[XMP_MAX_TAXA + 2] = {nullptr};            // per-level survivor lists used by the sweep
 	unsigned long long surv_cap_lvl[XMP_MAX_TAXA + 2] = {0};
-	uint4 *d_surv_arena = nullptr;
 	unsigned *d_nsurv_lvl = nullptr;                           // [XMP_MAX_TAXA + 1] counters, one per level
 	bool sweep = true;
 	unsigned sweep_fallback = 1;
@@ -495,17 +494,7 @@ void search_destroy(xmp_ctx *ctx) {
 	if (!S) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) {
-		if (S->pool[m].hdr) cudaFree(S->pool[m].hdr);
-		if (S->pool[m].sets) cudaFree(S->pool[m].sets);
-	}
-	if (S->d_bound) cudaFree(S->d_bound);
-	if (S->d_surv) cudaFree(S->d_surv);
-	if (S->d_surv_arena) cudaFree(S->d_surv_arena);
-	if (S->d_trees[0]) cudaFree(S->d_trees[0]);
-	if (S->d_trees[1]) cudaFree(S->d_trees[1]);
-	if (S->d_len) cudaFree(S->d_len);
-	if (S->h_pin) cudaFreeHost(S->h_pin);
+	// device buffers live in ctx->arena, the pinned scalars in ctx->h_pin: both outlive the search
 	S->topo.release();
 	S->pathbuf.release();
 	S->stage.release();
@@ -513,8 +502,8 @@ void search_destroy(xmp_ctx *ctx) {
 	ctx->search = nullptr;
 }
 
-static int alloc_search(xmp_ctx *ctx, Search *S) {
-	const unsigned n = S->n, W = ctx->n_blocks, Emax = 2 * n - 3;
+static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
+	const unsigned n = S->n, Emax = 2 * n - 3;
 	Layout &L = S->L;
 	L.n = n;
 	L.W = W;
@@ -529,72 +518,75 @@ static int alloc_search(xmp_ctx *ctx, Search *S) {
 	// batches stay big -- while allocating tens of GiB costs tens of milliseconds, which short searches on
 	// few taxa would notice (profiles/r01_search_tuning.md).
 	const size_t dflt = n >= 17 ? ((size_t) 48 << 30) : ((size_t) 12 << 30);
-	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>(free_b / 2, dflt);
+	// free_b does not count an arena this context already holds
+	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>((free_b + ctx->arena_bytes) / 2, dflt);
 	S->trees_cap = 1u << 20;
-	const size_t fixed = 2 * (size_t) S->trees_cap * L.trec + ((size_t) 64 << 20);
-	if (budget < fixed + ((size_t) 64 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
-	budget -= fixed;
+	if (budget < 2 * (size_t) S->trees_cap * L.trec + ((size_t) 128 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
 
 	// The deepest pool is skipped when the last two levels are fused (narrow state sets): it then only
 	// ever holds imported jobs.
 	S->fused_last = !(S->prm.flags & XMP_SEARCH_NO_FUSE) && W <= 32 && n >= 5;
 	const double last_cap = S->fused_last ? 1024.0 : 1e300;
-	// Largest per-level capacity C such that all pools fit; a level never needs more than (2m-5)!! nodes.
-	auto bytes_for = [&](double C) {
-		double tot = 0;
+	// Everything the search keeps on the device is carved out of ONE allocation owned by the context
+	// (ctx->arena): a search costs one cudaMalloc instead of ~2n, and none at all when the arena was
+	// reserved beforehand (xmp_cuda_search_reserve) or is left over from an earlier search.
+	// layout(C, base) places every buffer for per-level capacity C and returns the bytes used; with
+	// base == nullptr it only measures.  A level never needs more than (2m-5)!! nodes.
+	auto layout = [&](unsigned long long C, char *base) -> size_t {
+		size_t off = 0;
+		auto take = [&](size_t bytes) -> void * {
+			off = (off + 255) & ~(size_t) 255;
+			void *ptr = base ? base + off : nullptr;
+			off += bytes;
+			return ptr;
+		};
 		for (unsigned m = 3; m < n; ++m) {
-			double c = std::min(C, odd_factorial(m));
-			if (m + 1 == n) c = std::min(c, last_cap);
-			c = 32.0 * std::ceil(c / 32.0);                                // whole tiles
-			tot += c * ((double) 2 * (2 * m - 3) * W * 16 + 4.0 * L.NW + 64);   // + four slots in a survivor list
+			Pool &P = S->pool[m];
+			P.E = 2 * m - 3;
+			P.rec = 2ull * P.E * W;       // [MIDPOINT | UP][edge][block]
+			P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
+			if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
+			P.cap = (P.cap + 31ull) & ~31ull;                                 // whole tiles (headers: 32 slots, sets: <= 8)
+			P.count = 0;
+			P.hdr = (unsigned *) take((size_t) P.cap * L.NW * 4);
+			P.sets = (uint4 *) take((size_t) P.cap * P.rec * 16);
 		}
-		return tot + 5 * C * 16;   // survivors of the single-batch path and of the fused level
-	};
-	double lo = 256, hi = 16777216.0;
-	if (bytes_for(lo) > (double) budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
-	while (hi - lo > 1) {
-		double mid = (lo + hi) / 2;
-		if (bytes_for(mid) <= (double) budget) lo = mid; else hi = mid;
-	}
-	const unsigned long long C = (unsigned long long) lo;
-	for (unsigned m = 3; m < n; ++m) {
-		Pool &P = S->pool[m];
-		P.E = 2 * m - 3;
-		P.rec = 2ull * P.E * W;       // [MIDPOINT | UP][edge][block]
-		P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
-		if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
-		P.cap = (P.cap + 31ull) & ~31ull;                                 // whole tiles (headers: 32 slots, sets: <= 8)
-		P.count = 0;
-		XMP_CUDA(cudaMalloc(&P.hdr, (size_t) P.cap * L.NW * 4));
-		XMP_CUDA(cudaMalloc(&P.sets, (size_t) P.cap * P.rec * 16));
-	}
-	S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) S->beam * Emax);
-	XMP_CUDA(cudaMalloc(&S->d_surv, (size_t) S->surv_cap * 16));
-	XMP_CUDA(cudaMalloc(&S->d_trees[0], (size_t) S->trees_cap * L.trec));
-	XMP_CUDA(cudaMalloc(&S->d_trees[1], (size_t) S->trees_cap * L.trec));
-	{
+		S->surv_cap = std::max<unsigned long long>(C, (unsigned long long) S->beam * Emax);
+		S->d_surv = (uint4 *) take((size_t) S->surv_cap * 16);
+		S->d_trees[0] = (uint8_t *) take((size_t) S->trees_cap * L.trec);
+		S->d_trees[1] = (uint8_t *) take((size_t) S->trees_cap * L.trec);
 		// one survivor list per level: as many entries as the pool its children go to (the fused level
 		// keeps them only until the fused kernel has consumed them)
-		unsigned long long total = 0;
 		for (unsigned m = 3; m + 1 < n; ++m) {
 			S->surv_cap_lvl[m] = (S->fused_last && m + 2 == n) ? 4 * S->surv_cap : 4 * S->pool[m + 1].cap;
-			total += S->surv_cap_lvl[m];
+			S->d_surv_lvl[m] = (uint4 *) take((size_t) S->surv_cap_lvl[m] * 16);
 		}
-		XMP_CUDA(cudaMalloc(&S->d_surv_arena, (size_t) std::max<unsigned long long>(total, 1) * 16));
-		unsigned long long off = 0;
-		for (unsigned m = 3; m + 1 < n; ++m) {
-			S->d_surv_lvl[m] = S->d_surv_arena + off;
-			off += S->surv_cap_lvl[m];
-		}
+		S->d_bound = (unsigned *) take(1024);
+		S->d_len = (unsigned *) take(65536 * sizeof(unsigned));
+		return off + 256;
+	};
+	unsigned long long lo = 256, hi = 16777216ull;
+	if (layout(lo, nullptr) > budget) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes cannot hold even a minimal frontier", budget);
+	while (hi - lo > 1) {
+		unsigned long long mid = (lo + hi) / 2;
+		if (layout(mid, nullptr) <= budget) lo = mid; else hi = mid;
 	}
-	XMP_CUDA(cudaMalloc(&S->d_bound, 1024));
+	const size_t need = layout(lo, nullptr);
+	if (ctx->arena_bytes < need) {
+		if (ctx->arena) cudaFree(ctx->arena);
+		ctx->arena = nullptr;
+		ctx->arena_bytes = 0;
+		XMP_CUDA(cudaMalloc(&ctx->arena, need));
+		ctx->arena_bytes = need;
+	}
+	layout(lo, (char *) ctx->arena);
 	S->d_nsurv = S->d_bound + 1;
 	S->d_ntrees = S->d_bound + 2;
 	S->d_merges = (unsigned long long *) (S->d_bound + 4);
 	S->d_nsurv_lvl = S->d_bound + 8;
 	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 1024, ctx->stream));
-	XMP_CUDA(cudaMalloc(&S->d_len, 65536 * sizeof(unsigned)));
-	XMP_CUDA(cudaMallocHost(&S->h_pin, 1024));
+	if (!ctx->h_pin) XMP_CUDA(cudaMallocHost(&ctx->h_pin, 1024));
+	S->h_pin = ctx->h_pin;
 	return XMP_OK;
 }
 
@@ -1078,9 +1070,40 @@ static int dive(xmp_ctx *ctx, Search *S) {
 	return fetch_counters(ctx, S);
 }
 
+static void init_knobs(xmp_ctx *ctx, Search *S) {
+	S->n = ctx->num_taxa;
+	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
+	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
+	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
+	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
+	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
+	memset(&S->st, 0, sizeof S->st);
+}
+
 }  // namespace xmp
 
 using namespace xmp;
+
+// Sizes and allocates the search's device memory for a problem of the given shape ahead of time, the
+// way the reference sets up its arena in InitTreeData before the branch-and-bound timer starts
+// (src/common.c:1113-1224, src/arena.h): a following xmp_cuda_search_begin on such a problem with the
+// same budget allocates nothing.
+extern "C" int xmp_cuda_search_reserve(xmp_ctx *ctx, unsigned num_taxa, unsigned n_blocks, size_t mem_budget) {
+	if (!ctx) return set_error(XMP_ERR_ARG, "null context");
+	if (num_taxa < 4 || num_taxa > XMP_MAX_TAXA || n_blocks == 0) return set_error(XMP_ERR_ARG, "cannot reserve a search for %u taxa x %u blocks", num_taxa, n_blocks);
+	XMP_CUDA(cudaSetDevice(ctx->device));
+	search_destroy(ctx);
+	Search *S = new Search();
+	ctx->search = S;
+	memset(&S->prm, 0, sizeof S->prm);
+	S->prm.mem_budget = mem_budget;
+	S->prm.shard_count = 1;
+	init_knobs(ctx, S);
+	S->n = num_taxa;
+	int rc = alloc_search(ctx, S, n_blocks);
+	search_destroy(ctx);
+	return rc;
+}
 
 extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *params) {
 	if (!ctx || !ctx->d_rows || !params) return set_error(XMP_ERR_ARG, "no problem loaded");
@@ -1092,14 +1115,8 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	S->prm = *params;
 	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
 	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
-	S->n = ctx->num_taxa;
-	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
-	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
-	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
-	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
-	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
-	memset(&S->st, 0, sizeof S->st);
-	int rc = alloc_search(ctx, S);
+	init_knobs(ctx, S);
+	int rc = alloc_search(ctx, S, ctx->n_blocks);
 	if (rc) { search_destroy(ctx); return rc; }
 	S->bound = params->bound;
 	XMP_CUDA(cudaMemcpyAsync(S->d_bound, &S->bound, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));

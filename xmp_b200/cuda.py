@@ -24,7 +24,7 @@ EXPORTS = [
     "FitchScore_fw1_b2_w16_cuda", "FitchScore_fw1_stopearly_b2_w16_cuda",
     "xmp_cuda_load", "xmp_cuda_load_device_rows", "xmp_cuda_build_midpoints", "xmp_cuda_score_batch",
     "xmp_cuda_score_insertions_host",
-    "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
+    "xmp_cuda_search_reserve", "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
     "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
 ]
@@ -68,6 +68,7 @@ def lib():
         L.xmp_cuda_build_midpoints.argtypes = [vp, vp, sz, u, u, vp, vp]
         L.xmp_cuda_score_batch.argtypes = [vp, vp, sz, u, u, vp, u, vp, vp, vp]
         L.xmp_cuda_score_insertions_host.argtypes = [vp, vp, sz, u, u, vp]
+        L.xmp_cuda_search_reserve.argtypes = [vp, u, u, sz]
         L.xmp_cuda_search_begin.argtypes = [vp, C.POINTER(SearchParams)]
         L.xmp_cuda_search_run.argtypes = [vp, u, C.POINTER(C.c_int)]
         L.xmp_cuda_search_get_bound.argtypes = [vp, C.POINTER(u)]
@@ -182,6 +183,10 @@ class Context:
         return {"cost_w1": out[0], "merge": out[1], "merge_cost": out[2]}
 
     # ---- search ----
+    def search_reserve(self, num_taxa, n_blocks, mem_budget=0):
+        """Allocates the search's device memory now, so that search_begin does not have to."""
+        _check(lib().xmp_cuda_search_reserve(self._h, num_taxa, n_blocks, mem_budget))
+
     def search_begin(self, bound=NO_LIMIT, max_trees=NO_LIMIT, mem_budget=0, shard_index=0, shard_count=1,
                      split_level=0, flags=0):
         p = SearchParams(bound, max_trees, mem_budget, shard_index, shard_count, split_level, flags)
