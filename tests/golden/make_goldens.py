@@ -67,6 +67,11 @@ DATASETS = {
     "quick2": ("data/quick_test/two_incompat_sites_of_weight_2.phy", []),
     "53humans.12": ("data/from_minmaxsqueeze/53humans.12.phy", []),
     "53humans.16": ("data/from_minmaxsqueeze/53humans.16.phy", []),
+    # deep searches (24-28 tree sizes in flight) under the partition bound; 1.4 M / 9.8 M / 9.8 M optimal trees,
+    # of which -m keeps the first 1000 the depth-first search finds (src/yanbader.c:272-293)
+    "53humans.24": ("data/from_minmaxsqueeze/53humans.24.phy", ["-Bp", "-m", "1000"]),
+    "53humans.26": ("data/from_minmaxsqueeze/53humans.26.phy", ["-Bp", "-m", "1000"]),
+    "53humans.28": ("data/from_minmaxsqueeze/53humans.28.phy", ["-Bp", "-m", "1000"]),
 }
 PARSER_FIXTURES = "data/phylip_format_testing"
 # inputs of other golden files (partbound.json): bundled here, not run by this script

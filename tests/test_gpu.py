@@ -261,6 +261,26 @@ def test_search_random_alignments_with_ambiguity_codes(xc, tmp_path):
     assert checked >= 15
 
 
+# optimal trees in total, from uncapped runs of the reference in the build container (12 s / 95 s / 332 s of CPU)
+DEEP_TOTALS = {"53humans.24": 1403325, "53humans.26": 9823275, "53humans.28": 9823275}
+
+
+@pytest.mark.parametrize("name", sorted(DEEP_TOTALS))
+def test_search_deep_with_partition_bound_and_tree_cap(xc, alignment_dir, goldens, name):
+    """24-28 taxa under the native partition bound: millions of optimal trees pass through the device tree
+    buffer; -m keeps the first 1000 in the reference's depth-first order (src/yanbader.c:272-293)."""
+    g = goldens[name]
+    a, p = prepare(alignment_dir, goldens, name)
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
+    cap = int(g["flags"][g["flags"].index("-m") + 1])
+    score, n, paths, stats = xc.search(p)
+    assert (score, n) == (g["score"], DEEP_TOTALS[name])
+    kept = p.sort_paths_dfs(paths)[:cap]
+    check_against_golden(name, g, p, score, cap, [p.path_to_newick(x) + ";" for x in kept])
+    print("\n%s: %.3f s device, %d nodes (reference %d, %.2f s CPU), %d batches" %
+          (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
+
+
 def test_search_memory_is_reserved_ahead_and_reused(xc, alignment_dir, goldens):
     """xmp_cuda_search_reserve sets up the device memory before the search; the context keeps it, and
     searches of other shapes in the same context (smaller, larger, reserved or not) stay exact."""

@@ -28,6 +28,8 @@ def prepare(alignment_dir, goldens, name, **kw):
         opts |= xh.OPT_USEDISTBASESBOUNDREST
     if "m" in letters:
         opts |= xh.OPT_USEMSTBOUNDREST
+    if "p" in letters:
+        opts |= xh.OPT_USEPARTBOUND
     return a, xh.Problem(a, options=opts, bound=bound, **kw)
 
 

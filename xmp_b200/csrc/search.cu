@@ -218,6 +218,7 @@ struct ChildWalk {
 // One thread per (survivor, 128-bit column): at step j the UP and MIDPOINT sets of the child's position j go
 // to row j of its record, the column-0 thread adds the program word -- consecutive threads build consecutive
 // slots, so with the tiled layout every such store fills whole 128-byte lines.
+template <int PF>
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
@@ -248,14 +249,15 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
 		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T);
-		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
-		unsigned wj, first_edge = 0;
-		uint4 ux, us;
+		// software-pipelined by PF steps: the UP sets of step j + PF are requested before step j's arithmetic
+		unsigned wj, wk = 0, first_edge = 0;
+		uint4 ux, us, uxk = r0, usk = r0;
 		cw.step(0, wj, ux, us, upath, T, r0);
+		if (PF == 2) cw.step(1, wk, uxk, usk, upath, T, r0);          // Ec >= 5
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned wn = wj;
-			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			unsigned wn = PF == 2 ? wk : wj;
+			uint4 uxn = PF == 2 ? uxk : ux, usn = PF == 2 ? usk : us;
+			if (j + PF < Ec) cw.step(j + PF, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
@@ -265,7 +267,8 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 				cprog[j * 32u] = wj;
 				if (j == 0) first_edge = prog_edge(wj);
 			}
-			wj = wn; ux = uxn; us = usn;
+			if (PF == 2) { wj = wk; ux = uxk; us = usk; wk = wn; uxk = uxn; usk = usn; }
+			else { wj = wn; ux = uxn; us = usn; }
 		}
 		if (col == 0) {
 			ch[0] = sv.z;
@@ -290,7 +293,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 // edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the columns), apply the
 // acceptance test and emit complete trees.  This replaces k_build_children for the deepest pool and the
 // whole k_expand_score pass over it -- where almost all nodes of a search live.
-template <int G>
+template <int G, int PF>
 __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
                     unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
@@ -327,14 +330,15 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
 			bound = __shfl_sync(active, bound, leader);
 		}
-		unsigned wj;
-		uint4 ux, us;
+		// software-pipelined by PF steps: the UP sets of step j + PF are requested before step j's arithmetic
+		unsigned wj, wk = 0;
+		uint4 ux, us, uxk = r0, usk = r0;
 		cw.step(0, wj, ux, us, upath, T, r0);
+		if (PF == 2) cw.step(1, wk, uxk, usk, upath, T, r0);          // Ec >= 5
 		for (unsigned j = 0; j < Ec; ++j) {
-			// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
-			unsigned wn = wj;
-			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			unsigned wn = PF == 2 ? wk : wj;
+			uint4 uxn = PF == 2 ? uxk : ux, usn = PF == 2 ? usk : us;
+			if (j + PF < Ec) cw.step(j + PF, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
@@ -352,7 +356,8 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 					rec[4 + m + 1] = (uint8_t) prog_edge(wj);
 				}
 			}
-			wj = wn; ux = uxn; us = usn;
+			if (PF == 2) { wj = wk; ux = uxk; us = usk; wk = wn; uxk = uxn; usk = usn; }
+			else { wj = wn; ux = uxn; us = usn; }
 		}
 		if (sub == 0) my_merges += n_up + 2 * Ec;
 	}
@@ -468,6 +473,7 @@ struct Search {
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	unsigned min_batch = 32768, beam = 512;
+	unsigned prefetch = 1;        // walk steps whose loads are in flight ahead of the arithmetic (1 or 2)
 	xmp_search_stats st;
 	Scratch topo, pathbuf, stage;
 };
@@ -694,9 +700,15 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
-	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-	                                                         ctx->d_rows, S->d_merges, D);
+	if (S->prefetch == 2) {
+		XMP_CUDA(cudaFuncSetAttribute(k_build_children<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_build_children<2><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+		                                                            ctx->d_rows, S->d_merges, D);
+	} else {
+		XMP_CUDA(cudaFuncSetAttribute(k_build_children<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_build_children<1><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+		                                                            ctx->d_rows, S->d_merges, D);
+	}
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -709,12 +721,17 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
-#define XMP_FUSED(G)                                                                                                          \
+#define XMP_FUSED_PF(G, PF)                                                                                                   \
 	do {                                                                                                                      \
-		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
-		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
+		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));      \
+		k_expand_last_fused<G, PF><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,           \
 		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
 		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D); \
+	} while (0)
+#define XMP_FUSED(G)                                  \
+	do {                                              \
+		if (S->prefetch == 2) XMP_FUSED_PF(G, 2);     \
+		else XMP_FUSED_PF(G, 1);                      \
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
@@ -723,6 +740,7 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	else if (L.W <= 16) XMP_FUSED(16);
 	else XMP_FUSED(32);
 #undef XMP_FUSED
+#undef XMP_FUSED_PF
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -1076,6 +1094,7 @@ static void init_knobs(xmp_ctx *ctx, Search *S) {
 	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
+	S->prefetch = env_unsigned("XMP_PREFETCH", 1) == 2 ? 2u : 1u;
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
 }
