@@ -70,6 +70,21 @@ __device__ __forceinline__ unsigned path_byte(const unsigned *h, unsigned t) {
 	return (h[(HDR_PATH_W + (t >> 2)) * 32u] >> (8u * (t & 3u))) & 0xFFu;
 }
 
+// Writes a tree record: its length, then the insertion path of the node with header h (one byte per taxon,
+// copied a word at a time) with bytes t0 and t0 + 1 replaced by e0 and e1 (pass t0 + 1 >= 4 * words to skip e1).
+__device__ __forceinline__ void emit_tree(uint8_t *rec, const Layout &L, const unsigned *h, unsigned length,
+                                          unsigned t0, unsigned e0, unsigned e1, bool two) {
+	unsigned *out = (unsigned *) rec;
+	out[0] = length;
+	const unsigned words = (L.n + 3u) >> 2;
+	for (unsigned q = 0; q < words; ++q) {
+		unsigned w = h[(HDR_PATH_W + q) * 32u];
+		if (q == (t0 >> 2)) w = (w & ~(0xFFu << (8u * (t0 & 3u)))) | (e0 << (8u * (t0 & 3u)));
+		if (two && q == ((t0 + 1u) >> 2)) w = (w & ~(0xFFu << (8u * ((t0 + 1u) & 3u)))) | (e1 << (8u * ((t0 + 1u) & 3u)));
+		out[1 + q] = w;
+	}
+}
+
 __device__ __forceinline__ unsigned path_hash(const unsigned *h, unsigned m, unsigned e) {
 	unsigned x = 2166136261u;
 	for (unsigned t = 3; t < m; ++t) x = (x ^ path_byte(h, t)) * 16777619u;
@@ -123,10 +138,7 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
 		unsigned slot = block_append(keep, n_trees, s_warp);
 		if (keep && slot < trees_cap) {
-			uint8_t *rec = trees + (size_t) slot * L.trec;
-			*(unsigned *) rec = new_score;
-			for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = (uint8_t) path_byte(hdr, t);
-			rec[4 + m] = (uint8_t) prog_edge(hdr[(L.off_prog + pos) * 32u]);
+			emit_tree(trees + (size_t) slot * L.trec, L, hdr, new_score, m, prog_edge(hdr[(L.off_prog + pos) * 32u]), 0u, false);
 		}
 	} else {
 		unsigned slot = block_append(keep, n_surv, s_warp);
@@ -218,7 +230,6 @@ struct ChildWalk {
 // One thread per (survivor, 128-bit column): at step j the UP and MIDPOINT sets of the child's position j go
 // to row j of its record, the column-0 thread adds the program word -- consecutive threads build consecutive
 // slots, so with the tiled layout every such store fills whole 128-byte lines.
-template <int PF>
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
@@ -249,15 +260,15 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
 		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T);
-		// software-pipelined by PF steps: the UP sets of step j + PF are requested before step j's arithmetic
-		unsigned wj, wk = 0, first_edge = 0;
-		uint4 ux, us, uxk = r0, usk = r0;
+		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
+		// (two steps ahead was measured and gains nothing: profiles/r01_search_tuning.md)
+		unsigned wj, first_edge = 0;
+		uint4 ux, us;
 		cw.step(0, wj, ux, us, upath, T, r0);
-		if (PF == 2) cw.step(1, wk, uxk, usk, upath, T, r0);          // Ec >= 5
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned wn = PF == 2 ? wk : wj;
-			uint4 uxn = PF == 2 ? uxk : ux, usn = PF == 2 ? usk : us;
-			if (j + PF < Ec) cw.step(j + PF, wn, uxn, usn, upath, T, r0);
+			unsigned wn = wj;
+			uint4 uxn = ux, usn = us;
+			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
@@ -267,8 +278,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 				cprog[j * 32u] = wj;
 				if (j == 0) first_edge = prog_edge(wj);
 			}
-			if (PF == 2) { wj = wk; ux = uxk; us = usk; wk = wn; uxk = uxn; usk = usn; }
-			else { wj = wn; ux = uxn; us = usn; }
+			wj = wn; ux = uxn; us = usn;
 		}
 		if (col == 0) {
 			ch[0] = sv.z;
@@ -293,7 +303,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 // edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the columns), apply the
 // acceptance test and emit complete trees.  This replaces k_build_children for the deepest pool and the
 // whole k_expand_score pass over it -- where almost all nodes of a search live.
-template <int G, int PF>
+template <int G>
 __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
                     unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
@@ -330,15 +340,14 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
 			bound = __shfl_sync(active, bound, leader);
 		}
-		// software-pipelined by PF steps: the UP sets of step j + PF are requested before step j's arithmetic
-		unsigned wj, wk = 0;
-		uint4 ux, us, uxk = r0, usk = r0;
+		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
+		unsigned wj;
+		uint4 ux, us;
 		cw.step(0, wj, ux, us, upath, T, r0);
-		if (PF == 2) cw.step(1, wk, uxk, usk, upath, T, r0);          // Ec >= 5
 		for (unsigned j = 0; j < Ec; ++j) {
-			unsigned wn = PF == 2 ? wk : wj;
-			uint4 uxn = PF == 2 ? uxk : ux, usn = PF == 2 ? usk : us;
-			if (j + PF < Ec) cw.step(j + PF, wn, uxn, usn, upath, T, r0);
+			unsigned wn = wj;
+			uint4 uxn = ux, usn = us;
+			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
@@ -349,15 +358,10 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 				if (score + c < bound) atomicMin(bound_ptr, score + c);
 				const unsigned slot = atomicAdd(n_trees, 1u);
 				if (slot < trees_cap) {
-					uint8_t *rec = trees + (size_t) slot * L.trec;
-					*(unsigned *) rec = score + c;
-					for (unsigned t = 0; t < L.n; ++t) rec[4 + t] = (uint8_t) path_byte(ph, t);
-					rec[4 + m] = (uint8_t) cw.sp.xv;
-					rec[4 + m + 1] = (uint8_t) prog_edge(wj);
+					emit_tree(trees + (size_t) slot * L.trec, L, ph, score + c, m, cw.sp.xv, prog_edge(wj), true);
 				}
 			}
-			if (PF == 2) { wj = wk; ux = uxk; us = usk; wk = wn; uxk = uxn; usk = usn; }
-			else { wj = wn; ux = uxn; us = usn; }
+			wj = wn; ux = uxn; us = usn;
 		}
 		if (sub == 0) my_merges += n_up + 2 * Ec;
 	}
@@ -469,11 +473,11 @@ struct Search {
 	unsigned trees_cap = 0, ntrees_dev = 0;
 	unsigned *h_pin = nullptr;            // pinned copy of the device scalars: [0] bound, [1] n_surv, [2] n_trees
 	std::vector<uint8_t> host_trees;      // records (score + path) that left the device, each <= the bound at that time
+	unsigned host_bound = 0xffffffffu;    // the bound host_trees was last filtered against
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	unsigned min_batch = 32768, beam = 512;
-	unsigned prefetch = 1;        // walk steps whose loads are in flight ahead of the arithmetic (1 or 2)
 	xmp_search_stats st;
 	Scratch topo, pathbuf, stage;
 };
@@ -526,7 +530,7 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 	const size_t dflt = n >= 17 ? ((size_t) 48 << 30) : ((size_t) 12 << 30);
 	// free_b does not count an arena this context already holds
 	size_t budget = S->prm.mem_budget ? S->prm.mem_budget : std::min<size_t>((free_b + ctx->arena_bytes) / 2, dflt);
-	S->trees_cap = 1u << 20;
+	S->trees_cap = budget >= ((size_t) 8 << 30) ? 1u << 22 : 1u << 20;      // records the device holds between drains
 	if (budget < 2 * (size_t) S->trees_cap * L.trec + ((size_t) 128 << 20)) return set_error(XMP_ERR_NOMEM, "memory budget of %zu bytes is too small for the search", budget);
 
 	// The deepest pool is skipped when the last two levels are fused (narrow state sets): it then only
@@ -700,15 +704,9 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
-	if (S->prefetch == 2) {
-		XMP_CUDA(cudaFuncSetAttribute(k_build_children<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_build_children<2><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-		                                                            ctx->d_rows, S->d_merges, D);
-	} else {
-		XMP_CUDA(cudaFuncSetAttribute(k_build_children<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_build_children<1><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-		                                                            ctx->d_rows, S->d_merges, D);
-	}
+	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+	                                                         ctx->d_rows, S->d_merges, D);
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -721,17 +719,12 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
-#define XMP_FUSED_PF(G, PF)                                                                                                   \
+#define XMP_FUSED(G)                                                                                                          \
 	do {                                                                                                                      \
-		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));      \
-		k_expand_last_fused<G, PF><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,           \
+		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
+		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
 		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
 		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D); \
-	} while (0)
-#define XMP_FUSED(G)                                  \
-	do {                                              \
-		if (S->prefetch == 2) XMP_FUSED_PF(G, 2);     \
-		else XMP_FUSED_PF(G, 1);                      \
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
@@ -740,7 +733,6 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	else if (L.W <= 16) XMP_FUSED(16);
 	else XMP_FUSED(32);
 #undef XMP_FUSED
-#undef XMP_FUSED_PF
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -761,9 +753,11 @@ static int drain_trees(xmp_ctx *ctx, Search *S) {
 		S->host_trees.resize(old + bytes);
 		XMP_CUDA(cudaMemcpyAsync(S->host_trees.data() + old, S->d_trees[S->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		// Drop what the current bound already rules out.
-		size_t w = 0;
-		for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
+		// Drop what the current bound already rules out: only the new records, unless the bound has moved
+		// since the older ones were checked.
+		size_t w = S->bound < S->host_bound ? 0 : old;
+		S->host_bound = S->bound;
+		for (size_t r = w; r < S->host_trees.size(); r += S->L.trec) {
 			unsigned sc;
 			memcpy(&sc, S->host_trees.data() + r, 4);
 			if (sc <= S->bound) {
@@ -792,6 +786,45 @@ static int tidy_trees(xmp_ctx *ctx, Search *S) {
 	if (rc) return rc;
 	S->ntrees_dev = S->h_pin[2];
 	if (S->ntrees_dev > S->trees_cap / 2) return drain_trees(ctx, S);
+	return XMP_OK;
+}
+
+// The tree buffer overflowed inside the fused kernel (records past the end were dropped, the counter kept
+// counting): restore the counter, make room and redo this level's survivors piece by piece.  The counter
+// says how many trees the whole list yields, so the list is cut into pieces that should each fill about half
+// the buffer; a piece that still overflows is halved.  Emission is idempotent: records carry their own length.
+static int redo_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned ns, const uint4 *surv, const unsigned *nsurv, unsigned before) {
+	struct Range { unsigned lo, hi; };
+	std::vector<Range> todo;
+	const unsigned long long produced = S->h_pin[2] - before, half = S->trees_cap / 2;
+	unsigned pieces = (unsigned) std::min<unsigned long long>(ns, std::max<unsigned long long>(2, (produced + half - 1) / half));
+	if (pieces < 1) pieces = 1;
+	for (unsigned p = pieces; p-- > 0;) {
+		const unsigned lo = (unsigned) ((unsigned long long) ns * p / pieces), hi = (unsigned) ((unsigned long long) ns * (p + 1) / pieces);
+		if (hi > lo) todo.push_back(Range{lo, hi});
+	}
+	S->ntrees_dev = before;
+	while (!todo.empty()) {
+		Range r = todo.back();
+		todo.pop_back();
+		int rc = drain_trees(ctx, S);
+		if (rc) return rc;
+		rc = launch_fused(ctx, S, m, r.lo, r.hi, surv, nsurv);
+		if (rc) return rc;
+		rc = fetch_counters(ctx, S);
+		if (rc) return rc;
+		if (S->h_pin[2] > S->trees_cap) {
+			if (r.hi - r.lo < 2) return set_error(XMP_ERR_NOMEM, "tree buffer too small for a single partial tree's completions");
+			const unsigned mid = r.lo + (r.hi - r.lo) / 2;
+			todo.push_back(Range{mid, r.hi});
+			todo.push_back(Range{r.lo, mid});
+			S->ntrees_dev = 0;
+			XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
+			continue;
+		}
+		S->st.full_trees += S->h_pin[2];
+		S->ntrees_dev = S->h_pin[2];
+	}
 	return XMP_OK;
 }
 
@@ -843,33 +876,8 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		if (rc) return rc;
 		const unsigned ns = S->h_pin[1];
 		if (S->h_pin[2] > S->trees_cap) {
-			// The tree buffer overflowed and records were dropped: put the counter back, make room and
-			// redo the survivors in halves (emission is idempotent: records carry their own length).
-			struct Range { unsigned lo, hi; };
-			std::vector<Range> todo;
-			todo.push_back(Range{0, ns});
-			S->ntrees_dev = before;
-			while (!todo.empty()) {
-				Range r = todo.back();
-				todo.pop_back();
-				rc = drain_trees(ctx, S);
-				if (rc) return rc;
-				rc = launch_fused(ctx, S, m, r.lo, r.hi, S->d_surv, S->d_nsurv);
-				if (rc) return rc;
-				rc = fetch_counters(ctx, S);
-				if (rc) return rc;
-				if (S->h_pin[2] > S->trees_cap) {
-					if (r.hi - r.lo < 2) return set_error(XMP_ERR_NOMEM, "tree buffer too small for a single partial tree's completions");
-					const unsigned mid = r.lo + (r.hi - r.lo) / 2;
-					todo.push_back(Range{mid, r.hi});
-					todo.push_back(Range{r.lo, mid});
-					S->ntrees_dev = 0;
-					XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
-					continue;
-				}
-				S->st.full_trees += S->h_pin[2];
-				S->ntrees_dev = S->h_pin[2];
-			}
+			rc = redo_fused(ctx, S, m, ns, S->d_surv, S->d_nsurv, before);
+			if (rc) return rc;
 		} else {
 			S->st.full_trees += S->h_pin[2] - before;
 			S->ntrees_dev = S->h_pin[2];
@@ -1013,33 +1021,8 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 			S->st.nodes += ns;
 			S->st.score_calls += (unsigned long long) ns * (P.E + 2);
 			if (S->h_pin[2] > S->trees_cap) {
-				// The tree buffer overflowed inside the fused kernel: restore the counter, make room and redo
-				// this level's survivors in halves (emission is idempotent: records carry their own length).
-				struct Range { unsigned lo, hi; };
-				std::vector<Range> todo;
-				todo.push_back(Range{0, ns});
-				S->ntrees_dev = before;
-				while (!todo.empty()) {
-					Range r = todo.back();
-					todo.pop_back();
-					rc = drain_trees(ctx, S);
-					if (rc) return rc;
-					rc = launch_fused(ctx, S, m, r.lo, r.hi, S->d_surv_lvl[m], S->d_nsurv_lvl + m);
-					if (rc) return rc;
-					rc = fetch_counters(ctx, S);
-					if (rc) return rc;
-					if (S->h_pin[2] > S->trees_cap) {
-						if (r.hi - r.lo < 2) return set_error(XMP_ERR_NOMEM, "tree buffer too small for a single partial tree's completions");
-						const unsigned mid = r.lo + (r.hi - r.lo) / 2;
-						todo.push_back(Range{mid, r.hi});
-						todo.push_back(Range{r.lo, mid});
-						S->ntrees_dev = 0;
-						XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
-						continue;
-					}
-					S->st.full_trees += S->h_pin[2];
-					S->ntrees_dev = S->h_pin[2];
-				}
+				rc = redo_fused(ctx, S, m, ns, S->d_surv_lvl[m], S->d_nsurv_lvl + m, before);
+				if (rc) return rc;
 			} else {
 				S->st.full_trees += S->h_pin[2] - before;
 				S->ntrees_dev = S->h_pin[2];
@@ -1084,6 +1067,7 @@ static int dive(xmp_ctx *ctx, Search *S) {
 	// Trees found by the dive will be found again by the search proper.
 	S->ntrees_dev = 0;
 	S->host_trees.clear();
+	S->host_bound = 0xffffffffu;
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
 	return fetch_counters(ctx, S);
 }
@@ -1094,7 +1078,6 @@ static void init_knobs(xmp_ctx *ctx, Search *S) {
 	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
-	S->prefetch = env_unsigned("XMP_PREFETCH", 1) == 2 ? 2u : 1u;
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
 }
