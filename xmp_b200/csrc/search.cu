@@ -178,7 +178,7 @@ struct ChildWalk {
 	}
 	// Decodes the insertion at position P of the parent and recomputes UP along the root path.
 	__device__ __forceinline__ unsigned init(const unsigned *ph, const Layout &L, unsigned m, unsigned P, const uint4 *parent_up,
-	                                         const uint4 &row_new, uint4 *upath, unsigned T) {
+	                                         const uint4 &row_new, uint4 *upath, unsigned T, unsigned D, bool &overflow) {
 		prog = ph + L.off_prog * 32u;
 		PU = parent_up;
 		rs = L.W << L.ts_shift;
@@ -191,7 +191,7 @@ struct ChildWalk {
 		unsigned k = 1, cur = P, other = sp.sv;
 		for (unsigned depth = sp.dv; depth > 0; --depth) {
 			u = fitch_block(u, __ldg(PU + (size_t) other * rs));     // `other` hangs off the path: unchanged
-			upath[(size_t) k * T] = u;
+			if (k < D) upath[(size_t) k * T] = u; else overflow = true;
 			cur = parent_pos(cur, other);
 			mark(cur);
 			other = prog_sib(prog[cur * 32u]);
@@ -230,10 +230,14 @@ struct ChildWalk {
 // One thread per (survivor, 128-bit column): at step j the UP and MIDPOINT sets of the child's position j go
 // to row j of its record, the column-0 thread adds the program word -- consecutive threads build consecutive
 // slots, so with the tiled layout every such store fills whole 128-byte lines.
+// The two per-thread stacks hold D entries each; D comes from the deepest tree the level has produced so far
+// (depth_out collects it for the next level), not from the worst case m + 1, so that deep levels (20-36 taxa)
+// still fit four CTAs per SM.  (Compiling for six CTAs -- 80 registers -- was measured and is slower:
+// profiles/r01_search_tuning.md.)
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
-                 const uint4 *__restrict__ rows, unsigned long long *merges, unsigned D) {
+                 const uint4 *__restrict__ rows, unsigned long long *merges, unsigned D, unsigned *depth_out, unsigned *overflow_flag) {
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
@@ -242,7 +246,8 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned long long total = n_surv > s_begin ? (unsigned long long) (n_surv - s_begin) * W : 0ull;
-	unsigned my_merges = 0;
+	unsigned my_merges = 0, my_depth = 0;
+	bool overflow = false;
 	for (unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
 	     idx += (unsigned long long) gridDim.x * blockDim.x) {
 		const unsigned k = (unsigned) (idx / W), col = (unsigned) (idx % W);
@@ -259,7 +264,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		unsigned *cprog = ch + L.off_prog * 32u;
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T);
+		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T, D, overflow);
 		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
 		// (two steps ahead was measured and gains nothing: profiles/r01_search_tuning.md)
 		unsigned wj, first_edge = 0;
@@ -271,7 +276,10 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
-			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
+			if (prog_size(wj) > 1u) {
+				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
+			}
+			my_depth = max(my_depth, d);
 			CU[(size_t) j * rs] = ux;
 			CM[(size_t) j * rs] = fitch_block(ux, dn);
 			if (col == 0) {
@@ -295,6 +303,9 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	// statistics: one atomic per warp that did any work, not one per child
 	my_merges = warp_sum(my_merges);
 	if ((threadIdx.x & 31u) == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
+	my_depth = __reduce_max_sync(0xffffffffu, my_depth);
+	if ((threadIdx.x & 31u) == 0 && my_depth > *(volatile unsigned *) depth_out) atomicMax(depth_out, my_depth);
+	if (overflow) atomicOr(overflow_flag, 1u);
 }
 
 // ---- last two levels fused ---------------------------------------------------------------------------
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
                     unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
                     unsigned *bound_ptr, uint8_t *__restrict__ trees, unsigned *n_trees, unsigned trees_cap,
-                    unsigned long long *merges, unsigned D) {
+                    unsigned long long *merges, unsigned D, unsigned *overflow_flag) {
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
@@ -324,6 +335,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	const uint4 rt = __ldg(rows + (size_t) m * W + col);
 	const uint4 rl = __ldg(rows + (size_t) (m + 1) * W + col);
 	unsigned my_merges = 0;
+	bool overflow = false;
 	for (unsigned long long s = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + threadIdx.x / G; s < n_surv;
 	     s += (unsigned long long) gridDim.x * groups_per_block) {
 		const uint4 sv = surv[s];
@@ -331,7 +343,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		const unsigned *ph = hdr_of(parent, L, pnode);
 		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T);
+		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
 		unsigned bound = 0;
 		{
@@ -350,7 +362,9 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
-			if (prog_size(wj) > 1u) dstack[(size_t) d * T] = dn;
+			if (prog_size(wj) > 1u) {
+				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
+			}
 			unsigned c = col_ok ? cost_block(fitch_block(ux, dn), rl, col, wp) : 0u;
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
@@ -367,6 +381,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	}
 	my_merges = warp_sum(my_merges);
 	if (lane == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
+	if (overflow) atomicOr(overflow_flag, 1u);
 }
 
 // Headers for nodes whose sets were built from topologies (the root job, imported jobs).
@@ -478,6 +493,8 @@ struct Search {
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	unsigned min_batch = 32768, beam = 512;
+	unsigned maxdepth[XMP_MAX_TAXA + 2] = {0};   // deepest tree seen so far per tree size (sizes the walk kernels' stacks)
+	unsigned *d_maxdepth = nullptr, *d_overflow = nullptr;
 	xmp_search_stats st;
 	Scratch topo, pathbuf, stage;
 };
@@ -594,6 +611,8 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 	S->d_ntrees = S->d_bound + 2;
 	S->d_merges = (unsigned long long *) (S->d_bound + 4);
 	S->d_nsurv_lvl = S->d_bound + 8;
+	S->d_overflow = S->d_bound + 6;
+	S->d_maxdepth = S->d_bound + 128;          // [XMP_MAX_TAXA + 2]
 	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 1024, ctx->stream));
 	if (!ctx->h_pin) XMP_CUDA(cudaMallocHost(&ctx->h_pin, 1024));
 	S->h_pin = ctx->h_pin;
@@ -630,6 +649,13 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 				memcpy(row + stride, t.kid[0], E);
 				memcpy(row + 2 * stride, t.kid[1], E);
 				t.preorder(row + 3 * stride);
+				// depth of this tree (parents precede children in pre-order): the walk kernels size their stacks by it
+				uint8_t depth[2 * XMP_MAX_TAXA];
+				for (unsigned q = 0; q < E; ++q) {
+					const unsigned e = row[3 * stride + q], pe = t.par[e];
+					depth[e] = pe == 0xFFu ? 0 : (uint8_t) (depth[pe] + 1);
+					S->maxdepth[m] = std::max<unsigned>(S->maxdepth[m], depth[e]);
+				}
 			}
 			int rc = S->topo.reserve(h.size());
 			if (rc) return rc;
@@ -689,7 +715,9 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	return XMP_OK;
 }
 
-// Shared memory of the child-walk kernels: two stacks of D = m + 1 blocks per thread.
+// Shared memory of the child-walk kernels: two stacks of D blocks per thread.  A child of a tree of depth d is
+// at most d + 1 deep; its stacks are indexed by depth, so D = (deepest parent so far) + 2, capped by the worst
+// case m + 1 (a caterpillar).
 static unsigned walk_threads(unsigned D, size_t *smem) {
 	unsigned threads = 128;
 	while (threads > 32 && (size_t) 2 * D * 16 * threads > ((size_t) 96 << 10)) threads >>= 1;
@@ -700,13 +728,13 @@ static unsigned walk_threads(unsigned D, size_t *smem) {
 static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *surv, const unsigned *nsurv, unsigned long long child_first,
                            unsigned s_begin = 0, unsigned s_end = 0xffffffffu) {
 	Pool &P = S->pool[m], &C = S->pool[m + 1];
-	const unsigned D = m + 1;
+	const unsigned D = std::min(m + 1, S->maxdepth[m] + 2);
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-	                                                         ctx->d_rows, S->d_merges, D);
+	                                                         ctx->d_rows, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -715,7 +743,7 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, unsigned s_end, const uint4 *surv, const unsigned *nsurv) {
 	const Layout &L = S->L;
 	Pool &P = S->pool[m];
-	const unsigned D = m + 1;                        // a tree on m + 1 taxa is at most m edges deep
+	const unsigned D = std::min(m + 1, S->maxdepth[m] + 2);
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
@@ -724,7 +752,8 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
 		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
 		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
-		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D); \
+		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D, \
+		                                                            S->d_overflow);                                               \
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
@@ -740,9 +769,11 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 
 // Reads back n_surv, n_trees, bound and the merge counter (one small pinned copy, one sync).
 static int fetch_counters(xmp_ctx *ctx, Search *S) {
-	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 32 + 4 * (XMP_MAX_TAXA + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaMemcpyAsync(S->h_pin, S->d_bound, 1024, cudaMemcpyDeviceToHost, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	S->bound = S->h_pin[0];
+	for (unsigned m = 3; m <= S->n; ++m) S->maxdepth[m] = std::max(S->maxdepth[m], S->h_pin[128 + m]);
+	if (S->h_pin[6]) return set_error(XMP_ERR_NOMEM, "a walk stack overflowed: a tree was deeper than its level's recorded maximum (internal error)");
 	return XMP_OK;
 }
 
