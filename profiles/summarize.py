@@ -60,6 +60,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 def write_full(name, rep, title, cmd, tail):
     hdr, units, data = raw_metrics(os.path.join(OUT, rep))
+    _UNITS.update(dict(zip(hdr, units)))
     with open(os.path.join(P, name), "w") as f:
         f.write("# %s\n\n    %s\n\nRead here with `ncu -i gpurun_out/%s --page raw --csv`.\n\n" % (title, cmd, rep))
         f.write("| metric | " + " | ".join("launch %d" % (i + 1) for i in range(len(data))) + " | unit |\n|---|" + "---:|" * len(data) + "---|\n")
@@ -77,6 +78,13 @@ def write_full(name, rep, title, cmd, tail):
             f.write("\nWarp stall reasons >= 3 %% of active warp cycles (launch 1): " + ", ".join("%s %.0f %%" % (n, v) for v, n in sorted(stalls, reverse=True)) + ".\n")
         f.write("\n" + tail(hdr, data) + "\n")
     return hdr, data
+
+
+_UNITS = {}
+
+
+def units_of(hdr, key):
+    return _UNITS.get(key, "")
 
 
 def first_json(path):
@@ -171,6 +179,31 @@ def main():
                 "issue and latency at ~16 warps per SM; see `%s_search_tuning.md` for how it got here and what the integer-pipe microbenchmark says." % R)
     write_full("%s_ncu_full_k_expand_last_fused.md" % R, "prof_fused_h4.ncu-rep", "%s - `ncu --set full` of `xmp::k_expand_last_fused<2>` during the search of h4" % R,
                "ncu --set full --clock-control none --import-source on -k regex:k_expand_last_fused -s 12 -c 1 -o gpurun_out/prof_fused_h4 ./fastdnamp_b200 ... h4.phy  (scripts/gpu_fused_prof.sh)", t2)
+
+    # ---- search on mh3: the narrow, deep case
+    if os.path.exists(os.path.join(OUT, "search_launches_mh3.csv")):
+        def n3(d, tot):
+            return ("Exact search of mh3 (20 taxa x 22 patterns, ONE 128-bit block per state set; 2.7e8 partial trees, 6e9 edge evaluations, "
+                    "408,945 optimal trees; the reference's serial CPU program needs 224 s).  Seventeen tree sizes are in flight at once, every "
+                    "level's children are written to HBM and read back once: `k_build_children` and `k_expand_score<1>` share the time; the "
+                    "fused last level is a rounding error here because the bound prunes almost everything before it.")
+        write_launches("%s_launches_search_mh3.md" % R, "search_launches_mh3.csv", "%s - ncu launch list of the exact search of measure/mh3 (`fastdnamp_b200`)" % R,
+                       "ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/search_launches_mh3.csv ./fastdnamp_b200 --tbr=N --seed=1 --displaynewbounds=n --displaynewtrees=n --updatesecs=0 -o out.nex mh3.phy", n3)
+    if os.path.exists(os.path.join(OUT, "prof_score_mh3.ncu-rep")):
+        def t3(hdr, data):
+            rd = float(data[0][hdr.index("dram__bytes_read.sum")]); ru = units_of(hdr, "dram__bytes_read.sum")
+            return ("One thread per (partial tree, edge) pair, 16 B of MIDPOINT state per pair: a launch of this size moves tens of MB, far from "
+                    "the HBM roof; what the counters above say about where the cycles go is the starting point for the next round "
+                    "(`%s_search_tuning.md` lists what was tried on this kernel and did not help).  DRAM read in this launch: %s %s." % (R, rd, ru))
+        write_full("%s_ncu_full_k_expand_score.md" % R, "prof_score_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_expand_score<1>` during the search of mh3 (launch 300)" % R,
+                   "ncu --set full --clock-control none --import-source on -k regex:k_expand_score -s 300 -c 1 -o gpurun_out/prof_score_mh3 ./fastdnamp_b200 ... mh3.phy  (scripts/gpu_check.sh ncu)", t3)
+    if os.path.exists(os.path.join(OUT, "prof_children_mh3.ncu-rep")):
+        def t4(hdr, data):
+            return ("One thread per (surviving insertion, 128-bit column): reads the parent's UP rows (L2 / DRAM: the lanes of a warp share a few "
+                    "parents), writes the child's UP and MIDPOINT rows and its header in whole 128-byte lines (tiled pools).  Four 128-thread CTAs "
+                    "per SM (registers), stacks in shared memory sized by the deepest tree seen.")
+        write_full("%s_ncu_full_k_build_children.md" % R, "prof_children_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_build_children` during the search of mh3 (launch 300)" % R,
+                   "ncu --set full --clock-control none --import-source on -k regex:k_build_children -s 300 -c 1 -o gpurun_out/prof_children_mh3 ./fastdnamp_b200 ... mh3.phy  (scripts/gpu_check.sh ncu)", t4)
 
     write_scaling()
     shutil.copy(os.path.join(OUT, "bench.log"), os.path.join(P, "%s_bench_n1.json" % R))
