@@ -132,6 +132,7 @@ typedef struct {
 } xmp_search_params;
 #define XMP_SEARCH_NO_DIVE 1u   /* skip the greedy beam dive that tightens the bound first */
 #define XMP_SEARCH_NO_FUSE 2u   /* materialise the deepest pool instead of fusing the last two levels (testing) */
+#define XMP_SEARCH_NO_EAGER 4u  /* keep MIDPOINT sets in the frontier and score them in a separate pass (the layout for > 32 blocks) */
 
 typedef struct {
 	unsigned long long nodes;          /* partial trees expanded (= BranchAndBound() invocations) */

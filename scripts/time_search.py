@@ -24,7 +24,7 @@ for rep in range(2):
             ctx.search_reserve(p.num_taxa, p.n_blocks, budget)
         t2r = time.perf_counter(); reserve_ms = 1e3 * (t2r - tr); t2 = t2r
         ctx.load_problem(p); t3 = time.perf_counter()
-        ctx.search_begin(bound=p.bound, mem_budget=int(float(os.environ.get('XMP_BUDGET_GB', '0')) * 2**30)); t4 = time.perf_counter()
+        ctx.search_begin(bound=p.bound, mem_budget=int(float(os.environ.get('XMP_BUDGET_GB', '0')) * 2**30), flags=int(os.environ.get('XMP_FLAGS', '0'))); t4 = time.perf_counter()
         while not ctx.search_run(0): pass
         t5 = time.perf_counter()
         score, n, paths = ctx.search_result(); st = ctx.search_stats(); t6 = time.perf_counter()

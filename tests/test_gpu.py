@@ -254,7 +254,7 @@ def test_search_random_alignments_with_ambiguity_codes(xc, tmp_path):
         if p.num_sites == 0:
             continue
         want_score, want_n, want_trees, _, _ = ol.search(p)
-        score, n_trees, paths, _ = xc.search(p, flags=(xc.SEARCH_NO_FUSE if case % 4 == 1 else 0))
+        score, n_trees, paths, _ = xc.search(p, flags=(0, xc.SEARCH_NO_FUSE, xc.SEARCH_NO_EAGER, xc.SEARCH_NO_FUSE | xc.SEARCH_NO_EAGER)[case % 4])
         assert (score, n_trees) == (want_score, want_n), case
         assert p.newick_list(paths) == want_trees, case       # same trees, and in the reference's DFS order
         checked += 1
@@ -279,6 +279,16 @@ def test_search_deep_with_partition_bound_and_tree_cap(xc, alignment_dir, golden
     check_against_golden(name, g, p, score, cap, [p.path_to_newick(x) + ";" for x in kept])
     print("\n%s: %.3f s device, %d nodes (reference %d, %.2f s CPU), %d batches" %
           (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
+
+
+@pytest.mark.parametrize("name", ["Metazoan", "rbc14x759", "EukaryotesrDNA", "mh1"])
+def test_search_classic_layout_on_multi_block_sets(xc, alignment_dir, goldens, name):
+    """The layout that keeps MIDPOINT sets (used by default only above 32 blocks per set, i.e. mt-10 here) on
+    1-, 5-, 6- and 19-block sets, where the default is eager scoring: same trees either way."""
+    g = goldens[name]
+    a, p = prepare(alignment_dir, goldens, name)
+    score, n, trees, stats = run_search(xc, p, flags=xc.SEARCH_NO_EAGER)
+    check_against_golden(name, g, p, score, n, trees)
 
 
 def test_search_memory_is_reserved_ahead_and_reused(xc, alignment_dir, goldens):
@@ -351,7 +361,8 @@ def test_search_is_independent_of_scheduling(xc, alignment_dir, goldens):
     g = goldens["mh6"]
     a, p = prepare(alignment_dir, goldens, "mh6")
     for kw in ({"flags": xc.SEARCH_NO_DIVE}, {"mem_budget": 600 << 20}, {"flags": xc.SEARCH_NO_FUSE},
-               {"flags": xc.SEARCH_NO_FUSE | xc.SEARCH_NO_DIVE, "mem_budget": 400 << 20}):
+               {"flags": xc.SEARCH_NO_FUSE | xc.SEARCH_NO_DIVE, "mem_budget": 400 << 20},
+               {"flags": xc.SEARCH_NO_EAGER}, {"flags": xc.SEARCH_NO_EAGER | xc.SEARCH_NO_FUSE, "mem_budget": 600 << 20}):
         score, n, trees, stats = run_search(xc, p, **kw)
         check_against_golden("mh6", g, p, score, n, trees)
     # the one-level-per-synchronisation scheduler (kept for A/B measurements) instead of the sweep

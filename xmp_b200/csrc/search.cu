@@ -40,7 +40,13 @@ struct Layout {
 	unsigned off_prog;  // index of the first program word
 	unsigned ts_shift;  // records are tiled: 1 << ts_shift consecutive slots interleave their rows
 	unsigned trec;      // bytes per emitted tree record: score + path
+	unsigned off_cost;  // eager scoring: index of the first cost word (one per pre-order position); 0 = classic layout
 };
+// Two record layouts.  Classic: rows [MIDPOINT | UP], the scoring pass reads the MIDPOINT rows.  Eager (off_cost != 0,
+// state sets of up to 32 blocks): the kernel that builds a node also scores the NEXT taxon on each of its edges and
+// leaves the costs in the header, one word per position; MIDPOINT sets are never stored (rows = UP only, half the
+// bytes), and the scoring pass shrinks to reading 4 bytes per (tree, edge) pair and applying the current bound.
+__device__ __forceinline__ unsigned up_row0(const Layout &L, unsigned E) { return L.off_cost ? 0u : E; }
 // Header words: [0] tree length so far | [1, 1 + ceil(n/4)) insertion path, one byte per taxon (byte 0 = the
 // root's child) | [off_prog, off_prog + 2n-3) walk program (walk_prog.h), one word per pre-order position.
 #define HDR_PATH_W 1u
@@ -55,7 +61,7 @@ struct Layout {
 struct PoolView {
 	unsigned *hdr;
 	uint4 *sets;
-	unsigned nsets;           // rows per node = 2 * (2m-3)
+	unsigned nsets;           // rows per node: 2 * (2m-3), or 2m-3 with eager scoring
 	unsigned long long cap;   // slots (a multiple of 32); pools are rings: slot = index modulo cap
 };
 
@@ -132,6 +138,45 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 		const unsigned score = hdr[0];
 		keep = accept_insertion(s, s_bound, score, rest);
 		new_score = score + s;
+		if (keep && shard_count > 1) keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos) * 32u])) % shard_count) == shard_index;
+	}
+	if (last) {
+		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
+		unsigned slot = block_append(keep, n_trees, s_warp);
+		if (keep && slot < trees_cap) {
+			emit_tree(trees + (size_t) slot * L.trec, L, hdr, new_score, m, prog_edge(hdr[(L.off_prog + pos) * 32u]), 0u, false);
+		}
+	} else {
+		unsigned slot = block_append(keep, n_surv, s_warp);
+		if (keep) surv[slot] = make_uint4((unsigned) node, pos, new_score, 0u);
+	}
+}
+
+// Eager layout: the costs are already in the headers.  One thread per (tree, position); pairs are enumerated by
+// header tile (32 slots), position, slot, so that a warp reads one 128-byte line of cost words.
+__global__ void __launch_bounds__(256)
+k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes, unsigned rest,
+         unsigned *bound_ptr, int last, uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
+         unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
+	__shared__ unsigned s_bound, s_warp[9];
+	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
+	const unsigned E = 2 * m - 3, tile_pairs = E * 32u;
+	const unsigned long long pair = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long tile = pair / tile_pairs;
+	const unsigned r = (unsigned) (pair - tile * tile_pairs);
+	const unsigned pos = r >> 5;
+	const long long lin = (long long) ((tile << 5) + (r & 31u)) - (long long) (first & 31ull);   // index inside the batch
+	const bool valid = lin >= 0 && (unsigned long long) lin < n_nodes;
+	unsigned long long node = first + (valid ? (unsigned long long) lin : 0ull);
+	if (node >= pool.cap) node -= pool.cap;              // the batch may wrap around the end of the ring
+	__syncthreads();
+	bool keep = false;
+	unsigned new_score = 0;
+	const unsigned *hdr = hdr_of(pool, L, node);
+	if (valid) {
+		const unsigned score = hdr[0], cost = hdr[(L.off_cost + pos) * 32u];
+		keep = accept_insertion(cost, s_bound, score, rest);
+		new_score = score + cost;
 		if (keep && shard_count > 1) keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos) * 32u])) % shard_count) == shard_index;
 	}
 	if (last) {
@@ -257,7 +302,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		const uint4 sv = surv[s];
 		const unsigned pnode = sv.x, P = sv.y;
 		const unsigned *ph = hdr_of(parent, L, pnode);
-		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;
+		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;      // classic layout only (launch_children)
 		uint4 *CM = sets_of(child, L, cslot) + col;
 		uint4 *CU = CM + (size_t) Ec * rs;                  // DOWN sets are not kept: no later step reads them
 		unsigned *ch = hdr_of(child, L, cslot);
@@ -308,6 +353,104 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 	if (overflow) atomicOr(overflow_flag, 1u);
 }
 
+// Eager variant: the child's MIDPOINT sets are not stored; each is scored against the taxon the child will
+// receive next, and the per-position costs go to the child's header.  A child's W columns sit in consecutive
+// threads of ONE CTA (whole children per CTA), their costs meet in shared memory.
+__global__ void __launch_bounds__(128)
+k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
+                       const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
+                       const uint4 *__restrict__ rows, WeightPlanes wp, unsigned long long *merges, unsigned D,
+                       unsigned *depth_out, unsigned *overflow_flag) {
+	extern __shared__ uint4 smem[];
+	const unsigned T = blockDim.x;
+	uint4 *upath = smem + threadIdx.x;
+	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
+	unsigned *acc = (unsigned *) (smem + (size_t) 2 * D * T);        // [cpc][Ec], used when W > 1
+	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
+	const unsigned cpc = T / W;                                        // whole children per CTA (W <= 32 <= T)
+	const unsigned n_surv = min(*n_surv_ptr, s_end);
+	const unsigned n_children = n_surv > s_begin ? n_surv - s_begin : 0u;
+	const unsigned lc = threadIdx.x / W, col = threadIdx.x - lc * W;
+	const uint4 r0 = __ldg(rows + col);
+	const uint4 rt = __ldg(rows + (size_t) m * W + col);
+	const uint4 rn = __ldg(rows + (size_t) (m + 1) * W + col);         // the taxon the child is scored against
+	unsigned my_merges = 0, my_depth = 0;
+	bool overflow = false;
+	for (unsigned base = blockIdx.x * cpc; base < n_children; base += gridDim.x * cpc) {
+		const unsigned k = base + lc;
+		const bool active = lc < cpc && k < n_children;
+		if (W > 1) {
+			for (unsigned x = threadIdx.x; x < cpc * Ec; x += T) acc[x] = 0;
+			__syncthreads();
+		}
+		if (active) {
+			const unsigned s = s_begin + k;
+			unsigned long long cslot = child_first + k;
+			if (cslot >= child.cap) cslot -= child.cap;
+			const uint4 sv = surv[s];
+			const unsigned pnode = sv.x, P = sv.y;
+			const unsigned *ph = hdr_of(parent, L, pnode);
+			const uint4 *PU = sets_of(parent, L, pnode) + col;             // eager layout: rows are the UP sets
+			uint4 *CU = sets_of(child, L, cslot) + col;
+			unsigned *ch = hdr_of(child, L, cslot);
+			unsigned *cprog = ch + L.off_prog * 32u, *ccost = ch + L.off_cost * 32u;
+			ChildWalk cw;
+			const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
+			unsigned wj, first_edge = 0;
+			uint4 ux, us;
+			cw.step(0, wj, ux, us, upath, T, r0);
+			for (unsigned j = 0; j < Ec; ++j) {
+				unsigned wn = wj;
+				uint4 uxn = ux, usn = us;
+				if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+				const unsigned d = prog_depth(wj);
+				const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
+				if (prog_size(wj) > 1u) {
+					if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
+				}
+				my_depth = max(my_depth, d);
+				CU[(size_t) j * rs] = ux;
+				const unsigned c = cost_block(fitch_block(ux, dn), rn, col, wp);
+				if (W == 1) ccost[j * 32u] = c;
+				else if (c) atomicAdd(&acc[lc * Ec + j], c);
+				if (col == 0) {
+					cprog[j * 32u] = wj;
+					if (j == 0) first_edge = prog_edge(wj);
+				}
+				wj = wn; ux = uxn; us = usn;
+			}
+			if (col == 0) {
+				ch[0] = sv.z;
+				const unsigned pw = (L.n + 3u) >> 2;
+				for (unsigned q = 0; q < pw; ++q) {
+					unsigned w = ph[(HDR_PATH_W + q) * 32u];
+					if (q == (m >> 2)) w = (w & ~(0xFFu << (8u * (m & 3u)))) | (cw.sp.xv << (8u * (m & 3u)));
+					if (q == 0) w = (w & ~0xFFu) | first_edge;
+					ch[(HDR_PATH_W + q) * 32u] = w;
+				}
+				my_merges += n_up + 2 * Ec;
+			}
+		}
+		if (W > 1) {
+			__syncthreads();
+			for (unsigned x = threadIdx.x; x < cpc * Ec; x += T) {
+				const unsigned c_l = x / Ec, j = x - c_l * Ec, kk = base + c_l;
+				if (kk < n_children) {
+					unsigned long long cslot = child_first + kk;
+					if (cslot >= child.cap) cslot -= child.cap;
+					hdr_of(child, L, cslot)[(L.off_cost + j) * 32u] = acc[x];
+				}
+			}
+			__syncthreads();
+		}
+	}
+	my_merges = warp_sum(my_merges);
+	if ((threadIdx.x & 31u) == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
+	my_depth = __reduce_max_sync(0xffffffffu, my_depth);
+	if ((threadIdx.x & 31u) == 0 && my_depth > *(volatile unsigned *) depth_out) atomicMax(depth_out, my_depth);
+	if (overflow) atomicOr(overflow_flag, 1u);
+}
+
 // ---- last two levels fused ---------------------------------------------------------------------------
 // Parents have n-2 taxa.  A surviving child (n-1 taxa) is only ever scored once more, against the last
 // taxon, so it is never written to HBM: G lanes per child (one per 128-bit column) walk it, form each
@@ -341,7 +484,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		const uint4 sv = surv[s];
 		const unsigned pnode = sv.x, P = sv.y, score = sv.z;
 		const unsigned *ph = hdr_of(parent, L, pnode);
-		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) E * rs + col;
+		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) up_row0(L, E) * rs + col;
 		ChildWalk cw;
 		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
@@ -426,8 +569,27 @@ __global__ void k_scatter_sets(PoolView pool, Layout L, unsigned m, unsigned lon
 	const uint4 *rec = src + (size_t) j * 2 * E * W;
 	uint4 *dst = sets_of(pool, L, first + j) + col;
 	const size_t rs = (size_t) W << L.ts_shift;
-	dst[(size_t) i * rs] = rec[(size_t) e * W + col];
-	dst[(size_t) (E + i) * rs] = rec[((size_t) E + e) * W + col];
+	if (L.off_cost) {
+		dst[(size_t) i * rs] = rec[((size_t) E + e) * W + col];
+	} else {
+		dst[(size_t) i * rs] = rec[(size_t) e * W + col];
+		dst[(size_t) (E + i) * rs] = rec[((size_t) E + e) * W + col];
+	}
+}
+
+// Eager layout: cost of inserting taxon m at every position of the imported nodes, from their staged MIDPOINT sets.
+__global__ void k_stage_costs(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n_jobs,
+                              const uint8_t *__restrict__ topo, unsigned topo_stride, const uint4 *__restrict__ src,
+                              const uint4 *__restrict__ taxon_row, WeightPlanes wp) {
+	const unsigned E = 2 * m - 3, W = L.W;
+	const unsigned long long idx = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (unsigned long long) n_jobs * E) return;
+	const unsigned i = (unsigned) (idx % E), j = (unsigned) (idx / E);
+	const unsigned e = topo[(size_t) j * 4 * topo_stride + 3 * topo_stride + i];
+	const uint4 *mid = src + ((size_t) j * 2 * E + e) * W;
+	unsigned c = 0;
+	for (unsigned b = 0; b < W; ++b) c += cost_block(mid[b], __ldg(taxon_row + b), b, wp);
+	hdr_of(pool, L, first + j)[(L.off_cost + i) * 32u] = c;
 }
 
 // Insertion paths of nodes first .. first + n - 1 as plain byte records (job descriptors for export).
@@ -459,8 +621,8 @@ struct Pool {
 	uint4 *sets = nullptr;
 	unsigned long long cap = 0, count = 0, rec = 0;   // rec = uint4 per node
 	unsigned long long head = 0;          // ring: open nodes occupy slots head .. head + count - 1 (modulo cap)
-	unsigned E = 0;
-	PoolView view() const { return PoolView{hdr, sets, 2 * E, cap}; }
+	unsigned E = 0, rows = 0;             // rows per node: 2E classic, E eager
+	PoolView view() const { return PoolView{hdr, sets, rows, cap}; }
 	unsigned long long slot(unsigned long long i) const { return (head + i) % cap; }
 };
 
@@ -492,6 +654,7 @@ struct Search {
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
+	bool eager = false;           // nodes carry their insertion costs instead of MIDPOINT sets (Layout::off_cost)
 	unsigned min_batch = 32768, beam = 512;
 	unsigned maxdepth[XMP_MAX_TAXA + 2] = {0};   // deepest tree seen so far per tree size (sizes the walk kernels' stacks)
 	unsigned *d_maxdepth = nullptr, *d_overflow = nullptr;
@@ -535,7 +698,9 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 	L.n = n;
 	L.W = W;
 	L.off_prog = HDR_PATH_W + ((n + 3u) >> 2);
-	L.NW = L.off_prog + Emax;
+	S->eager = !(S->prm.flags & XMP_SEARCH_NO_EAGER) && W <= 32;
+	L.off_cost = S->eager ? L.off_prog + Emax : 0u;
+	L.NW = L.off_prog + Emax + (S->eager ? Emax : 0u);
 	L.ts_shift = W == 1 ? 3u : (W == 2 ? 2u : (W <= 4 ? 1u : 0u));     // one 128-byte line per row of a tile
 	L.trec = 4 + ((n + 3u) & ~3u);
 
@@ -570,7 +735,8 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 		for (unsigned m = 3; m < n; ++m) {
 			Pool &P = S->pool[m];
 			P.E = 2 * m - 3;
-			P.rec = 2ull * P.E * W;       // [MIDPOINT | UP][edge][block]
+			P.rows = S->eager ? P.E : 2 * P.E;
+			P.rec = (unsigned long long) P.rows * W;       // classic: [MIDPOINT | UP][edge][block]; eager: [UP][edge][block]
 			P.cap = (unsigned long long) std::min((double) C, odd_factorial(m));
 			if (m + 1 == n) P.cap = (unsigned long long) std::min((double) P.cap, last_cap);
 			P.cap = (P.cap + 31ull) & ~31ull;                                 // whole tiles (headers: 32 slots, sets: <= 8)
@@ -634,7 +800,7 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 		while (done < k) {
 			Pool &P = S->pool[m];
 			// at most 65536 nodes and 256 MiB of staging per round
-			unsigned part = (unsigned) std::min<size_t>(k - done, std::max<size_t>(1, std::min<size_t>(65536, ((size_t) 256 << 20) / ((size_t) P.rec * 16))));
+			unsigned part = (unsigned) std::min<size_t>(k - done, std::max<size_t>(1, std::min<size_t>(65536, ((size_t) 256 << 20) / ((size_t) 2 * P.E * L.W * 16))));
 			if (P.count + part > P.cap) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m, P.cap);
 			const unsigned long long tail = P.slot(P.count);
 			part = (unsigned) std::min<unsigned long long>(part, P.cap - tail);      // up to the end of the ring, the rest next time
@@ -663,9 +829,9 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			if (rc) return rc;
 			XMP_CUDA(cudaMemcpyAsync(S->topo.ptr, h.data(), h.size(), cudaMemcpyHostToDevice, ctx->stream));
 			XMP_CUDA(cudaMemcpyAsync(S->pathbuf.ptr, sel.data() + done * L.n, (size_t) part * L.n, cudaMemcpyHostToDevice, ctx->stream));
-			rc = S->stage.reserve((size_t) part * P.rec * 16);
+			rc = S->stage.reserve((size_t) part * 2 * P.E * L.W * 16);
 			if (rc) return rc;
-			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, (uint4 *) S->stage.ptr, (size_t) P.rec, true, S->d_len);
+			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, (uint4 *) S->stage.ptr, (size_t) 2 * P.E * L.W, true, S->d_len);
 			if (rc) return rc;
 			{
 				const unsigned long long threads = (unsigned long long) part * E * L.W;
@@ -676,6 +842,12 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			k_write_headers<<<(part + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
 			                                                            (const uint8_t *) S->pathbuf.ptr, S->d_len);
 			XMP_CUDA(cudaGetLastError());
+			if (S->eager) {
+				const unsigned long long threads = (unsigned long long) part * E;
+				k_stage_costs<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
+				                                                                         (const uint4 *) S->stage.ptr, ctx->d_rows + (size_t) m * L.W, ctx->wp);
+				XMP_CUDA(cudaGetLastError());
+			}
 			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 			S->st.launches += 3;
 			P.count += part;
@@ -698,6 +870,15 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	const unsigned long long pairs = (tiles << L.ts_shift) * P.E;
 	uint8_t *trees = S->d_trees[S->cur];   // slots are absolute: d_ntrees already counts the records present
 	const unsigned room = S->trees_cap;
+	if (S->eager) {
+		const unsigned long long tiles32 = ((first & 31ull) + chunk + 31ull) >> 5;
+		const unsigned long long pairs32 = tiles32 * 32ull * P.E;
+		k_select<<<(unsigned) ((pairs32 + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, rest, S->d_bound, last, surv, nsurv, trees,
+		                                                                   S->d_ntrees, room, sc, si);
+		XMP_CUDA(cudaGetLastError());
+		S->st.launches += 1;
+		return XMP_OK;
+	}
 #define XMP_EXPAND(G)                                                                                                   \
 	k_expand_score<G><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
 	                                                                              S->d_bound, last, surv, nsurv, trees,             \
@@ -732,6 +913,15 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
+	if (S->eager) {
+		if (S->L.W > 1) smem += (size_t) (threads / S->L.W) * (2 * m - 1) * sizeof(unsigned);      // per-position costs of the CTA's children
+		XMP_CUDA(cudaFuncSetAttribute(k_build_children_eager, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_build_children_eager<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+		                                                               ctx->d_rows, ctx->wp, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+		XMP_CUDA(cudaGetLastError());
+		S->st.launches += 1;
+		return XMP_OK;
+	}
 	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
 	                                                         ctx->d_rows, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);

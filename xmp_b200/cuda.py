@@ -15,6 +15,7 @@ _LIB = None
 NO_LIMIT = 0x7FFFFFFF
 SEARCH_NO_DIVE = 1
 SEARCH_NO_FUSE = 2
+SEARCH_NO_EAGER = 4
 
 EXPORTS = [
     "xmp_cuda_last_error", "xmp_cuda_device_count", "xmp_cuda_init", "xmp_cuda_destroy", "xmp_cuda_set_stream",
