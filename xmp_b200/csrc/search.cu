@@ -152,42 +152,87 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	}
 }
 
-// Eager layout: the costs are already in the headers.  One thread per (tree, position); pairs are enumerated by
-// header tile (32 slots), position, slot, so that a warp reads one 128-byte line of cost words.
+// Eager layout: the costs are already in the headers.  Pairs are enumerated by header tile (32 slots), position,
+// slot, so that a warp reads whole 128-byte lines of cost words.  A CTA's life is a chain of latencies -- the
+// bound word, the header words, the atomic that reserves its place in the survivor list -- and with one pair
+// per thread a launch is limited by how many such chains the GPU can have in flight (measured: 68 us for 11 M
+// pairs, the same as the kernel that also read and scored the MIDPOINT sets).  So every thread takes K pairs,
+// 256 apart, loads them all at once, and the CTA reserves list space once.
+template <int K>
 __global__ void __launch_bounds__(256)
 k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes, unsigned rest,
          unsigned *bound_ptr, int last, uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
          unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
-	__shared__ unsigned s_bound, s_warp[9];
+	__shared__ unsigned s_bound, s_warp[8], s_base;
 	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
 	const unsigned E = 2 * m - 3, tile_pairs = E * 32u;
-	const unsigned long long pair = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-	const unsigned long long tile = pair / tile_pairs;
-	const unsigned r = (unsigned) (pair - tile * tile_pairs);
-	const unsigned pos = r >> 5;
-	const long long lin = (long long) ((tile << 5) + (r & 31u)) - (long long) (first & 31ull);   // index inside the batch
-	const bool valid = lin >= 0 && (unsigned long long) lin < n_nodes;
-	unsigned long long node = first + (valid ? (unsigned long long) lin : 0ull);
-	if (node >= pool.cap) node -= pool.cap;              // the batch may wrap around the end of the ring
-	__syncthreads();
-	bool keep = false;
-	unsigned new_score = 0;
-	const unsigned *hdr = hdr_of(pool, L, node);
-	if (valid) {
-		const unsigned score = hdr[0], cost = hdr[(L.off_cost + pos) * 32u];
-		keep = accept_insertion(cost, s_bound, score, rest);
-		new_score = score + cost;
-		if (keep && shard_count > 1) keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos) * 32u])) % shard_count) == shard_index;
+	const unsigned long long base = (unsigned long long) blockIdx.x * (256u * K);
+	const unsigned long long tile0 = base / tile_pairs;
+	const unsigned r0 = (unsigned) (base - tile0 * tile_pairs) + threadIdx.x;
+	unsigned node[K], pos[K], score[K], cost[K];
+	bool valid[K];
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+		const unsigned rr = r0 + 256u * i, q = rr / tile_pairs, r = rr - q * tile_pairs;
+		pos[i] = r >> 5;
+		const long long lin = (long long) (((tile0 + q) << 5) + (r & 31u)) - (long long) (first & 31ull);   // index inside the batch
+		valid[i] = lin >= 0 && (unsigned long long) lin < n_nodes;
+		unsigned long long nd = first + (valid[i] ? (unsigned long long) lin : 0ull);
+		if (nd >= pool.cap) nd -= pool.cap;              // the batch may wrap around the end of the ring
+		node[i] = (unsigned) nd;
+		const unsigned *hdr = hdr_of(pool, L, nd);
+		score[i] = valid[i] ? hdr[0] : 0u;
+		cost[i] = valid[i] ? hdr[(L.off_cost + pos[i]) * 32u] : 0u;
 	}
-	if (last) {
-		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
-		unsigned slot = block_append(keep, n_trees, s_warp);
-		if (keep && slot < trees_cap) {
-			emit_tree(trees + (size_t) slot * L.trec, L, hdr, new_score, m, prog_edge(hdr[(L.off_prog + pos) * 32u]), 0u, false);
+	__syncthreads();
+	const unsigned bound = s_bound;
+	unsigned mask = 0, best = 0xffffffffu;
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+		bool keep = valid[i] && accept_insertion(cost[i], bound, score[i], rest);
+		if (keep && shard_count > 1) {
+			const unsigned *hdr = hdr_of(pool, L, node[i]);
+			keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos[i]) * 32u])) % shard_count) == shard_index;
 		}
-	} else {
-		unsigned slot = block_append(keep, n_surv, s_warp);
-		if (keep) surv[slot] = make_uint4((unsigned) node, pos, new_score, 0u);
+		if (keep) {
+			mask |= 1u << i;
+			best = min(best, score[i] + cost[i]);
+		}
+	}
+	if (last && best < bound) atomicMin(bound_ptr, best);
+	// place in the list: exclusive scan of the per-thread counts over the CTA, one atomic per CTA
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cnt = (unsigned) __popc(mask);
+	unsigned incl = cnt;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((int) lane >= o) incl += v;
+	}
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned total = 0;
+		for (unsigned w = 0; w < 8; ++w) {
+			const unsigned c = s_warp[w];
+			s_warp[w] = total;
+			total += c;
+		}
+		s_base = total ? atomicAdd(last ? n_trees : n_surv, total) : 0u;
+	}
+	__syncthreads();
+	unsigned slot = s_base + s_warp[warp] + incl - cnt;
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+		if (!((mask >> i) & 1u)) continue;
+		if (last) {
+			if (slot < trees_cap) {
+				const unsigned *hdr = hdr_of(pool, L, node[i]);
+				emit_tree(trees + (size_t) slot * L.trec, L, hdr, score[i] + cost[i], m, prog_edge(hdr[(L.off_prog + pos[i]) * 32u]), 0u, false);
+			}
+		} else {
+			surv[slot] = make_uint4(node[i], pos[i], score[i] + cost[i], 0u);
+		}
+		++slot;
 	}
 }
 
@@ -873,8 +918,8 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	if (S->eager) {
 		const unsigned long long tiles32 = ((first & 31ull) + chunk + 31ull) >> 5;
 		const unsigned long long pairs32 = tiles32 * 32ull * P.E;
-		k_select<<<(unsigned) ((pairs32 + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, rest, S->d_bound, last, surv, nsurv, trees,
-		                                                                   S->d_ntrees, room, sc, si);
+		k_select<8><<<(unsigned) ((pairs32 + 2047) / 2048), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, rest, S->d_bound, last, surv, nsurv, trees,
+		                                                                        S->d_ntrees, room, sc, si);
 		XMP_CUDA(cudaGetLastError());
 		S->st.launches += 1;
 		return XMP_OK;
