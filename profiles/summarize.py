@@ -184,25 +184,29 @@ def main():
     if os.path.exists(os.path.join(OUT, "search_launches_mh3.csv")):
         def n3(d, tot):
             return ("Exact search of mh3 (20 taxa x 22 patterns, ONE 128-bit block per state set; 2.7e8 partial trees, 6e9 edge evaluations, "
-                    "408,945 optimal trees; the reference's serial CPU program needs 224 s).  Seventeen tree sizes are in flight at once, every "
-                    "level's children are written to HBM and read back once: `k_build_children` and `k_expand_score<1>` share the time; the "
-                    "fused last level is a rounding error here because the bound prunes almost everything before it.")
+                    "408,945 optimal trees; the reference's serial CPU program needs 224 s).  Seventeen tree sizes are in flight at once.  With "
+                    "eager scoring `k_build_children_eager` builds every child and scores the next taxon on its edges (costs to the header, no "
+                    "MIDPOINT sets stored); `k_select` applies the current bound to 4 bytes per (tree, edge) pair.  The fused last level is a "
+                    "rounding error here because the bound prunes almost everything before it.  Before eager scoring the same search spent 138 ms "
+                    "in `k_build_children` and 62 ms in `k_expand_score<1>` (`%s_ncu_full_k_expand_score.md`)." % R)
         write_launches("%s_launches_search_mh3.md" % R, "search_launches_mh3.csv", "%s - ncu launch list of the exact search of measure/mh3 (`fastdnamp_b200`)" % R,
                        "ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/search_launches_mh3.csv ./fastdnamp_b200 --tbr=N --seed=1 --displaynewbounds=n --displaynewtrees=n --updatesecs=0 -o out.nex mh3.phy", n3)
-    if os.path.exists(os.path.join(OUT, "prof_score_mh3.ncu-rep")):
+    if os.path.exists(os.path.join(OUT, "prof_select_mh3.ncu-rep")):
         def t3(hdr, data):
-            rd = float(data[0][hdr.index("dram__bytes_read.sum")]); ru = units_of(hdr, "dram__bytes_read.sum")
-            return ("One thread per (partial tree, edge) pair, 16 B of MIDPOINT state per pair: a launch of this size moves tens of MB, far from "
-                    "the HBM roof; what the counters above say about where the cycles go is the starting point for the next round "
-                    "(`%s_search_tuning.md` lists what was tried on this kernel and did not help).  DRAM read in this launch: %s %s." % (R, rd, ru))
-        write_full("%s_ncu_full_k_expand_score.md" % R, "prof_score_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_expand_score<1>` during the search of mh3 (launch 300)" % R,
-                   "ncu --set full --clock-control none --import-source on -k regex:k_expand_score -s 300 -c 1 -o gpurun_out/prof_score_mh3 ./fastdnamp_b200 ... mh3.phy  (scripts/gpu_check.sh ncu)", t3)
+            return ("Eight (tree, edge) pairs per thread, 4 B of cost and 4 B of tree length per pair from the tiled headers, one list "
+                    "reservation per CTA.  With one pair per thread the kernel took as long as the classic scoring pass it replaced: a CTA's "
+                    "life is a chain of latencies (bound word, header words, the reserving atomic), and the launch was limited by how many "
+                    "such chains fit on the GPU at once (`%s_search_tuning.md`)." % R)
+        write_full("%s_ncu_full_k_select.md" % R, "prof_select_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_select<8>` during the search of mh3 (launch 300)" % R,
+                   "ncu --set full --clock-control none --import-source on -k regex:k_select -s 300 -c 1 -o gpurun_out/prof_select_mh3 ./fastdnamp_b200 ... mh3.phy  (scripts/gpu_check.sh ncu)", t3)
     if os.path.exists(os.path.join(OUT, "prof_children_mh3.ncu-rep")):
         def t4(hdr, data):
             return ("One thread per (surviving insertion, 128-bit column): reads the parent's UP rows (L2 / DRAM: the lanes of a warp share a few "
-                    "parents), writes the child's UP and MIDPOINT rows and its header in whole 128-byte lines (tiled pools).  Four 128-thread CTAs "
-                    "per SM (registers), stacks in shared memory sized by the deepest tree seen.")
-        write_full("%s_ncu_full_k_build_children.md" % R, "prof_children_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_build_children` during the search of mh3 (launch 300)" % R,
+                    "parents), writes the child's UP rows, its header and -- eager scoring -- the cost of the next taxon on every edge, in whole "
+                    "128-byte lines (tiled pools).  Four 128-thread CTAs per SM (registers), stacks in shared memory sized by the deepest tree seen.  "
+                    "This is where the narrow, deep searches now live; the SASS is branchy (the walk program's selects became branches) and the "
+                    "issue slots are a quarter to a third busy: instruction count per step and exposed load latency, not bandwidth.")
+        write_full("%s_ncu_full_k_build_children.md" % R, "prof_children_mh3.ncu-rep", "%s - `ncu --set full` of `xmp::k_build_children_eager` during the search of mh3 (launch 300)" % R,
                    "ncu --set full --clock-control none --import-source on -k regex:k_build_children -s 300 -c 1 -o gpurun_out/prof_children_mh3 ./fastdnamp_b200 ... mh3.phy  (scripts/gpu_check.sh ncu)", t4)
 
     write_scaling()

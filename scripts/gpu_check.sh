@@ -36,7 +36,7 @@ PY
   CMD="$GRAFT_REPO_ROOT/fastdnamp_b200 --tbr=N --seed=1 --displaynewbounds=n --displaynewtrees=n --updatesecs=0 -o /tmp/xw/out3.nex /tmp/xw/mh3.phy"
   (cd /tmp/xw && $CMD > $GRAFT_REPO_ROOT/gpurun_out/mh3_plain.log 2>&1 &&
    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $GRAFT_REPO_ROOT/gpurun_out/search_launches_mh3.csv $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_search_mh3.log 2>&1)
-  (cd /tmp/xw && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_expand_score -s 300 -c 1 -f -o $GRAFT_REPO_ROOT/gpurun_out/prof_score_mh3 $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_score_mh3.log 2>&1)
+  (cd /tmp/xw && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_select -s 300 -c 1 -f -o $GRAFT_REPO_ROOT/gpurun_out/prof_select_mh3 $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_select_mh3.log 2>&1)
   (cd /tmp/xw && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_build_children -s 300 -c 1 -f -o $GRAFT_REPO_ROOT/gpurun_out/prof_children_mh3 $CMD > $GRAFT_REPO_ROOT/gpurun_out/ncu_children_mh3.log 2>&1)
 fi
 tail -6 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log; cat gpurun_out/bench.log | cut -c1-600; tail -3 gpurun_out/bench.err; cat gpurun_out/bench_ref.log | cut -c1-300
