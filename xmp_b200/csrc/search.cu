@@ -290,11 +290,18 @@ struct ChildWalk {
 		return k;           // merges done
 	}
 	// Step j of the child's pre-order: its program word, its UP set and its sibling's.
-	__device__ __forceinline__ void step(unsigned j, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) const {
+	// The parent's program word that step j of the child starts from (a load from the parent's header).
+	__device__ __forceinline__ unsigned word_for(unsigned j) const {
+		unsigned i = parent_index(j, sp.P);
+		if (i >= E) i = E - 1;
+		return prog[i * 32u];
+	}
+	// w = word_for(j), loaded by the caller two steps ahead: the word and the rows it leads to are two dependent
+	// loads, and with the word requested inside the step that chain sat on the critical path of every step.
+	__device__ __forceinline__ void step(unsigned j, unsigned w, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) const {
 		const unsigned P = sp.P;
 		unsigned i = parent_index(j, P);
 		if (i >= E) i = E - 1;
-		const unsigned w = prog[i * 32u];
 		const bool anc = on_path(i);
 		word = child_word(j, w, anc, sp);
 		const unsigned d = prog_depth(w);
@@ -359,11 +366,14 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		// (two steps ahead was measured and gains nothing: profiles/r01_search_tuning.md)
 		unsigned wj, first_edge = 0;
 		uint4 ux, us;
-		cw.step(0, wj, ux, us, upath, T, r0);
+		unsigned pw1 = cw.word_for(1);                      // Ec >= 5
+		cw.step(0, cw.word_for(0), wj, ux, us, upath, T, r0);
 		for (unsigned j = 0; j < Ec; ++j) {
+			const unsigned pw2 = cw.word_for(j + 2);        // clamped past the end
 			unsigned wn = wj;
 			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
+			pw1 = pw2;
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) {
@@ -443,11 +453,14 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 			const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
 			unsigned wj, first_edge = 0;
 			uint4 ux, us;
-			cw.step(0, wj, ux, us, upath, T, r0);
+			unsigned pw1 = cw.word_for(1);                  // Ec >= 5
+			cw.step(0, cw.word_for(0), wj, ux, us, upath, T, r0);
 			for (unsigned j = 0; j < Ec; ++j) {
+				const unsigned pw2 = cw.word_for(j + 2);    // clamped past the end
 				unsigned wn = wj;
 				uint4 uxn = ux, usn = us;
-				if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+				if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
+				pw1 = pw2;
 				const unsigned d = prog_depth(wj);
 				const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 				if (prog_size(wj) > 1u) {
@@ -543,11 +556,14 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
 		unsigned wj;
 		uint4 ux, us;
-		cw.step(0, wj, ux, us, upath, T, r0);
+		unsigned pw1 = cw.word_for(1);                      // Ec >= 5
+		cw.step(0, cw.word_for(0), wj, ux, us, upath, T, r0);
 		for (unsigned j = 0; j < Ec; ++j) {
+			const unsigned pw2 = cw.word_for(j + 2);        // clamped past the end
 			unsigned wn = wj;
 			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) cw.step(j + 1, wn, uxn, usn, upath, T, r0);
+			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
+			pw1 = pw2;
 			const unsigned d = prog_depth(wj);
 			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
 			if (prog_size(wj) > 1u) {
