@@ -3,20 +3,26 @@
 # list and full captures of the top kernels.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out /tmp/xw
 nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
+if [ "$2" != "nopytest" ]; then
 timeout 2400 python -m pytest tests -m gpu -q --timeout=900 -p no:cacheprovider -s > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?" >> gpurun_out/bench.err
+if [ "$2" != "nopytest" ]; then
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
-if [ "$1" = "ncu" ]; then
+fi
+if [ "$1" = "ncu" ] && [ "$2" != "nopytest" ]; then
   timeout 300 python bench.py --steps 3 --warmup 3 --kernel-only > gpurun_out/plain_ko.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 3 --warmup 3 --kernel-only > gpurun_out/ncu_launches.log 2>&1
   timeout 300 python bench.py --steps 3 --warmup 3 --kernel-only > gpurun_out/plain_ko2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_score_wide -s 3 -c 2 -f -o gpurun_out/prof_score_wide \
       python bench.py --steps 3 --warmup 3 --kernel-only > gpurun_out/ncu_full.log 2>&1
+fi
+if [ "$1" = "ncu" ]; then
   python - <<'PY'
 import gzip, json
 b = json.loads(gzip.open("tests/golden/alignments.json.gz").read())
