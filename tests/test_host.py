@@ -217,3 +217,42 @@ def test_site_pair_costs_equal_the_reference_table():
     for i, v in PB["site_pair_table_samples"].items():
         assert table[int(i) - 1] == v
     assert L.xmph_site_pair_cost(0) == -1 and L.xmph_site_pair_cost(65536) == -1
+
+
+_REF_EXE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "fastdnamp_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_partition_bound_equals_compiled_reference_on_random_alignments(tmp_path):
+    """Fuzz: random alignments with ambiguity codes, duplicated columns (weights > 1) and all three
+    strategies through the reference's own program (--onlycomputelowerbound=Y) and through host/partbound.c."""
+    import subprocess
+    rng = np.random.default_rng(20261020)
+    alphabet = np.array(list("ACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    checked = 0
+    for case in range(30):
+        n, sites = int(rng.integers(5, 13)), int(rng.integers(6, 70))
+        base = rng.integers(0, len(alphabet), (n, sites))
+        for t in range(1, n):                       # related rows, so that columns are informative
+            keep = rng.random(sites) < 0.55
+            base[t, keep] = base[rng.integers(0, t), keep]
+        cols = rng.integers(0, sites, sites + int(rng.integers(0, sites)))      # repeats give weights > 1
+        f = tmp_path / ("pb%d.phy" % case)
+        f.write_text("%d %d\n" % (n, len(cols)) + "".join("T%-9d%s\n" % (t, "".join(alphabet[base[t, cols]])) for t in range(n)))
+        letters, strategy = [("-Bp", 0), ("-BpC", 1), ("-BpL", 2), ("-Bdp", 0)][case % 4]
+        stale = [2, 1, 0][case % 3]
+        d = tmp_path / ("run%d" % case)
+        d.mkdir()
+        r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0",
+                            "--onlycomputelowerbound=Y", "--pbmaxiters=%d" % stale, letters, str(f)], cwd=d, capture_output=True, text=True)
+        if r.returncode != 0:
+            continue                                # e.g. fewer than 4 informative taxa left: nothing to compare
+        want = [[int(x) for x in l.split()] for l in (d / "restBound.txt").read_text().splitlines()[1:]]
+        opts = xh.OPT_NEXUSFMT | xh.OPT_USEPARTBOUND | (xh.OPT_USEDISTBASESBOUNDREST if "d" in letters else 0)
+        try:
+            p = xh.Problem(xh.Alignment(str(f)), options=opts, part_strategy=strategy, part_max_stale=stale)
+        except xh.HostError:
+            continue
+        assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == want, (case, letters, stale)
+        checked += 1
+    assert checked >= 20
