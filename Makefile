@@ -7,7 +7,7 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xp
 CFLAGS    := -O3 -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
 
 CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu xmp_b200/csrc/microbench.cu
-CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh include/xmp_cuda.h
+CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh xmp_b200/csrc/child_walk.cuh xmp_b200/csrc/walk_prog.h include/xmp_cuda.h
 HOST_SRCS := host/phylip.c host/prep.c host/trees.c host/partbound.c
 
 .PHONY: all host cuda cli oracle ref clean

@@ -167,6 +167,21 @@ def test_walk_program_derivation(tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
 
 
+def test_child_walk_replayed_on_the_host(tmp_path):
+    """xmp_b200/csrc/child_walk.cuh -- the per-thread child construction of the search kernels, compiled here for the
+    host -- against state sets, programs and insertion costs computed from scratch: 1-3 blocks per set, ambiguity
+    codes, weighted and weight-1 costs, eager and classic record layouts, every insertion position up to 36 taxa."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "child_walk_check")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
+                    os.path.join(os.path.dirname(os.path.abspath(__file__)), "child_walk_check.cu")], check=True)
+    for taxa, reps in (("12", "24"), ("36", "8")):
+        r = subprocess.run([exe, taxa, reps], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+
+
 # ---- partition lower bound (-Bp, reference src/partbound.c) --------------------------------------
 def _partbound_goldens():
     import json

@@ -9,6 +9,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The Fitch arithmetic below is also compiled for the host, where a "not gpu" test replays the kernels' child
+// walk (tests/child_walk_check.cu); loads through the read-only path and POPC have host stand-ins there.
+#if defined(__CUDA_ARCH__)
+#define XMP_LDG(p) __ldg(p)
+#define XMP_POPC(x) __popc(x)
+#else
+#define XMP_LDG(p) (*(p))
+#define XMP_POPC(x) ((unsigned) __builtin_popcount(x))
+#endif
+#define XMP_FHD __host__ __device__ __forceinline__
+
 namespace xmp {
 
 // Site weights, bit-sliced: plane k holds bit 3 of nibble s set iff bit k of weights[site s] is set.
@@ -23,39 +34,39 @@ struct WeightPlanes {
 };
 
 // Bit 3 of each nibble set iff that site's sets do not intersect.
-__device__ __forceinline__ unsigned empty_mask(unsigned a, unsigned b) {
+XMP_FHD unsigned empty_mask(unsigned a, unsigned b) {
 	unsigned x = a & b;
 	return ~(((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u;
 }
 
 // Preliminary Fitch set of a node from its two neighbours.
-__device__ __forceinline__ unsigned fitch_word(unsigned a, unsigned b) {
+XMP_FHD unsigned fitch_word(unsigned a, unsigned b) {
 	unsigned e = empty_mask(a, b);
 	unsigned m = (e - (e >> 3)) | e;          // 0xF where the intersection is empty
 	return (a & b) | ((a | b) & m);
 }
 
-__device__ __forceinline__ uint4 fitch_block(const uint4 &a, const uint4 &b) {
+XMP_FHD uint4 fitch_block(const uint4 &a, const uint4 &b) {
 	return make_uint4(fitch_word(a.x, b.x), fitch_word(a.y, b.y), fitch_word(a.z, b.z), fitch_word(a.w, b.w));
 }
 
-__device__ __forceinline__ unsigned cost_word_w1(unsigned a, unsigned b) {
-	return __popc(empty_mask(a, b));
+XMP_FHD unsigned cost_word_w1(unsigned a, unsigned b) {
+	return XMP_POPC(empty_mask(a, b));
 }
 
-__device__ __forceinline__ unsigned cost_word(unsigned a, unsigned b, unsigned word, const WeightPlanes &wp) {
+XMP_FHD unsigned cost_word(unsigned a, unsigned b, unsigned word, const WeightPlanes &wp) {
 	unsigned e = empty_mask(a, b);
-	if (word >= wp.heavy_words) return __popc(e);
+	if (word >= wp.heavy_words) return XMP_POPC(e);
 	unsigned s = 0;
-	for (unsigned k = 0; k < wp.n_planes; ++k) s += __popc(e & __ldg(wp.planes + (size_t) k * wp.n_words + word)) << k;
+	for (unsigned k = 0; k < wp.n_planes; ++k) s += XMP_POPC(e & XMP_LDG(wp.planes + (size_t) k * wp.n_words + word)) << k;
 	return s;
 }
 
 // Cost of one 128-bit block; `block` is its index inside the state set.
-__device__ __forceinline__ unsigned cost_block(const uint4 &a, const uint4 &b, unsigned block, const WeightPlanes &wp) {
+XMP_FHD unsigned cost_block(const uint4 &a, const uint4 &b, unsigned block, const WeightPlanes &wp) {
 	unsigned w = 4 * block;
 	if (w >= wp.heavy_words) {
-		return __popc(empty_mask(a.x, b.x)) + __popc(empty_mask(a.y, b.y)) + __popc(empty_mask(a.z, b.z)) + __popc(empty_mask(a.w, b.w));
+		return XMP_POPC(empty_mask(a.x, b.x)) + XMP_POPC(empty_mask(a.y, b.y)) + XMP_POPC(empty_mask(a.z, b.z)) + XMP_POPC(empty_mask(a.w, b.w));
 	}
 	return cost_word(a.x, b.x, w, wp) + cost_word(a.y, b.y, w + 1, wp) + cost_word(a.z, b.z, w + 2, wp) + cost_word(a.w, b.w, w + 3, wp);
 }

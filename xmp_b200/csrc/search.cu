@@ -30,48 +30,10 @@
 #include <string.h>
 #include "ctx.h"
 #include "walk_prog.h"
+#include "child_walk.cuh"
 
 namespace xmp {
 
-struct Layout {
-	unsigned n;         // taxa in the problem
-	unsigned W;         // 128-bit blocks per state set
-	unsigned NW;        // header words per node: score | insertion path (packed bytes) | walk program
-	unsigned off_prog;  // index of the first program word
-	unsigned ts_shift;  // records are tiled: 1 << ts_shift consecutive slots interleave their rows
-	unsigned trec;      // bytes per emitted tree record: score + path
-	unsigned off_cost;  // eager scoring: index of the first cost word (one per pre-order position); 0 = classic layout
-};
-// Two record layouts.  Classic: rows [MIDPOINT | UP], the scoring pass reads the MIDPOINT rows.  Eager (off_cost != 0,
-// state sets of up to 32 blocks): the kernel that builds a node also scores the NEXT taxon on each of its edges and
-// leaves the costs in the header, one word per position; MIDPOINT sets are never stored (rows = UP only, half the
-// bytes), and the scoring pass shrinks to reading 4 bytes per (tree, edge) pair and applying the current bound.
-__device__ __forceinline__ unsigned up_row0(const Layout &L, unsigned E) { return L.off_cost ? 0u : E; }
-// Header words: [0] tree length so far | [1, 1 + ceil(n/4)) insertion path, one byte per taxon (byte 0 = the
-// root's child) | [off_prog, off_prog + 2n-3) walk program (walk_prog.h), one word per pre-order position.
-#define HDR_PATH_W 1u
-
-// Both arrays of a pool are tiled so that threads working on CONSECUTIVE slots touch consecutive addresses
-// when they access the same row -- and every row is indexed by pre-order position, which all lanes of a
-// warp reach at the same step of their walks:
-//   header word w of slot s:        hdr [((s / 32) * NW + w) * 32 + s % 32]                     (128-byte lines)
-//   block c of row k of slot s:     sets[(((s / TS) * nsets + k) * TS + s % TS) * W + c]        TS = 1 << ts_shift
-// with TS * W * 16 B = one 128-byte line for narrow sets (W = 1: 8 slots, W = 2: 4, W <= 4: 2) and TS = 1,
-// i.e. plain records, from W = 5 up.  Rows of a node: MIDPOINT at [0, E), UP at [E, 2E); DOWN sets are transient.
-struct PoolView {
-	unsigned *hdr;
-	uint4 *sets;
-	unsigned nsets;           // rows per node: 2 * (2m-3), or 2m-3 with eager scoring
-	unsigned long long cap;   // slots (a multiple of 32); pools are rings: slot = index modulo cap
-};
-
-__device__ __forceinline__ unsigned *hdr_of(const PoolView &p, const Layout &L, unsigned long long slot) {
-	return p.hdr + (slot >> 5) * L.NW * 32ull + (slot & 31ull);               // word w at [w * 32]
-}
-__device__ __forceinline__ uint4 *sets_of(const PoolView &p, const Layout &L, unsigned long long slot) {
-	const unsigned ts = L.ts_shift;
-	return p.sets + ((((slot >> ts) * p.nsets) << ts) + (slot & ((1ull << ts) - 1ull))) * L.W;   // row k at [(k << ts) * W]
-}
 __device__ __forceinline__ unsigned path_byte(const unsigned *h, unsigned t) {
 	return (h[(HDR_PATH_W + (t >> 2)) * 32u] >> (8u * (t & 3u))) & 0xFFu;
 }
@@ -235,93 +197,6 @@ k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned
 		++slot;
 	}
 }
-
-// ---- walking a child tree ----------------------------------------------------------------------------
-// The child of parent node N obtained by inserting the next taxon on the edge at position P, visited in
-// pre-order without ever materialising its topology: step j of the child is step j (before P) or j - 2 (after)
-// of the parent's walk program with three spliced steps at P (walk_prog.h) -- selects, the same trip count
-// for every lane of a level, and every lane is at the same position j at the same time.
-//
-// Per-lane state with dynamic indexing lives in shared memory, element k of thread t at [k * blockDim.x + t]
-// (16-byte accesses are then bank-conflict free whatever k each lane uses; local memory would serialise
-// into one wavefront per distinct index):
-//   upath[k]   UP sets recomputed along the root path: k = 0 the new internal node, k = dv - d the ancestor at
-//              depth d; every other UP set is the parent tree's, read from its record (L1 hits: the lanes of a
-//              warp share a handful of parents);
-//   dstack[d]  DOWN set of the current ancestor at depth d.
-struct ChildWalk {
-	const unsigned *prog;         // parent's program: word i at prog[i * 32]
-	const uint4 *PU;              // parent's UP rows for this lane's column: row i at PU[i * rs]
-	unsigned rs, E;
-	Splice sp;
-	unsigned on0, on1, on2, on3, on4, on5, on6;   // parent positions that are proper ancestors of P (positions < 224)
-	uint4 rt;
-
-	__device__ __forceinline__ bool on_path(unsigned e) const {
-		const unsigned w = e < 96 ? (e < 32 ? on0 : (e < 64 ? on1 : on2)) : (e < 160 ? (e < 128 ? on3 : on4) : (e < 192 ? on5 : on6));
-		return (w >> (e & 31u)) & 1u;
-	}
-	__device__ __forceinline__ void mark(unsigned e) {
-		const unsigned bit = 1u << (e & 31u);
-		if (e < 32) on0 |= bit; else if (e < 64) on1 |= bit; else if (e < 96) on2 |= bit; else if (e < 128) on3 |= bit;
-		else if (e < 160) on4 |= bit; else if (e < 192) on5 |= bit; else on6 |= bit;
-	}
-	// Decodes the insertion at position P of the parent and recomputes UP along the root path.
-	__device__ __forceinline__ unsigned init(const unsigned *ph, const Layout &L, unsigned m, unsigned P, const uint4 *parent_up,
-	                                         const uint4 &row_new, uint4 *upath, unsigned T, unsigned D, bool &overflow) {
-		prog = ph + L.off_prog * 32u;
-		PU = parent_up;
-		rs = L.W << L.ts_shift;
-		E = 2 * m - 3;
-		rt = row_new;
-		sp = make_splice(P, prog[P * 32u], E);
-		on0 = on1 = on2 = on3 = on4 = on5 = on6 = 0;
-		uint4 u = fitch_block(rt, __ldg(PU + (size_t) P * rs));
-		upath[0] = u;
-		unsigned k = 1, cur = P, other = sp.sv;
-		for (unsigned depth = sp.dv; depth > 0; --depth) {
-			u = fitch_block(u, __ldg(PU + (size_t) other * rs));     // `other` hangs off the path: unchanged
-			if (k < D) upath[(size_t) k * T] = u; else overflow = true;
-			cur = parent_pos(cur, other);
-			mark(cur);
-			other = prog_sib(prog[cur * 32u]);
-			++k;
-		}
-		return k;           // merges done
-	}
-	// Step j of the child's pre-order: its program word, its UP set and its sibling's.
-	// The parent's program word that step j of the child starts from (a load from the parent's header).
-	__device__ __forceinline__ unsigned word_for(unsigned j) const {
-		unsigned i = parent_index(j, sp.P);
-		if (i >= E) i = E - 1;
-		return prog[i * 32u];
-	}
-	// w = word_for(j), loaded by the caller two steps ahead: the word and the rows it leads to are two dependent
-	// loads, and with the word requested inside the step that chain sat on the critical path of every step.
-	__device__ __forceinline__ void step(unsigned j, unsigned w, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) const {
-		const unsigned P = sp.P;
-		unsigned i = parent_index(j, P);
-		if (i >= E) i = E - 1;
-		const bool anc = on_path(i);
-		word = child_word(j, w, anc, sp);
-		const unsigned d = prog_depth(w);
-		// where the two UP sets come from: 0 = the parent's record (row), 1 = upath[k], 2 = the new taxon's row, 3 = none
-		unsigned src_u = anc ? 1u : 0u, row_u = i, k_u = sp.dv - d;
-		unsigned s = prog_sib(w);
-		unsigned src_s = 0u, row_s = s, k_s = sp.dv - d;
-		if (s == XMP_NO_POS) src_s = 3u;
-		else if (s == P) { src_s = 1u; k_s = 0u; }              // the sibling was the insertion edge: now the new internal node
-		else if (on_path(s)) src_s = 1u;
-		if (j == P) {
-			src_u = 1u; k_u = 0u;
-			row_s = sp.sv; src_s = sp.sv == XMP_NO_POS ? 3u : 0u;
-		}
-		if (j == P + 1u) { src_u = 2u; src_s = 0u; row_s = P; }
-		if (j == P + 2u) { src_u = 0u; row_u = P; src_s = 2u; }
-		ux = src_u == 0u ? __ldg(PU + (size_t) row_u * rs) : (src_u == 1u ? upath[(size_t) k_u * T] : rt);
-		us = src_s == 0u ? __ldg(PU + (size_t) row_s * rs) : (src_s == 1u ? upath[(size_t) k_s * T] : (src_s == 2u ? rt : r0));
-	}
-};
 
 // ---- child construction ------------------------------------------------------------------------------
 // One thread per (survivor, 128-bit column): at step j the UP and MIDPOINT sets of the child's position j go
