@@ -90,13 +90,19 @@ struct ChildWalk {
 		on0 = on1 = on2 = on3 = on4 = on5 = on6 = 0;
 		uint4 u = fitch_block(rt, XMP_LDG(PU + (size_t) P * rs));
 		upath[0] = u;
+		// Up the root path.  The set hanging off the path at each level is requested one level ahead: the chain
+		// of dependent loads is then the program words alone (mostly L1 hits: a warp shares a few parents), not
+		// program word -> row -> program word -> row.
 		unsigned k = 1, cur = P, other = sp.sv;
+		uint4 off = sp.dv > 0 ? XMP_LDG(PU + (size_t) other * rs) : rt;       // `other` hangs off the path: unchanged
 		for (unsigned depth = sp.dv; depth > 0; --depth) {
-			u = fitch_block(u, XMP_LDG(PU + (size_t) other * rs));     // `other` hangs off the path: unchanged
-			if (k < D) upath[(size_t) k * T] = u; else overflow = true;
 			cur = parent_pos(cur, other);
 			mark(cur);
 			other = prog_sib(prog[cur * 32u]);
+			const uint4 off_next = depth > 1 ? XMP_LDG(PU + (size_t) other * rs) : rt;
+			u = fitch_block(u, off);
+			if (k < D) upath[(size_t) k * T] = u; else overflow = true;
+			off = off_next;
 			++k;
 		}
 		return k;           // merges done
@@ -114,7 +120,7 @@ struct ChildWalk {
 		const unsigned P = sp.P;
 		unsigned i = parent_index(j, P);
 		if (i >= E) i = E - 1;
-		const bool anc = on_path(i);
+		const bool anc = i < P && i + prog_size(w) > P;          // proper ancestor of P: its subtree [i, i + size) holds P
 		word = child_word(j, w, anc, sp);
 		const unsigned d = prog_depth(w);
 		// where the two UP sets come from: 0 = the parent's record (row), 1 = upath[k], 2 = the new taxon's row, 3 = none
