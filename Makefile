@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --use_fast_math
-CFLAGS    := -O3 -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
+CFLAGS    := -O3 -mpopcnt -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
 
 CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu xmp_b200/csrc/microbench.cu
 CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh xmp_b200/csrc/child_walk.cuh xmp_b200/csrc/walk_prog.h include/xmp_cuda.h
