@@ -95,6 +95,21 @@ def test_oracle_search_reproduces_reference_output(alignment_dir, goldens, name)
     assert body.encode() in golden_output(name)
 
 
+def test_oracle_search_under_the_partition_bound_with_a_tree_cap(alignment_dir, goldens):
+    """53humans.24 -Bp -m 1000: restBound[] from host/partbound.c drives the oracle search through exactly the
+    reference's nodes (same counters), 1,403,325 optimal trees are counted, and the first 1000 in depth-first
+    order are the ones the reference kept (src/yanbader.c:272-293) -- its result file byte for byte."""
+    g = goldens["53humans.24"]
+    a, p = prepare(alignment_dir, goldens, "53humans.24")
+    assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
+    score, n, trees, nodes, calls = ol.search(p, max_trees=1000)
+    assert (score, n, len(trees)) == (g["score"], 1403325, 1000)
+    assert nodes == g["ref_bandb_nodes"] and calls + 2 == g["ref_score_calls"]
+    assert sorted(canonical_newick(t) for t in trees) == golden_trees("53humans.24")
+    body = "".join("\tTREE FASTDNAMP_%d = [&U] %s\n" % (i + 1, t) for i, t in enumerate(trees))
+    assert body.encode() in golden_output("53humans.24")
+
+
 def test_mt10_golden_is_the_reference_repo_file(goldens):
     """tests/golden/trees/mt-10.out.gz equals reference build-vswin32/mt-10.tre (CRLF stripped); the sha
     below was taken from that file when the fixture was generated."""
