@@ -7,20 +7,24 @@
 // child tree's UP / DOWN / MIDPOINT sets and recurse; complete trees lower the bound and are recorded
 // (:195-213).  Here the same search tree is explored a batch of partial trees at a time:
 //
-//   k_expand_score      every (partial tree, edge) pair of the batch in one launch: weighted Fitch cost
-//                       (AND / empty-nibble mask / POPC), group-shuffle reduction, the reference's signed
-//                       acceptance test, ballot compaction of survivors (one counter atomic per CTA); on
-//                       the last level survivors are complete trees: atomicMin on the bound, a tree record.
-//   k_build_children    one thread per (survivor, 128-bit column): walks the child in pre-order through the
-//                       parent's walk program with the insertion spliced in, recomputes UP along the root
-//                       path and DOWN / MIDPOINT everywhere, writes the child's record and header.
+//   k_build_children_eager  one thread per (survivor, 128-bit column): walks the child in pre-order through the
+//                       parent's walk program with the insertion spliced in (child_walk.cuh), recomputes UP along
+//                       the root path and DOWN / MIDPOINT everywhere, scores the NEXT taxon on every MIDPOINT
+//                       (AND / empty-nibble mask / POPC) and writes the child's UP rows, header, program and costs.
+//   k_select            every (partial tree, edge) pair of a batch, 8 per thread: cost and length from the headers,
+//                       the reference's signed acceptance test against the current bound, one survivor-list
+//                       reservation per CTA; on the last level survivors are complete trees: atomicMin on the
+//                       bound, a tree record.
 //   k_expand_last_fused the same walk for parents with n-2 taxa, but each MIDPOINT is scored against the
 //                       last taxon on the spot: the deepest level is never stored.
+//   k_expand_score / k_build_children   the classic pair for state sets wider than 32 blocks: MIDPOINT rows are
+//                       stored by the builder and scored by a separate pass (group-shuffle reduction per pair).
 //
 // Frontier layout in HBM: one ring-buffer pool per tree size m.  A node is a header (length, insertion
-// path, byte arrays over edge ids, walk program) plus a record of 2 * (2m-3) state sets laid out
-// [MIDPOINT | UP][edge][block] (DOWN sets are transient), so the scoring kernel streams a contiguous
-// MIDPOINT array per node.  The scheduler (run_sweep) expands every level that holds a worthwhile batch in
+// path, walk program, and -- eager layout -- the insertion cost of the next taxon per position) plus a record
+// of state-set rows indexed by pre-order position: [UP] (eager) or [MIDPOINT | UP] (classic); DOWN sets are
+// transient.  Headers and rows are tiled so that a warp whose lanes work on different nodes at the same position
+// touches whole 128-byte lines.  The scheduler (run_sweep) expands every level that holds a worthwhile batch in
 // one pass, deepest first, with a single host synchronisation per pass; pool capacities bound the memory.
 //
 // Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
