@@ -271,3 +271,68 @@ def test_partition_bound_equals_compiled_reference_on_random_alignments(tmp_path
         assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == want, (case, letters, stale)
         checked += 1
     assert checked >= 20
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_preprocessing_equals_compiled_reference_on_random_alignments(tmp_path):
+    """Fuzz of everything before the search: random alignments (ambiguity codes, gaps, repeated and constant
+    columns, few to many taxa) and random settings (-d, --startcol / --endcol, -Bd / -Bm / -Bdm) through the
+    reference's own program and through host/prep.c: site counts, constant weight, taxon order, MST upper bound
+    and restBound[] must agree."""
+    import re
+    import subprocess
+    zinit = _REF_EXE + "_zinit"          # -Bm reads an uninitialised local in the reference (SURVEY F4)
+    rng = np.random.default_rng(424242)
+    alphabet = np.array(list("ACGTACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    checked = 0
+    for case in range(48):
+        n, sites = int(rng.integers(4, 18)), int(rng.integers(4, 70))
+        base = rng.integers(0, len(alphabet), (n, sites))
+        for t in range(1, n):
+            keep = rng.random(sites) < rng.uniform(0.3, 0.95)
+            base[t, keep] = base[rng.integers(0, t), keep]
+        cols = rng.integers(0, sites, sites + int(rng.integers(0, sites)))
+        f = tmp_path / ("pre%d.phy" % case)
+        f.write_text("%d %d\n" % (n, len(cols)) + "".join("T%-9d%s\n" % (t, "".join(alphabet[base[t, cols]])) for t in range(n)))
+        letters = ["d", "m", "dm"][case % 3]
+        flags, opts, kw = ["-B" + letters], xh.OPT_NEXUSFMT | xh.OPT_IMPROVEINITUPPERBOUND, {}
+        opts |= (xh.OPT_USEDISTBASESBOUNDREST if "d" in letters else 0) | (xh.OPT_USEMSTBOUNDREST if "m" in letters else 0)
+        if case % 4 == 1:
+            flags.append("-d")
+            opts |= xh.OPT_DISCARDMISSAMBIG
+        if case % 5 == 2:
+            lo, hi = sorted(int(x) for x in rng.integers(1, len(cols) + 1, 2))
+            flags += ["--startcol=%d" % lo, "--endcol=%d" % (hi + 1)]
+            kw = {"start_col": lo - 1, "end_col": hi}
+        d = tmp_path / ("pre_run%d" % case)
+        d.mkdir()
+        # no reordered.phy with -d: when every site is discarded the reference writes gigabytes of garbage there
+        save = [] if "-d" in flags else ["--savereordereddataset=Y"]
+        r = subprocess.run([zinit if "m" in letters and os.path.exists(zinit) else _REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=Y",
+                            "--displaynewtrees=n", "--updatesecs=0", "--onlycomputelowerbound=Y"] + save + flags + [str(f)],
+                           cwd=d, capture_output=True, text=True, timeout=60)
+        try:
+            p = xh.Problem(xh.Alignment(str(f)), options=opts, **kw)
+        except xh.HostError:
+            assert r.returncode != 0, (case, flags)           # both refuse (e.g. nothing informative left)
+            continue
+        if r.returncode != 0:
+            continue
+        if p.num_sites + p.n_constant_sites + p.n_nonpi_sites == 0:
+            continue          # -d discarded every site: the reference then reads uninitialised weights (garbage site counts)
+        e = r.stderr
+        assert p.n_constant_sites == int(re.search(r"(\d+) constant sites", e).group(1)), (case, flags)
+        assert p.n_nonpi_sites == int(re.search(r"(\d+) non-parsimoniously-informative sites", e).group(1)), (case, flags)
+        assert p.constant_weight == int(re.search(r"having a total weight of (\d+)", e).group(1)), (case, flags)
+        assert p.num_sites == int(re.search(r"(\d+) parsimoniously-informative sites", e).group(1)), (case, flags)
+        mm = re.search(r"Improving initial upper bound to (\d+)", e)
+        if mm:
+            assert p.mst_upper_bound == int(mm.group(1)), (case, flags)
+        rp = d / "reordered.phy"
+        if rp.exists():
+            order = [int(l[1:10]) for l in rp.read_text().splitlines()[1:] if l.startswith("T")]
+            assert [int(t) + 1 for t in p.taxon_map] == order, (case, flags)
+        want = [[int(x) for x in l.split()] for l in (d / "restBound.txt").read_text().splitlines()[1:]]
+        assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == want, (case, flags)
+        checked += 1
+    assert checked >= 30
