@@ -125,3 +125,46 @@ def test_too_low_bound_finds_nothing(alignment_dir, goldens):
     a, p = prepare(alignment_dir, goldens, "its10")
     score, n, trees, _, _ = ol.search(p, bound=goldens["its10"]["score"] - 1)
     assert n == 0 and trees == [] and score == goldens["its10"]["score"] - 1
+
+
+_REF_EXE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "fastdnamp_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_search_equals_compiled_reference_on_random_alignments(tmp_path):
+    """Fuzz of the whole pipeline on small random alignments (ambiguity codes, repeated columns): the
+    reference's own program (raw Newick output, MEASURE counters) against host preprocessing + oracle search:
+    same length, same trees in the same order, same number of BranchAndBound() and FitchScore() calls."""
+    import re
+    import subprocess
+    from xmp_b200 import hostlib as xh
+    rng = np.random.default_rng(777)
+    alphabet = np.array(list("ACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    checked = 0
+    for case in range(24):
+        n, sites = int(rng.integers(4, 10)), int(rng.integers(6, 50))
+        base = rng.integers(0, len(alphabet), (n, sites))
+        for t in range(1, n):
+            keep = rng.random(sites) < 0.6
+            base[t, keep] = base[rng.integers(0, t), keep]
+        cols = rng.integers(0, sites, sites * 2)
+        f = tmp_path / ("fz%d.phy" % case)
+        f.write_text("%d %d\n" % (n, len(cols)) + "".join("T%-9d%s\n" % (t, "".join(alphabet[base[t, cols]])) for t in range(n)))
+        d = tmp_path / ("fz_run%d" % case)
+        d.mkdir()
+        r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0", "-r",
+                            "-o", "out.tre", str(f)], cwd=d, capture_output=True, text=True, timeout=120)
+        try:
+            p = xh.Problem(xh.Alignment(str(f)))          # default settings, like the reference run: -Bd, MST upper bound
+        except xh.HostError:
+            continue
+        if r.returncode != 0 or p.num_sites == 0:
+            continue
+        want = (d / "out.tre").read_text().split()
+        score, n_trees, trees, nodes, calls = ol.search(p)
+        assert trees == want, case
+        assert n_trees == len(want), case
+        assert nodes == int(re.search(r"BranchAndBound\(\) executed\s+(\d+)", r.stderr).group(1)), case
+        assert calls + 2 == int(re.search(r"ScoreFitch\(\) executed\s+(\d+)", r.stderr).group(1)), case
+        checked += 1
+    assert checked >= 15
