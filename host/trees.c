@@ -188,6 +188,33 @@ void xmph_sort_paths_dfs(unsigned char *paths, size_t n, unsigned num_taxa) {
 	free(keys); free(sorted); free(idx); free(tmp);
 }
 
+typedef struct {
+	const unsigned char *paths; const unsigned *taxon_map; unsigned num_taxa; int nexus;
+	size_t first, count, len;
+	char *buf;
+} fmt_job;
+
+static void *fmt_thread(void *x) {
+	fmt_job *j = (fmt_job *) x;
+	char *o = j->buf;
+	for (size_t k = j->first; k < j->first + j->count; ++k) {
+		if (j->nexus) {
+			memcpy(o, "\tTREE FASTDNAMP_", 16); o += 16;
+			size_t v = k + 1;
+			char digits[24];
+			int nd = 0;
+			do { digits[nd++] = (char) ('0' + v % 10); v /= 10; } while (v);
+			while (nd) *o++ = digits[--nd];
+			memcpy(o, " = [&U] ", 8); o += 8;
+		}
+		o += xmph_path_to_newick(j->paths + k * j->num_taxa, j->num_taxa, j->taxon_map, o);
+		*o++ = ';';
+		*o++ = '\n';
+	}
+	j->len = (size_t) (o - j->buf);
+	return NULL;
+}
+
 int xmph_write_trees(FILE *out, int nexus, unsigned score, const xmph_alignment *a, const unsigned *taxon_map,
                      const unsigned char *paths, size_t n_trees) {
 	char *buf = (char *) malloc(16 * (size_t) a->num_taxa + 16);
@@ -202,11 +229,44 @@ int xmph_write_trees(FILE *out, int nexus, unsigned score, const xmph_alignment 
 			fprintf(out, "\t\t%u\t%s%c\n", i + 1, a->labels[i], i + 1 < a->num_taxa ? ',' : ';');
 		}
 	}
-	for (size_t k = 0; k < n_trees; ++k) {
-		size_t n = xmph_path_to_newick(paths + k * a->num_taxa, a->num_taxa, taxon_map, buf);
-		if (nexus) fprintf(out, "\tTREE FASTDNAMP_%zu = [&U] ", k + 1);
-		fwrite(buf, 1, n, out);
-		fputs(";\n", out);
+	(void) buf;
+	/* tree lines: formatted a block of trees per thread into memory, written out in order */
+	{
+		enum { BLOCK = 16384 };
+		long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		unsigned threads = cores > 0 ? (unsigned) cores : 1;
+		if (threads > 32) threads = 32;
+		if (n_trees < 4 * BLOCK) threads = 1;
+		const size_t line_max = 16 * (size_t) a->num_taxa + 64;
+		fmt_job jobs[32];
+		pthread_t th[32];
+		int failed = 0;
+		for (unsigned t = 0; t < threads; ++t) {
+			jobs[t].buf = (char *) malloc(BLOCK * line_max);
+			if (!jobs[t].buf) failed = 1;
+		}
+		for (size_t base = 0; base < n_trees && !failed; base += (size_t) threads * BLOCK) {
+			unsigned used = 0;
+			for (unsigned t = 0; t < threads; ++t) {
+				const size_t first = base + (size_t) t * BLOCK;
+				if (first >= n_trees) break;
+				jobs[t].paths = paths; jobs[t].taxon_map = taxon_map; jobs[t].num_taxa = a->num_taxa; jobs[t].nexus = nexus;
+				jobs[t].first = first;
+				jobs[t].count = n_trees - first < BLOCK ? n_trees - first : BLOCK;
+				++used;
+			}
+			unsigned started = 0;
+			for (unsigned t = 1; t < used; ++t) {
+				if (pthread_create(&th[t], NULL, fmt_thread, &jobs[t])) break;
+				started = t;
+			}
+			fmt_thread(&jobs[0]);
+			for (unsigned t = started + 1; t < used; ++t) fmt_thread(&jobs[t]);      /* threads that could not be started */
+			for (unsigned t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+			for (unsigned t = 0; t < used; ++t) fwrite(jobs[t].buf, 1, jobs[t].len, out);
+		}
+		for (unsigned t = 0; t < threads; ++t) free(jobs[t].buf);
+		if (failed) { free(buf); return xmph_fail("Out of memory while writing result trees."); }
 	}
 	if (nexus) fprintf(out, "END;\n");
 	free(buf);

@@ -336,3 +336,45 @@ def test_preprocessing_equals_compiled_reference_on_random_alignments(tmp_path):
         assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == want, (case, flags)
         checked += 1
     assert checked >= 30
+
+
+def test_large_tree_sets_sort_and_write_like_small_ones(alignment_dir, goldens, tmp_path):
+    """The multi-threaded paths of host/trees.c (depth-first sort by radix, block-wise formatting), used from
+    ~20,000 / 65,536 trees up, against the plain ones: same order as sorting the DFS keys, same bytes as writing
+    the set in small pieces, NEXUS numbering intact."""
+    import ctypes as C
+    from tests import oracle_lib as ol
+    a, p = prepare(alignment_dir, goldens, "mh3")
+    n, N = p.num_taxa, 100_000
+    rng = np.random.default_rng(11)
+    paths = ol.random_paths(rng, N, n)
+    paths = np.concatenate([paths, paths[:5000]])                       # duplicates keep their multiplicity
+    ordered = p.sort_paths_dfs(paths)
+    keys = [bytes(xh.path_to_dfs(x, n)) for x in ordered[::37]]
+    assert keys == sorted(keys)
+    assert sorted(map(bytes, ordered)) == sorted(map(bytes, paths))
+    small = p.sort_paths_dfs(paths[:3000])                              # single-threaded path
+    assert [bytes(xh.path_to_dfs(x, n)) for x in small] == sorted(bytes(xh.path_to_dfs(x, n)) for x in paths[:3000])
+
+    L = xh.lib()
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    L.xmph_write_trees.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    tm = np.ascontiguousarray(p.taxon_map, dtype=np.uint32)
+
+    def write(arr, nexus):
+        arr = np.ascontiguousarray(arr)
+        f = libc.fopen(str(tmp_path / "w.out").encode(), b"w")
+        assert L.xmph_write_trees(f, nexus, 118, C.byref(a._a), tm.ctypes.data, arr.ctypes.data, len(arr)) == 0
+        libc.fclose(f)
+        return (tmp_path / "w.out").read_bytes()
+
+    whole = write(ordered, 0)
+    assert whole == b"".join(write(ordered[i:i + 9000], 0) for i in range(0, len(ordered), 9000))
+    assert whole.split(b"\n")[4321].decode() == p.path_to_newick(ordered[4321]) + ";"
+    nx = write(ordered, 1).split(b"\n")
+    first = nx.index(b"\tTREE FASTDNAMP_1 = [&U] " + p.path_to_newick(ordered[0]).encode() + b";")
+    assert nx[first + 77776].decode() == "\tTREE FASTDNAMP_77777 = [&U] " + p.path_to_newick(ordered[77776]) + ";"
+    assert nx[first + len(ordered)] == b"END;"
