@@ -138,6 +138,16 @@ def run_one(name):
             "ref_bandb_seconds": float(re.search(r"Time to perform branch and bound search:\s+([\d.]+)s", err).group(1)),
             "ref_wall_seconds": round(wall, 2),
         }
+        if "-m" in extra:
+            # the cap hides how many optimal trees there are: count them in a second run without it
+            uncapped = [f for i, f in enumerate(extra) if f != "-m" and (i == 0 or extra[i - 1] != "-m")]
+            out2 = os.path.join(cwd, "all.tre")
+            t0 = time.time()
+            p2 = subprocess.run([exe] + COMMON + uncapped + ["-r", "-o", out2, src], cwd=cwd, capture_output=True, text=True)
+            if p2.returncode == 0:
+                with open(out2, "rb") as fh:
+                    rec["num_trees_total"] = sum(1 for _ in fh)
+                rec["ref_bandb_seconds_uncapped"] = float(re.search(r"Time to perform branch and bound search:\s+([\d.]+)s", p2.stderr).group(1))
         if len(trees) <= SMALL_SET:
             os.makedirs(os.path.join(HERE, "trees"), exist_ok=True)
             with gzip.GzipFile(os.path.join(HERE, "trees", name + ".txt.gz"), "wb", mtime=0) as f:

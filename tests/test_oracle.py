@@ -103,7 +103,7 @@ def test_oracle_search_under_the_partition_bound_with_a_tree_cap(alignment_dir, 
     a, p = prepare(alignment_dir, goldens, "53humans.24")
     assert [[i, int(p.rest_bound[i])] for i in range(2, p.num_taxa)] == g["rest_bound"]
     score, n, trees, nodes, calls = ol.search(p, max_trees=1000)
-    assert (score, n, len(trees)) == (g["score"], 1403325, 1000)
+    assert (score, n, len(trees)) == (g["score"], g["num_trees_total"], 1000) and n == 1403325
     assert nodes == g["ref_bandb_nodes"] and calls + 2 == g["ref_score_calls"]
     assert sorted(canonical_newick(t) for t in trees) == golden_trees("53humans.24")
     body = "".join("\tTREE FASTDNAMP_%d = [&U] %s\n" % (i + 1, t) for i, t in enumerate(trees))
