@@ -8,8 +8,10 @@
  * and hands subtree jobs to idle GPUs.  Two options are new: --gpus=<n> and --membudget=<MiB>.
  *
  * Not built in (the reference computes them on the CPU before the search; see DESIGN.md "Out of
- * scope"): the -Bi/-Bk/-BK/-Bh/-Bp lower bounds (load their restBound.txt with -Bf <file>) and the TBR
- * heuristic (--tbr is accepted and ignored: a greedy beam dive on the device seeds the bound instead).
+ * scope"): the -Bi/-Bk/-BK/-Bh lower bounds (load their restBound.txt with -Bf <file>).  --tbr is
+ * accepted: in the reference it lowers the bound to the greedy stepwise-addition tree's length and
+ * discards the TBR result (src/common.c:2608-2632, src/greedytree.c:92-100); here a greedy beam dive
+ * on the device seeds the bound, whatever --tbr says.
  */
 #include <limits.h>
 #include <pthread.h>
