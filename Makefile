@@ -10,8 +10,8 @@ CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.
 CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh xmp_b200/csrc/child_walk.cuh xmp_b200/csrc/walk_prog.h include/xmp_cuda.h
 HOST_SRCS := host/phylip.c host/prep.c host/trees.c host/partbound.c
 
-.PHONY: all host cuda cli oracle ref clean
-all: host cuda cli oracle
+.PHONY: all host cuda cli oracle ref checks clean
+all: host cuda cli oracle checks
 
 host: host/libxmp_host.so
 host/libxmp_host.so: $(HOST_SRCS) host/xmp_host.h
@@ -28,9 +28,15 @@ fastdnamp_b200: host/fastdnamp.c host/libxmp_host.so xmp_b200/libxmp_b200.so
 
 oracle:
 	$(MAKE) -C oracle oracle
+
+# stand-alone GPU check programs (test infrastructure: they link the oracle as the checker)
+checks: tests/sweep_m_check
+tests/sweep_m_check: tests/sweep_m_check.cu xmp_b200/libxmp_b200.so include/xmp_cuda.h | oracle
+	$(NVCC) -O2 -std=c++17 $(ARCH) -Iinclude -o $@ tests/sweep_m_check.cu -Lxmp_b200 -lxmp_b200 -Loracle -loracle \
+	  -Xlinker -rpath,'$$ORIGIN/../xmp_b200' -Xlinker -rpath,'$$ORIGIN/../oracle'
 ref:
 	$(MAKE) -C oracle ref
 
 clean:
-	rm -f host/libxmp_host.so xmp_b200/libxmp_b200.so fastdnamp_b200 xmp_b200/csrc/ptxas.log
+	rm -f host/libxmp_host.so xmp_b200/libxmp_b200.so fastdnamp_b200 xmp_b200/csrc/ptxas.log tests/sweep_m_check
 	$(MAKE) -C oracle clean

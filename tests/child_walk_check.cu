@@ -177,21 +177,26 @@ int main(int argc, char **argv) {
 					const uint4 r0 = rows[col], rt = rows[(size_t) m * W + col], rn = rows[(size_t) (m + 1) * W + col];
 					bool overflow = false;
 					ChildWalk cw;
-					cw.init(ph, L, m, P, PU, rt, upath.data(), T, D, overflow);
+					// eager layout: the root-path UP sets live in the child's own rows (tiled like a pool's), as in the kernel
+					std::vector<uint4> crows((size_t) Ec * ((size_t) W << L.ts_shift) + 64);
+					uint4 *CU = eager ? crows.data() + col : nullptr;
+					uint4 *up_arg = eager ? nullptr : upath.data();
+					cw.init(ph, L, m, P, PU, rt, up_arg, T, D, overflow, CU);
 					unsigned wj, pw1 = cw.word_for(1);
 					uint4 ux, us;
-					cw.step(0, cw.word_for(0), wj, ux, us, upath.data(), T, r0);
+					cw.step(0, cw.word_for(0), wj, ux, us, up_arg, T, r0);
 					for (unsigned j = 0; j < Ec; ++j) {
 						const unsigned pw2 = cw.word_for(j + 2);
 						unsigned wn = wj;
 						uint4 uxn = ux, usn = us;
-						if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath.data(), T, r0);
+						if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, up_arg, T, r0);
 						pw1 = pw2;
 						const unsigned d = prog_depth(wj);
 						const uint4 dn = d == 0 ? r0 : fitch_block(dstack[d - 1], us);
 						if (prog_size(wj) > 1u) {
 							if (d < D) dstack[d] = dn; else overflow = true;
 						}
+						if (CU) CU[(size_t) j * ((size_t) W << L.ts_shift)] = ux;
 						const uint4 m_j = fitch_block(ux, dn);
 						cost[j] += cost_block(m_j, rn, col, wp);
 						// --- checks ---

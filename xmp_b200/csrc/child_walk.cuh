@@ -59,37 +59,43 @@ XMP_HD uint4 *sets_of(const PoolView &p, const Layout &L, unsigned long long slo
 // into one wavefront per distinct index):
 //   upath[k]   UP sets recomputed along the root path: k = 0 the new internal node, k = dv - d the ancestor at
 //              depth d; every other UP set is the parent tree's, read from its record (L1 hits: the lanes of a
-//              warp share a handful of parents);
+//              warp share a handful of parents).  A kernel that writes the child's UP rows anyway (the eager
+//              builder) keeps these sets in the child's record instead (ChildWalk::gup) and has no upath[];
 //   dstack[d]  DOWN set of the current ancestor at depth d.
 struct ChildWalk {
 	const unsigned *prog;         // parent's program: word i at prog[i * 32]
 	const uint4 *PU;              // parent's UP rows for this lane's column: row i at PU[i * rs]
 	unsigned rs, E;
 	Splice sp;
-	unsigned on0, on1, on2, on3, on4, on5, on6;   // parent positions that are proper ancestors of P (positions < 224)
+	// "Is my sibling P or an ancestor of P?" without a table: in pre-order the ancestors a_0 .. a_{dv-1} of P come
+	// first at their depths, so before the walk leaves P's subtree the latest node seen at depth e is an ancestor iff
+	// e < (ancestors seen so far); afterwards the off-path siblings come back up with strictly decreasing depth.
+	// lim = number of depths whose latest node is still an ancestor of P.  A node at depth d hangs off the root path
+	// (its sibling is P or an ancestor, whose recomputed UP set sits in upath[dv - d]) iff it is no ancestor itself
+	// and d <= lim; then lim = d (ancestor: lim = d + 1).
+	unsigned lim;
 	uint4 rt;
+	// Where the UP sets recomputed along the root path live.  nullptr: the shared-memory stack upath[].  Otherwise the
+	// child's own UP rows in its record (row = pre-order position, stride rs): init() writes the ancestors' rows there
+	// (an ancestor keeps its position, the new internal node sits at P), step() reads them back by position with plain
+	// loads -- a thread sees its own earlier stores -- and the per-thread stack, half of the walk's shared memory, goes.
+	uint4 *gup;
 
-	XMP_HD bool on_path(unsigned e) const {
-		const unsigned w = e < 96 ? (e < 32 ? on0 : (e < 64 ? on1 : on2)) : (e < 160 ? (e < 128 ? on3 : on4) : (e < 192 ? on5 : on6));
-		return (w >> (e & 31u)) & 1u;
-	}
-	XMP_HD void mark(unsigned e) {
-		const unsigned bit = 1u << (e & 31u);
-		if (e < 32) on0 |= bit; else if (e < 64) on1 |= bit; else if (e < 96) on2 |= bit; else if (e < 128) on3 |= bit;
-		else if (e < 160) on4 |= bit; else if (e < 192) on5 |= bit; else on6 |= bit;
-	}
 	// Decodes the insertion at position P of the parent and recomputes UP along the root path.
 	XMP_HD unsigned init(const unsigned *ph, const Layout &L, unsigned m, unsigned P, const uint4 *parent_up,
-	                                         const uint4 &row_new, uint4 *upath, unsigned T, unsigned D, bool &overflow) {
+	                                         const uint4 &row_new, uint4 *upath, unsigned T, unsigned D, bool &overflow,
+	                                         uint4 *child_rows = nullptr) {
 		prog = ph + L.off_prog * 32u;
 		PU = parent_up;
 		rs = L.W << L.ts_shift;
 		E = 2 * m - 3;
 		rt = row_new;
 		sp = make_splice(P, prog[P * 32u], E);
-		on0 = on1 = on2 = on3 = on4 = on5 = on6 = 0;
+		lim = 0;
 		uint4 u = fitch_block(rt, XMP_LDG(PU + (size_t) P * rs));
-		upath[0] = u;
+		gup = child_rows;
+		if (gup) gup[(size_t) P * rs] = u;
+		else upath[0] = u;
 		// Up the root path.  The set hanging off the path at each level is requested one level ahead: the chain
 		// of dependent loads is then the program words alone (mostly L1 hits: a warp shares a few parents), not
 		// program word -> row -> program word -> row.
@@ -97,11 +103,12 @@ struct ChildWalk {
 		uint4 off = sp.dv > 0 ? XMP_LDG(PU + (size_t) other * rs) : rt;       // `other` hangs off the path: unchanged
 		for (unsigned depth = sp.dv; depth > 0; --depth) {
 			cur = parent_pos(cur, other);
-			mark(cur);
 			other = prog_sib(prog[cur * 32u]);
 			const uint4 off_next = depth > 1 ? XMP_LDG(PU + (size_t) other * rs) : rt;
 			u = fitch_block(u, off);
-			if (k < D) upath[(size_t) k * T] = u; else overflow = true;
+			if (gup) gup[(size_t) cur * rs] = u;
+			else if (k < D) upath[(size_t) k * T] = u;
+			else overflow = true;
 			off = off_next;
 			++k;
 		}
@@ -116,7 +123,8 @@ struct ChildWalk {
 	}
 	// w = word_for(j), loaded by the caller two steps ahead: the word and the rows it leads to are two dependent
 	// loads, and with the word requested inside the step that chain sat on the critical path of every step.
-	XMP_HD void step(unsigned j, unsigned w, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) const {
+	// Steps must be taken in order j = 0, 1, 2, ... (lim is running state).
+	XMP_HD void step(unsigned j, unsigned w, unsigned &word, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T, const uint4 &r0) {
 		const unsigned P = sp.P;
 		unsigned i = parent_index(j, P);
 		if (i >= E) i = E - 1;
@@ -128,14 +136,19 @@ struct ChildWalk {
 		unsigned s = prog_sib(w);
 		unsigned src_s = 0u, row_s = s, k_s = sp.dv - d;
 		if (s == XMP_NO_POS) src_s = 3u;
-		else if (s == P) { src_s = 1u; k_s = 0u; }              // the sibling was the insertion edge: now the new internal node
-		else if (on_path(s)) src_s = 1u;
+		else if (!anc && d <= lim) src_s = 1u;                  // s == P included: d == dv there, k_s = 0
+		lim = anc ? d + 1u : (lim < d ? lim : d);               // the spliced steps re-read positions P - 1 and P: no change
 		if (j == P) {
 			src_u = 1u; k_u = 0u;
 			row_s = sp.sv; src_s = sp.sv == XMP_NO_POS ? 3u : 0u;
 		}
 		if (j == P + 1u) { src_u = 2u; src_s = 0u; row_s = P; }
 		if (j == P + 2u) { src_u = 0u; row_u = P; src_s = 2u; }
+		if (gup) {          // on-path sets by position: my own (an ancestor, or the new node at P: position j) / my sibling's (s <= P)
+			ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? gup[(size_t) j * rs] : rt);
+			us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? gup[(size_t) s * rs] : (src_s == 2u ? rt : r0));
+			return;
+		}
 		ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? upath[(size_t) k_u * T] : rt);
 		us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? upath[(size_t) k_s * T] : (src_s == 2u ? rt : r0));
 	}

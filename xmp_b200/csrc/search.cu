@@ -297,9 +297,9 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
                        unsigned *depth_out, unsigned *overflow_flag) {
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
-	uint4 *upath = smem + threadIdx.x;
-	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
-	unsigned *acc = (unsigned *) (smem + (size_t) 2 * D * T);        // [cpc][Ec], used when W > 1
+	uint4 *upath = nullptr;                                           // the root-path UP sets go through the child's record
+	uint4 *dstack = smem + threadIdx.x;
+	unsigned *acc = (unsigned *) (smem + (size_t) D * T);            // [cpc][Ec], used when W > 1
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned cpc = T / W;                                        // whole children per CTA (W <= 32 <= T)
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
@@ -329,7 +329,7 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 			unsigned *ch = hdr_of(child, L, cslot);
 			unsigned *cprog = ch + L.off_prog * 32u, *ccost = ch + L.off_cost * 32u;
 			ChildWalk cw;
-			const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
+			const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow, CU);
 			unsigned wj, first_edge = 0;
 			uint4 ux, us;
 			unsigned pw1 = cw.word_for(1);                  // Ec >= 5
@@ -836,13 +836,14 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	return XMP_OK;
 }
 
-// Shared memory of the child-walk kernels: two stacks of D blocks per thread.  A child of a tree of depth d is
+// Shared memory of the child-walk kernels: two stacks of D blocks per thread (one for the eager builder, whose
+// root-path UP sets live in the child's record).  A child of a tree of depth d is
 // at most d + 1 deep; its stacks are indexed by depth, so D = (deepest parent so far) + 2, capped by the worst
 // case m + 1 (a caterpillar).
-static unsigned walk_threads(unsigned D, size_t *smem) {
+static unsigned walk_threads(unsigned D, size_t *smem, unsigned stacks = 2) {
 	unsigned threads = 128;
-	while (threads > 32 && (size_t) 2 * D * 16 * threads > ((size_t) 96 << 10)) threads >>= 1;
-	*smem = (size_t) 2 * D * 16 * threads;
+	while (threads > 32 && (size_t) stacks * D * 16 * threads > ((size_t) 96 << 10)) threads >>= 1;
+	*smem = (size_t) stacks * D * 16 * threads;
 	return threads;
 }
 
@@ -851,7 +852,7 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 	Pool &P = S->pool[m], &C = S->pool[m + 1];
 	const unsigned D = std::min(m + 1, S->maxdepth[m] + 2);
 	size_t smem = 0;
-	const unsigned threads = walk_threads(D, &smem);
+	const unsigned threads = walk_threads(D, &smem, S->eager ? 1 : 2);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 	if (S->eager) {
 		if (S->L.W > 1) smem += (size_t) (threads / S->L.W) * (2 * m - 1) * sizeof(unsigned);      // per-position costs of the CTA's children
