@@ -1,7 +1,7 @@
 #!/bin/bash
 # One short GPU call without Python: (1) the m-sweep of the synthetic microbenchmark (tests/sweep_m_check),
 # (2) A/B of walk-kernel variants through the command line, each run checked against the reference's output
-# file (sha256 from tests/golden/datasets.json, prepared in variants/data by scripts/prep_oneshot.sh).
+# file (sha256 from tests/golden/datasets.json, prepared in variants/data by scripts/build_variant.sh).
 ROOT=${GRAFT_REPO_ROOT:-$(cd "$(dirname "$0")/.." && pwd)}
 OUT=$ROOT/gpurun_out
 mkdir -p $OUT /tmp/xw

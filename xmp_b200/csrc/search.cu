@@ -290,7 +290,11 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 // Eager variant: the child's MIDPOINT sets are not stored; each is scored against the taxon the child will
 // receive next, and the per-position costs go to the child's header.  A child's W columns sit in consecutive
 // threads of ONE CTA (whole children per CTA), their costs meet in shared memory.
+#ifdef XMP_EAGER_MIN_CTAS            // A/B knob (scripts/build_variant.sh): register target as CTAs of 128 threads per SM
+__global__ void __launch_bounds__(128, XMP_EAGER_MIN_CTAS)
+#else
 __global__ void __launch_bounds__(128)
+#endif
 k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                        const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
                        const uint4 *__restrict__ rows, WeightPlanes wp, unsigned long long *merges, unsigned D,
