@@ -407,7 +407,12 @@ int main(int argc, char **argv) {
 	if (c.s.options & XMPH_OPT_SAVEREORDEREDDATASET) save_reordered(&p);
 	if (xmph_write_rest_bound(&p, "restBound.txt")) die(xmph_last_error());
 
-	if (c.s.options & XMPH_OPT_ONLYCOMPUTELOWERBOUND) return 0;
+	if (c.s.options & XMPH_OPT_ONLYCOMPUTELOWERBOUND) {
+		if (c.out != stdout) fclose(c.out);
+		xmph_free_problem(&p);
+		xmph_free_alignment(&a);
+		return 0;
+	}
 	if (p.num_sites == 0) die("No parsimoniously-informative sites: every tree is equally parsimonious, nothing to search.");
 
 	int avail = xmp_cuda_device_count();
