@@ -7,12 +7,12 @@
 //   * checks the costs of the first two trees of every chunk against the CPU oracle (oracle/liboracle.so; this
 //     file is test infrastructure, the oracle is only the checker) and the whole chunk against the fused
 //     host-buffer path (xmp_cuda_score_insertions_host), which shares no kernel with the resident path.
-// 4096 trees per m; a chunk is as many trees as fit 62 GiB of edge state (m = 63: 4 chunks of 1008 trees --
+// 4096 trees per m; a chunk is as many trees as fit 62 GiB of edge state (m = 63: 4 chunks of 1032 trees --
 // "in tree-chunks on one GPU").  One JSON line per m on stdout.
 //
 //   nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Iinclude -o tests/sweep_m_check tests/sweep_m_check.cu \
 //        -Lxmp_b200 -lxmp_b200 -Loracle -loracle -Xlinker -rpath,'$ORIGIN/../xmp_b200' -Xlinker -rpath,'$ORIGIN/../oracle'
-//   tests/sweep_m_check [peak_GBps] [m ...]
+//   tests/sweep_m_check [peak_GBps] [m ...]          exit 0 = all equal, 1 = a parity check failed, 2 / 3 = CUDA / library error
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <chrono>
@@ -115,8 +115,13 @@ int main(int argc, char **argv) {
 	std::vector<unsigned> ms;
 	for (int i = 2; i < argc; ++i) ms.push_back((unsigned) atoi(argv[i]));
 	if (ms.empty()) ms = {4, 8, 16, 63};
-	const unsigned N_TREES = 4096;
-	const size_t STATE_BUDGET = (size_t) 62 << 30;
+	// defaults = the BASELINE workload; tests/test_gpu.py runs a reduced copy (SWEEP_TREES, SWEEP_STATE_GIB)
+	const unsigned N_TREES = getenv("SWEEP_TREES") ? (unsigned) atoi(getenv("SWEEP_TREES")) : 4096;
+	const size_t STATE_BUDGET = (size_t) (getenv("SWEEP_STATE_GIB") ? atoi(getenv("SWEEP_STATE_GIB")) : 62) << 30;
+	if (N_TREES == 0 || STATE_BUDGET < ((size_t) 1 << 30)) {
+		fprintf(stderr, "SWEEP_TREES / SWEEP_STATE_GIB out of range\n");
+		return 2;
+	}
 
 	double t0 = now_s();
 	uint8_t *rows;
