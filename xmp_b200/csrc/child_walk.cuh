@@ -145,9 +145,20 @@ struct ChildWalk {
 		if (j == P + 1u) { src_u = 2u; src_s = 0u; row_s = P; }
 		if (j == P + 2u) { src_u = 0u; row_u = P; src_s = 2u; }
 		if (gup) {          // on-path sets by position: my own (an ancestor, or the new node at P: position j) / my sibling's (s <= P)
+#ifdef XMP_WALK_UL
+			// A/B variant (scripts/build_variant.sh): both rows come from global memory, so pick the ADDRESS and load
+			// unconditionally (any valid row when the value is not used) -- selects instead of branch regions.
+			const uint4 *pu = src_u == 1u ? gup + (size_t) j * rs : PU + (size_t) row_u * rs;
+			const uint4 *ps = src_s == 1u ? gup + (size_t) s * rs : PU + (size_t) (src_s == 0u ? row_s : 0u) * rs;
+			const uint4 a = *pu, b = *ps;
+			ux = src_u == 2u ? rt : a;
+			us = src_s < 2u ? b : (src_s == 2u ? rt : r0);
+			return;
+#else
 			ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? gup[(size_t) j * rs] : rt);
 			us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? gup[(size_t) s * rs] : (src_s == 2u ? rt : r0));
 			return;
+#endif
 		}
 		ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? upath[(size_t) k_u * T] : rt);
 		us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? upath[(size_t) k_s * T] : (src_s == 2u ? rt : r0));
