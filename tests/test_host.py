@@ -175,11 +175,13 @@ def test_child_walk_replayed_on_the_host(tmp_path):
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     exe = str(tmp_path / "child_walk_check")
-    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
-                    os.path.join(os.path.dirname(os.path.abspath(__file__)), "child_walk_check.cu")], check=True)
-    for taxa, reps in (("12", "24"), ("36", "8")):
-        r = subprocess.run([exe, taxa, reps], capture_output=True, text=True)
-        assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+    # the shipped walk, and the A/B variant kept behind XMP_WALK_UL (scripts/build_variant.sh)
+    for flags in ([], ["-DXMP_WALK_UL"]):
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets"] + flags + ["-o", exe,
+                        os.path.join(os.path.dirname(os.path.abspath(__file__)), "child_walk_check.cu")], check=True)
+        for taxa, reps in (("12", "24"), ("36", "8")):
+            r = subprocess.run([exe, taxa, reps], capture_output=True, text=True)
+            assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
 
 
 # ---- partition lower bound (-Bp, reference src/partbound.c) --------------------------------------
