@@ -451,7 +451,7 @@ int main(int argc, char **argv) {
 
 	/* Gather: every shard reports the trees it holds at the final bound. */
 	unsigned char *paths = NULL;
-	unsigned long long n_trees = 0;
+	unsigned long long n_trees = 0, n_paths = 0;   /* optimal trees found / of which the paths are held */
 	xmp_search_stats total;
 	memset(&total, 0, sizeof total);
 	for (unsigned g = 0; g < c.n_gpus; ++g) {
@@ -459,9 +459,12 @@ int main(int argc, char **argv) {
 		unsigned long long n = 0;
 		xmp_search_stats st;
 		if (xmp_cuda_search_set_bound(ws[g].ctx, sh.bound)) die(xmp_cuda_last_error());
+		unsigned long long stored = 0;     /* < n only when -m made the shard cut its set back to its first max_trees */
 		if (xmp_cuda_search_result(ws[g].ctx, &score, &n, NULL, 0)) die(xmp_cuda_last_error());
-		paths = (unsigned char *) realloc(paths, (size_t) (n_trees + n + 1) * p.num_taxa);
-		if (n && xmp_cuda_search_result(ws[g].ctx, &score, &n, paths + (size_t) n_trees * p.num_taxa, (size_t) n)) die(xmp_cuda_last_error());
+		if (xmp_cuda_search_stored(ws[g].ctx, &stored)) die(xmp_cuda_last_error());
+		paths = (unsigned char *) realloc(paths, (size_t) (n_paths + stored + 1) * p.num_taxa);
+		if (stored && xmp_cuda_search_result(ws[g].ctx, &score, &n, paths + (size_t) n_paths * p.num_taxa, (size_t) stored)) die(xmp_cuda_last_error());
+		n_paths += stored;
 		n_trees += n;
 		if (xmp_cuda_search_stats(ws[g].ctx, &st)) die(xmp_cuda_last_error());
 		total.nodes += st.nodes;
@@ -475,8 +478,8 @@ int main(int argc, char **argv) {
 	}
 	t_output = now_seconds();
 
-	xmph_sort_paths_dfs(paths, (size_t) n_trees, p.num_taxa);
-	size_t n_out = n_trees > c.s.max_trees ? c.s.max_trees : (size_t) n_trees;
+	xmph_sort_paths_dfs(paths, (size_t) n_paths, p.num_taxa);
+	size_t n_out = n_paths > c.s.max_trees ? c.s.max_trees : (size_t) n_paths;
 	if (xmph_write_trees(c.out, (c.s.options & XMPH_OPT_NEXUSFMT) != 0, sh.bound, &a, p.taxon_map, paths, n_out)) die(xmph_last_error());
 	if (c.out != stdout) fclose(c.out);
 	if (!(c.s.options & XMPH_OPT_QUIET) && n_trees == 0) {

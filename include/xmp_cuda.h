@@ -165,6 +165,14 @@ int xmp_cuda_search_import_jobs(xmp_ctx *ctx, const uint8_t *jobs, unsigned n_jo
 /* Result: optimal length, number of optimal trees found by this shard, and up to cap of their paths
  * (num_taxa bytes each, unordered).  Valid once done. */
 int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned long long *n_trees, uint8_t *paths, size_t cap);
+/* The -m cap (reference src/yanbader.c:272-293: keep the first maxTrees trees of the depth-first search, go on
+ * counting).  With a finite max_trees a shard that has collected more than 4 x max_trees (and a million) optimal
+ * trees keeps only the max_trees that come first in the reference's depth-first order; n_trees above still
+ * counts all of them, *n_stored says for how many the paths are held (= n_trees when nothing was cut). */
+int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored);
+/* Host-side utility (no device needed): moves the first `keep` of n_paths insertion paths (num_taxa bytes each)
+ * in the reference's depth-first order (src/yanbader.c:103,238-243) to the front, in that order. */
+int xmp_cuda_paths_keep_first_dfs(uint8_t *paths, size_t n_paths, unsigned num_taxa, size_t keep);
 int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out);
 
 /* ------------------------------------------------------------------------------------------------

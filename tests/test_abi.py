@@ -54,3 +54,24 @@ def test_product_never_touches_the_oracle():
     mk = open(os.path.join(ROOT, "Makefile")).read()
     cuda_rule = mk[mk.index("xmp_b200/libxmp_b200.so:"):mk.index("cli:")]
     assert "oracle" not in cuda_rule
+
+
+def test_keep_first_dfs_is_the_head_of_the_depth_first_order():
+    """xmp_cuda_paths_keep_first_dfs (the host-side half of the -m cap: the reference keeps the FIRST maxTrees trees
+    its depth-first search meets, src/yanbader.c:272-293) against the host library's full depth-first sort
+    (host/trees.c), on random path sets with duplicates-free keys, small and large enough for the threaded path."""
+    import numpy as np
+    from tests import oracle_lib as ol
+    from xmp_b200 import hostlib as xh
+    rng = np.random.default_rng(99)
+    for n, count, keep in ((5, 40, 7), (12, 3000, 100), (28, 200000, 1000), (36, 70000, 70000), (100, 500, 1)):
+        paths = np.unique(ol.random_paths(rng, count, n, n), axis=0)
+        rng.shuffle(paths)
+        full = paths.copy()
+        xh.lib().xmph_sort_paths_dfs(full.ctypes.data, len(full), n)
+        got = xc.paths_keep_first_dfs(paths, keep)
+        assert got.shape == (min(keep, len(paths)), n)
+        assert (got == full[:keep]).all(), (n, count, keep)
+        # the order itself: keys of consecutive trees are non-decreasing in the reference's job coordinates
+        keys = [tuple(xh.path_to_dfs(p, n)[3:]) for p in got[:50]]
+        assert keys == sorted(keys)

@@ -30,6 +30,8 @@
 // Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
 // recorded carries its length and the final filter keeps those equal to the final bound.
 #include <algorithm>
+#include <numeric>
+#include <thread>
 #include <stdlib.h>
 #include <string.h>
 #include "ctx.h"
@@ -595,6 +597,8 @@ struct Search {
 	unsigned *h_pin = nullptr;            // pinned copy of the device scalars: [0] bound, [1] n_surv, [2] n_trees
 	std::vector<uint8_t> host_trees;      // records (score + path) that left the device, each <= the bound at that time
 	unsigned host_bound = 0xffffffffu;    // the bound host_trees was last filtered against
+	unsigned long long dropped = 0;       // optimal trees counted but no longer held (the -m cap, see cap_host_trees)
+	unsigned dropped_score = 0;           //   ... and the length they had: they only count while that is still the bound
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
@@ -912,6 +916,87 @@ static int fetch_counters(xmp_ctx *ctx, Search *S) {
 	return XMP_OK;
 }
 
+// ---- the -m cap in bounded memory -------------------------------------------------------------------
+// The reference keeps the first maxTrees optimal trees its depth-first search meets and goes on counting
+// (src/yanbader.c:272-293).  "First" is lexicographic order of the job coordinates: at every tree size the
+// pre-order position of the edge that received the next taxon (src/yanbader.c:103,238-243).  A path in the
+// library's append-only edge ids becomes those coordinates by replaying the insertions on a position table:
+// inserting at position P puts the new internal edge at P, the new leaf at P + 1, and moves everything that
+// sat at P or behind it two places back.
+static void dfs_key(const uint8_t *path, unsigned n, uint8_t *key) {
+	uint8_t pos[2 * XMP_MAX_TAXA];
+	pos[2] = 0;
+	pos[0] = 1;
+	pos[1] = 2;
+	key[0] = key[1] = key[2] = 0;
+	for (unsigned t = 3; t < n; ++t) {
+		const unsigned E = 2 * t - 3, P = pos[path[t]];
+		for (unsigned e = 0; e < E; ++e)
+			if (pos[e] >= P) pos[e] = (uint8_t) (pos[e] + 2);
+		pos[2 * t - 3] = (uint8_t) (P + 1);
+		pos[2 * t - 2] = (uint8_t) P;
+		key[t] = (uint8_t) P;
+	}
+}
+
+// Moves the `keep` records that come first in the reference's depth-first order to the front of recs (in that
+// order); the others follow in no particular order.  path_off = offset of the path inside a record.
+static void keep_first_dfs(uint8_t *recs, size_t n_rec, size_t stride, size_t path_off, unsigned n, size_t keep) {
+	if (n_rec == 0 || keep == 0) return;
+	keep = std::min(keep, n_rec);
+	std::vector<uint8_t> keys(n_rec * n);
+	unsigned n_thr = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+	if (n_rec < 65536) n_thr = 1;
+	auto work = [&](size_t lo, size_t hi) {
+		for (size_t i = lo; i < hi; ++i) dfs_key(recs + i * stride + path_off, n, keys.data() + i * n);
+	};
+	if (n_thr == 1) work(0, n_rec);
+	else {
+		std::vector<std::thread> th;
+		for (unsigned k = 0; k < n_thr; ++k) th.emplace_back(work, n_rec * k / n_thr, n_rec * (k + 1) / n_thr);
+		for (auto &x : th) x.join();
+	}
+	std::vector<size_t> idx(n_rec);
+	std::iota(idx.begin(), idx.end(), (size_t) 0);
+	auto less = [&](size_t a, size_t b) {
+		const int c = memcmp(keys.data() + a * n, keys.data() + b * n, n);
+		return c != 0 ? c < 0 : a < b;
+	};
+	if (keep < n_rec) std::nth_element(idx.begin(), idx.begin() + keep, idx.end(), less);
+	std::sort(idx.begin(), idx.begin() + keep, less);
+	std::vector<uint8_t> out(n_rec * stride);
+	for (size_t i = 0; i < n_rec; ++i) memcpy(out.data() + i * stride, recs + idx[i] * stride, stride);
+	memcpy(recs, out.data(), n_rec * stride);
+}
+
+// Host-side utility and test hook (no device needed): the first `keep` of n_paths insertion paths (num_taxa bytes
+// each) in the reference's depth-first order are moved to the front, in that order.
+extern "C" int xmp_cuda_paths_keep_first_dfs(uint8_t *paths, size_t n_paths, unsigned num_taxa, size_t keep) {
+	if (!paths || num_taxa < 3 || num_taxa > XMP_MAX_TAXA) return set_error(XMP_ERR_ARG, "bad path array");
+	keep_first_dfs(paths, n_paths, num_taxa, 0, num_taxa, keep);
+	return XMP_OK;
+}
+
+// With a finite max_trees the records held on the host are cut back to the max_trees that come first whenever
+// they outgrow 4 x max_trees (and a million): a search with billions of optimal trees then needs the memory of a
+// few million records instead of all of them.  What is cut is still counted (Search::dropped) as long as its
+// length stays the bound.  Every shard keeps its own first max_trees; the first max_trees overall are among them.
+static void cap_host_trees(Search *S) {
+	const size_t trec = S->L.trec, n_rec = S->host_trees.size() / trec, keep = S->prm.max_trees;
+	if (S->prm.max_trees >= 0x7fffffffu || keep == 0) return;
+	if (n_rec <= std::max<size_t>(4 * keep, (size_t) 1 << 20)) return;
+	for (size_t r = 0; r < S->host_trees.size(); r += trec) {       // all at the bound? (they are, once filtered)
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		if (sc != S->bound) return;
+	}
+	if (S->dropped_score != S->bound) S->dropped = 0;
+	keep_first_dfs(S->host_trees.data(), n_rec, trec, 4, S->L.n, keep);
+	S->host_trees.resize(keep * trec);
+	S->dropped += n_rec - keep;
+	S->dropped_score = S->bound;
+}
+
 // Moves every tree record off the device into host_trees.
 static int drain_trees(xmp_ctx *ctx, Search *S) {
 	if (S->ntrees_dev) {
@@ -932,6 +1017,7 @@ static int drain_trees(xmp_ctx *ctx, Search *S) {
 			}
 		}
 		S->host_trees.resize(w);
+		cap_host_trees(S);
 	}
 	S->ntrees_dev = 0;
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
@@ -1233,6 +1319,8 @@ static int dive(xmp_ctx *ctx, Search *S) {
 	// Trees found by the dive will be found again by the search proper.
 	S->ntrees_dev = 0;
 	S->host_trees.clear();
+	S->dropped = 0;
+	S->dropped_score = 0;
 	S->host_bound = 0xffffffffu;
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
 	return fetch_counters(ctx, S);
@@ -1486,7 +1574,21 @@ extern "C" int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned lo
 		++count;
 	}
 	if (score) *score = S->bound;
-	if (n_trees) *n_trees = count;
+	if (n_trees) *n_trees = count + (S->dropped_score == S->bound ? S->dropped : 0);
+	return XMP_OK;
+}
+
+extern "C" int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored) {
+	if (!ctx || !ctx->search || !n_stored) return set_error(XMP_ERR_ARG, "no search in progress");
+	Search *S = ctx->search;
+	if (!S->finished) return set_error(XMP_ERR_ARG, "the search has not finished");
+	unsigned long long count = 0;
+	for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		count += sc == S->bound;
+	}
+	*n_stored = count;
 	return XMP_OK;
 }
 

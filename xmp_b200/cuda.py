@@ -28,6 +28,7 @@ EXPORTS = [
     "xmp_cuda_search_reserve", "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
     "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
+    "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs",
 ]
 
 
@@ -79,6 +80,8 @@ def lib():
         L.xmp_cuda_search_import_jobs.argtypes = [vp, vp, u]
         L.xmp_cuda_search_result.argtypes = [vp, C.POINTER(u), C.POINTER(C.c_ulonglong), vp, sz]
         L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
+        L.xmp_cuda_search_stored.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+        L.xmp_cuda_paths_keep_first_dfs.argtypes = [vp, sz, u, sz]
         L.xmp_cuda_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
         for name in ("FitchBases_b2_w16_cuda",):
             getattr(L, name).restype = None
@@ -223,18 +226,28 @@ class Context:
             _check(lib().xmp_cuda_search_import_jobs(self._h, _ptr(jobs), len(jobs)))
 
     def search_result(self):
-        """(optimal length, number of optimal trees, their insertion paths [n_trees][num_taxa])."""
-        score, n = C.c_uint(0), C.c_ulonglong(0)
+        """(optimal length, number of optimal trees, their insertion paths [n_stored][num_taxa]); n_stored is the
+        number of optimal trees unless a finite max_trees made the library cut the set back (xmp_cuda_search_stored)."""
+        score, n, stored = C.c_uint(0), C.c_ulonglong(0), C.c_ulonglong(0)
         _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), None, 0))
-        paths = np.zeros((n.value, self.num_taxa), dtype=np.uint8)
-        if n.value:
-            _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), _ptr(paths), n.value))
+        _check(lib().xmp_cuda_search_stored(self._h, C.byref(stored)))
+        paths = np.zeros((stored.value, self.num_taxa), dtype=np.uint8)
+        if stored.value:
+            _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), _ptr(paths), stored.value))
         return score.value, n.value, paths
 
     def search_stats(self):
         st = SearchStats()
         _check(lib().xmp_cuda_search_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+
+def paths_keep_first_dfs(paths, keep):
+    """The first `keep` insertion paths in the reference's depth-first order, in that order (host only)."""
+    paths = np.ascontiguousarray(paths, dtype=np.uint8).copy()
+    if len(paths):
+        _check(lib().xmp_cuda_paths_keep_first_dfs(_ptr(paths), len(paths), paths.shape[1], keep))
+    return paths[:keep]
 
 
 def search(problem, device=0, bound=None, **kw):
