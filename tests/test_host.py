@@ -244,10 +244,10 @@ def test_partition_bound_equals_compiled_reference_on_random_alignments(tmp_path
     """Fuzz: random alignments with ambiguity codes, duplicated columns (weights > 1) and all three
     strategies through the reference's own program (--onlycomputelowerbound=Y) and through host/partbound.c."""
     import subprocess
-    rng = np.random.default_rng(20261020)
+    rng = np.random.default_rng(int(os.environ.get("XMP_FUZZ_SEED", "20261020")))      # one-off wider sweeps: other seeds / more cases
     alphabet = np.array(list("ACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
     checked = 0
-    for case in range(30):
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "30"))):
         n, sites = int(rng.integers(5, 13)), int(rng.integers(6, 70))
         base = rng.integers(0, len(alphabet), (n, sites))
         for t in range(1, n):                       # related rows, so that columns are informative
@@ -284,10 +284,10 @@ def test_preprocessing_equals_compiled_reference_on_random_alignments(tmp_path):
     import re
     import subprocess
     zinit = _REF_EXE + "_zinit"          # -Bm reads an uninitialised local in the reference
-    rng = np.random.default_rng(424242)
+    rng = np.random.default_rng(int(os.environ.get("XMP_FUZZ_SEED", "424242")))
     alphabet = np.array(list("ACGTACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
     checked = 0
-    for case in range(48):
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "48"))):
         n, sites = int(rng.integers(4, 18)), int(rng.integers(4, 70))
         base = rng.integers(0, len(alphabet), (n, sites))
         for t in range(1, n):
