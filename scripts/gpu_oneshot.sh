@@ -23,7 +23,7 @@ run() {   # variant name extra-flags...
 	echo "$v $n rc=$rc $ok $(grep 'Site merges' /tmp/xw/err.txt | tr -s ' ') | $(grep 'BranchAndBound() executed' /tmp/xw/err.txt | tr -s ' ') | $(grep 'launches' /tmp/xw/err.txt | tr -s ' ') | t=$(awk "BEGIN{print $EPOCHREALTIME - $T0}")" >> $OUT/ab.log
 	rm -f /tmp/xw/out.nex
 }
-V="base ${VARIANTS:-lim limgup limgupv2}"
+V="base ${VARIANTS:-six ul ul6}"    # build them first: scripts/build_variant.sh six -DXMP_EAGER_MIN_CTAS=6 etc.
 DEADLINE=${DEADLINE:-46}
 late() { awk "BEGIN{exit !($EPOCHREALTIME - $T0 > $DEADLINE)}"; }
 its36() { run $1 its36 -Bf $ROOT/variants/data/its36_restBound.txt -b 233 -m 100000; }
