@@ -260,8 +260,12 @@ def test_partition_bound_equals_compiled_reference_on_random_alignments(tmp_path
         stale = [2, 1, 0][case % 3]
         d = tmp_path / ("run%d" % case)
         d.mkdir()
-        r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0",
-                            "--onlycomputelowerbound=Y", "--pbmaxiters=%d" % stale, letters, str(f)], cwd=d, capture_output=True, text=True)
+        try:
+            r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0",
+                                "--onlycomputelowerbound=Y", "--pbmaxiters=%d" % stale, letters, str(f)], cwd=d, capture_output=True, text=True,
+                               timeout=120)
+        except subprocess.TimeoutExpired:
+            continue                                # the reference does not return on some degenerate inputs (no informative site, --pbmaxiters=0)
         if r.returncode != 0:
             continue                                # e.g. fewer than 4 informative taxa left: nothing to compare
         want = [[int(x) for x in l.split()] for l in (d / "restBound.txt").read_text().splitlines()[1:]]
