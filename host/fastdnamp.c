@@ -413,7 +413,6 @@ int main(int argc, char **argv) {
 		xmph_free_alignment(&a);
 		return 0;
 	}
-	if (p.num_sites == 0) die("No parsimoniously-informative sites: every tree is equally parsimonious, nothing to search.");
 
 	int avail = xmp_cuda_device_count();
 	if (avail <= 0) die("No CUDA device found.  This program has no CPU search path, aborting.");

@@ -446,7 +446,9 @@ int xmph_write_rest_bound(const xmph_problem *p, const char *path) {
 /* ---- packing -------------------------------------------------------------------------------- */
 static void pack_rows(xmph_problem *p) {
 	const unsigned ns = p->num_sites;
-	p->n_blocks = ns ? (ns - 1) / XMPH_SITES_PER_BLOCK + 1 : 0;
+	/* No informative site at all: one block of padding, so that the search runs as usual and -- like the reference's,
+	 * whose Fitch calls then see zero blocks -- finds every tree optimal at the constant weight. */
+	p->n_blocks = ns ? (ns - 1) / XMPH_SITES_PER_BLOCK + 1 : 1;
 	const size_t row_bytes = (size_t) p->n_blocks * XMPH_BLOCK_BYTES, padded = row_bytes * 2;
 	if (posix_memalign((void **) &p->rows, 64, row_bytes * p->num_taxa + 64)) p->rows = NULL;
 	p->weights = (unsigned *) malloc((padded + 1) * sizeof(unsigned));

@@ -280,6 +280,21 @@ def test_search_deep_with_partition_bound_and_tree_cap(xc, alignment_dir, golden
           (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
 
 
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent; the host side and the oracle are covered by "
+                                        "tests/test_oracle.py, the device search of such a problem has not run on a GPU yet")
+def test_search_without_informative_sites(xc, tmp_path):
+    """No parsimony-informative site: every tree is optimal at the constant weight, in the reference's depth-first order."""
+    from xmp_b200 import hostlib as xh
+    f = tmp_path / "zero.phy"
+    f.write_text("6 3\nA         AC-\nB         ANG\nC         ACG\nD         TCG\nE         ACG\nF         ACR\n")
+    p = xh.Problem(xh.Alignment(str(f)))
+    assert (p.num_sites, p.n_blocks) == (0, 1)
+    want_score, want_n, want_trees, _, _ = ol.search(p)
+    score, n_trees, paths, _ = xc.search(p)
+    assert (score, n_trees) == (want_score, want_n) == (p.constant_weight, 105)
+    assert p.newick_list(paths) == want_trees
+
+
 @pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent: the host-side cut (xmp_cuda_paths_keep_first_dfs) "
                                         "is covered by tests/test_abi.py, its use inside a search has not run on a GPU yet")
 def test_search_deep_with_the_cap_applied_inside_the_library(xc, alignment_dir, goldens):

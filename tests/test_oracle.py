@@ -158,8 +158,8 @@ def test_oracle_search_equals_compiled_reference_on_random_alignments(tmp_path):
             p = xh.Problem(xh.Alignment(str(f)))          # default settings, like the reference run: -Bd, MST upper bound
         except xh.HostError:
             continue
-        if r.returncode != 0 or p.num_sites == 0:
-            continue
+        if r.returncode != 0:
+            continue                                # (an alignment without any informative site is searched like any other)
         want = (d / "out.tre").read_text().split()
         score, n_trees, trees, nodes, calls = ol.search(p)
         assert trees == want, case
@@ -168,3 +168,26 @@ def test_oracle_search_equals_compiled_reference_on_random_alignments(tmp_path):
         assert calls + 2 == int(re.search(r"ScoreFitch\(\) executed\s+(\d+)", r.stderr).group(1)), case
         checked += 1
     assert checked >= 15
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_alignment_without_informative_sites_is_searched_like_the_reference_does(tmp_path):
+    """No parsimony-informative site: the reference's search runs on zero blocks and returns every tree, at the constant
+    weight, in depth-first order (and honours -m).  Here the problem keeps one block of padding and takes the same path."""
+    import subprocess
+    from xmp_b200 import hostlib as xh
+    for k, text in enumerate(("5 4\nA         ACGT\nB         ACGT\nC         ACGT\nD         ACGA\nE         ACGT\n",
+                              "6 3\nA         AC-\nB         ANG\nC         ACG\nD         TCG\nE         ACG\nF         ACR\n")):
+        f = tmp_path / ("zero%d.phy" % k)
+        f.write_text(text)
+        for extra in ([], ["-m", "4"]):
+            r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0", "-r",
+                                "-o", "out.tre"] + extra + [str(f)], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+            assert r.returncode == 0, r.stderr
+            want = (tmp_path / "out.tre").read_text().split()
+            p = xh.Problem(xh.Alignment(str(f)))
+            assert (p.num_sites, p.n_blocks) == (0, 1) and (p.rows == 0xFF).all()
+            score, n_trees, trees, _, _ = ol.search(p, max_trees=int(extra[1]) if extra else 0x7FFFFFFF)
+            assert score == p.constant_weight
+            assert trees == want and n_trees >= len(want)
+            assert len(want) == (4 if extra else {5: 15, 6: 105}[p.num_taxa])
