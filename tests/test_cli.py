@@ -92,3 +92,30 @@ def test_search_without_a_device_fails_loudly(alignment_dir, tmp_path):
     r = run(["-q", str(alignment_dir / "h3.phy")], tmp_path)
     assert r.returncode == 1 and "No CUDA device found.  This program has no CPU search path, aborting." in r.stderr
     assert r.stdout == ""
+
+
+_REF_EXE = os.path.join(ROOT, "oracle", "_ref", "fastdnamp_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("flags", [["-d"], ["--startcol=3", "--endcol=40"], ["-d", "--startcol=10", "--endcol=300", "-b", "5000"],
+                                   ["-m", "7", "-q"]])
+def test_option_plumbing_matches_the_compiled_reference(alignment_dir, tmp_path, flags):
+    """-d, --startcol / --endcol, -b, -m, -q and reading the alignment from standard input ('-'): the same command line
+    through the reference's own program and through fastdnamp_b200, up to the search: identical restBound.txt,
+    reordered.phy and site-count lines (with -q: identical, i.e. empty, stderr)."""
+    src = (alignment_dir / "Metazoan.phy").read_bytes()
+    common = ["--tbr=N", "--seed=1", "--updatesecs=0", "--displaynewtrees=n", "--onlycomputelowerbound=Y", "--savereordereddataset=Y"] + flags + ["-"]
+    outs = []
+    for exe, name in ((_REF_EXE, "ref"), (EXE, "ours")):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe] + common, cwd=d, input=src, capture_output=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        err = r.stderr.decode()
+        counts = [l for l in err.splitlines() if "sites" in l and ("constant" in l or "informative" in l)]
+        outs.append(((d / "restBound.txt").read_bytes(), (d / "reordered.phy").read_bytes(), counts,
+                     [l for l in err.splitlines() if l.startswith(("Initial bound", "Up to", "Sites ", "Sites containing", "Reading data"))]))
+        if "-q" in flags:
+            assert err == ""
+    assert outs[0] == outs[1]
