@@ -119,3 +119,24 @@ def test_option_plumbing_matches_the_compiled_reference(alignment_dir, tmp_path,
         if "-q" in flags:
             assert err == ""
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("flags", [[], ["-Bdm", "-b", "400", "-m", "10", "-r", "-o", "o.tre", "--keeptempfiles=Y", "--displaynewbounds=n"],
+                                   ["-Bp", "--pbmaxiters=1", "-d", "--startcol=2", "--endcol=60", "--updatesecs=7"],
+                                   ["-BpC", "--displaynewtrees=n", "--savereordereddataset=Y"]])
+def test_settings_and_preprocessing_report_is_the_references(alignment_dir, tmp_path, flags):
+    """Everything the two programs print before the search (ReportSettings, src/common.c:252-369, and the preprocessing
+    lines) is the same text, except the one line that names the build ("Single-processor version.")."""
+    outs = []
+    for exe, name in ((_REF_EXE + "_zinit" if any("m" in f[2:] for f in flags if f.startswith("-B")) else _REF_EXE, "ref"), (EXE, "ours")):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, "--tbr=N", "--seed=1", "--onlycomputelowerbound=Y"] + flags + [str(alignment_dir / "h3.phy")], cwd=d, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        lines = r.stderr.splitlines()
+        build = [l for l in lines if l in ("Single-processor version.", "B200 (CUDA) version searching on 1 GPU.")]
+        assert len(build) == 1
+        outs.append([l for l in lines if l not in build])
+    assert outs[0] == outs[1]
