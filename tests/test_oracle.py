@@ -191,3 +191,59 @@ def test_alignment_without_informative_sites_is_searched_like_the_reference_does
             assert score == p.constant_weight
             assert trees == want and n_trees >= len(want)
             assert len(want) == (4 if extra else {5: 15, 6: 105}[p.num_taxa])
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_nexus_files_equal_the_compiled_references_on_random_alignments(tmp_path):
+    """The result FILE, byte for byte, in the default NEXUS format: random alignments with awkward taxon labels (inner
+    blanks, punctuation, trailing blanks that the reader trims, src/common.c:2896-2936) and a random -m, through the
+    reference's own program and through host reader + preprocessing + oracle search + host writer (host/trees.c)."""
+    import ctypes as C
+    import subprocess
+    from xmp_b200 import hostlib as xh
+    L, libc = xh.lib(), C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    L.xmph_write_trees.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(int(os.environ.get("XMP_FUZZ_SEED", "31337")))
+    alphabet = np.array(list("ACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    label_chars = list("abcXYZ019_.-#'()[]:, ")
+    checked = 0
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "30"))):
+        n, sites = int(rng.integers(4, 9)), int(rng.integers(6, 40))
+        base = rng.integers(0, len(alphabet), (n, sites))
+        for t in range(1, n):
+            keep = rng.random(sites) < 0.6
+            base[t, keep] = base[rng.integers(0, t), keep]
+        labels = []
+        for t in range(n):
+            k = int(rng.integers(1, 11))
+            lab = "".join(rng.choice(label_chars, k)).strip() or "t"
+            labels.append(("%d%s" % (t, lab))[:10].ljust(10))           # unique, exactly the 10-character field
+        f = tmp_path / ("nx%d.phy" % case)
+        f.write_text("%d %d\n" % (n, sites) + "".join(labels[t] + "".join(alphabet[base[t]]) + "\n" for t in range(n)))
+        cap = [0x7FFFFFFF, 1, 3][case % 3]
+        extra = [] if cap == 0x7FFFFFFF else ["-m", str(cap)]
+        d = tmp_path / ("nx_run%d" % case)
+        d.mkdir()
+        r = subprocess.run([_REF_EXE, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0",
+                            "-o", "out.nex"] + extra + [str(f)], cwd=d, capture_output=True, text=True, timeout=120)
+        if r.returncode != 0:
+            continue
+        want = (d / "out.nex").read_bytes()
+        a = xh.Alignment(str(f))
+        p = xh.Problem(a)
+        score, n_trees, trees, _, _ = ol.search(p, max_trees=cap)
+        # the same trees as insertion paths: everything the oracle finds at the optimum below the 3-taxon tree, in DFS order
+        _, all_paths, _ = ol.search_subtree(p, np.zeros(p.num_taxa, np.uint8), 3, score)
+        paths = np.ascontiguousarray(p.sort_paths_dfs(all_paths)[:len(trees)])
+        assert p.newick_list(paths) == trees and n_trees == len(all_paths)
+        tm = np.ascontiguousarray(p.taxon_map, dtype=np.uint32)
+        fh = libc.fopen(str(d / "ours.nex").encode(), b"w")
+        assert L.xmph_write_trees(fh, 1, score, C.byref(a._a), tm.ctypes.data, paths.ctypes.data, len(paths)) == 0
+        libc.fclose(fh)
+        assert (d / "ours.nex").read_bytes() == want, case
+        checked += 1
+    assert checked >= 20
+
