@@ -140,3 +140,75 @@ def test_settings_and_preprocessing_report_is_the_references(alignment_dir, tmp_
         assert len(build) == 1
         outs.append([l for l in lines if l not in build])
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_phylip_reader_fuzz_against_the_compiled_reference(tmp_path):
+    """The same alignment laid out at random -- interleaved blocks of random width, blank lines, lower case, U for T,
+    blanks / tabs / digits inside the sequences, CR LF line ends -- and sometimes damaged (bad character, a line too long
+    or too short, truncated file): both programs must say the same thing up to the search (src/common.c:2850-2948)."""
+    import numpy as np
+    rng = np.random.default_rng(int(os.environ.get("XMP_FUZZ_SEED", "8128")))
+    states = list("ACGTACGTACGTURYSWKMBDHV-N?")
+    ok = bad = 0
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "60"))):
+        n, sites = int(rng.integers(4, 9)), int(rng.integers(5, 60))
+        seqs = [[str(rng.choice(states)) for _ in range(sites)] for _ in range(n)]
+        for t in range(1, n):
+            for s in range(sites):
+                if rng.random() < 0.6:
+                    seqs[t][s] = seqs[int(rng.integers(0, t))][s]
+        eol = "\r\n" if case % 5 == 0 else "\n"
+        lines, pos, first = ["%d %d" % (n, sites)], 0, True
+        damage = ["", "badchar", "long", "short", "truncate"][case % 5 if case % 2 else 0]
+        while pos < sites:
+            width = int(rng.integers(1, sites - pos + 1))
+            for t in range(n):
+                chunk = seqs[t][pos:pos + width]
+                if rng.random() < 0.3:
+                    chunk = [c.lower() for c in chunk]
+                text = ""
+                for c in chunk:
+                    text += c
+                    r = rng.random()
+                    if r < 0.08:
+                        text += " "
+                    elif r < 0.11:
+                        text += "\t"
+                    elif r < 0.14:
+                        text += str(int(rng.integers(0, 10)))
+                label = ("T%d x" % t).ljust(10) if first else ""
+                lines.append(label + text)
+            if rng.random() < 0.5:
+                lines.append("" if rng.random() < 0.5 else "   ")
+            pos += width
+            first = False
+        if damage == "badchar":
+            k = int(rng.integers(1, len(lines)))
+            lines[k] += "!"
+        elif damage == "long":
+            lines[-1 if lines[-1].strip() else -2] += "A"
+        elif damage == "short":
+            k = n if len(lines) > n else 1
+            if len(lines[k].rstrip()) > 11:
+                lines[k] = lines[k].rstrip()[:-1]
+        elif damage == "truncate":
+            lines = lines[:max(2, len(lines) - int(rng.integers(1, n + 1)))]
+        f = tmp_path / ("rd%d.phy" % case)
+        f.write_bytes((eol.join(lines) + (eol if rng.random() < 0.8 else "")).encode())
+        res = []
+        for exe, name in ((_REF_EXE, "ref"), (EXE, "ours")):
+            d = tmp_path / ("%s%d" % (name, case))
+            d.mkdir()
+            r = subprocess.run([exe, "--tbr=N", "--seed=1", "--updatesecs=0", "--onlycomputelowerbound=Y", "--savereordereddataset=Y", str(f)],
+                               cwd=d, capture_output=True, timeout=60)
+            err = [l for l in r.stderr.decode(errors="replace").splitlines()
+                   if l not in ("Single-processor version.", "B200 (CUDA) version searching on 1 GPU.")]
+            files = tuple((d / x).read_bytes() if (d / x).exists() else None for x in ("restBound.txt", "reordered.phy"))
+            res.append((r.returncode, err, files))
+        if res[0][0] not in (0, 1):
+            continue                                   # the reference itself crashed on this input (it reads past short files)
+        assert res[0] == res[1], (case, damage, res[0][1][-2:], res[1][1][-2:])
+        ok += res[0][0] == 0
+        bad += res[0][0] == 1
+    assert ok >= 20 and bad >= 5
