@@ -394,7 +394,8 @@ int main(int argc, char **argv) {
 	if (c.in != stdin) fclose(c.in);
 
 	t_order = now_seconds();   /* recoding and compression are counted as input time, as in the reference */
-	if (xmph_prepare(&a, &c.s, &p)) die(xmph_last_error());
+	const int prepare_failed = xmph_prepare(&a, &c.s, &p);
+	if (prepare_failed && p.num_taxa == 0) die(xmph_last_error());
 	t_upper = t_lower = now_seconds();
 	if (!(c.s.options & XMPH_OPT_QUIET)) {
 		fprintf(stderr, "%d constant sites.\n", (int) p.n_constant_sites);
@@ -403,6 +404,18 @@ int main(int argc, char **argv) {
 	}
 	if ((c.s.options & XMPH_OPT_IMPROVEINITUPPERBOUND) && p.mst_upper_bound < c.s.bound && (c.s.options & XMPH_OPT_DISPLAYNEWBOUNDS)) {
 		fprintf(stderr, "Improving initial upper bound to %u, based on minimum spanning tree weight.\n", p.mst_upper_bound);
+	}
+	if (prepare_failed) die(xmph_last_error());      /* a restBound file that does not parse: the reference gets this far too */
+	if (c.s.options & XMPH_OPT_USELOADRESTBOUND) {
+		/* the reference's LoadRestBound says so on stderr, whatever -q says (src/common.c:1530-1554): header line + data lines + 1 */
+		char line[256];
+		unsigned n_lines = 2;
+		FILE *f = fopen(c.s.rest_bound_file, "rb");
+		if (f) {
+			if (fgets(line, sizeof line, f)) while (fgets(line, sizeof line, f)) ++n_lines;
+			fclose(f);
+		}
+		fprintf(stderr, "Read %u lines from '%s'.\n", n_lines, c.s.rest_bound_file);
 	}
 	if (c.s.options & XMPH_OPT_SAVEREORDEREDDATASET) save_reordered(&p);
 	if (xmph_write_rest_bound(&p, "restBound.txt")) die(xmph_last_error());

@@ -507,7 +507,16 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 	}
 	if (s->options & XMPH_OPT_USEDISTBASESBOUNDREST) distinct_bases_bound(p);
 	if ((s->options & XMPH_OPT_USELOADRESTBOUND) && load_rest_bound(p, s->rest_bound_file)) {
+		/* The reference has reported the site counts and the MST bound by the time it reads this file
+		 * (src/common.c:1205-1209): leave those numbers (and nothing else) for the caller's report. */
+		const xmph_problem keep = *p;
 		xmph_free_problem(p);
+		p->num_taxa = keep.num_taxa;
+		p->num_sites = keep.num_sites;
+		p->n_constant_sites = keep.n_constant_sites;
+		p->n_nonpi_sites = keep.n_nonpi_sites;
+		p->constant_weight = keep.constant_weight;
+		p->mst_upper_bound = keep.mst_upper_bound;
 		return -1;
 	}
 	if (s->options & XMPH_OPT_USEMSTBOUNDREST) mst_bound(p, s->threads);

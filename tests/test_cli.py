@@ -212,3 +212,24 @@ def test_phylip_reader_fuzz_against_the_compiled_reference(tmp_path):
         ok += res[0][0] == 0
         bad += res[0][0] == 1
     assert ok >= 20 and bad >= 5
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("body, quiet", [("2\t99\n3\t60\n5 7\n", False), ("2\t99\n3\t60\n", True), ("2\t9\nx y\n", False), ("", False),
+                                         (None, False)])
+def test_loading_rest_bound_files_like_the_reference(alignment_dir, tmp_path, body, quiet):
+    """-Bf <file> (src/common.c:1530-1554): same restBound.txt afterwards, same 'Read N lines' / parse-error text on
+    stderr (the reference prints the former even under -q), same exit code."""
+    rb = tmp_path / "in.txt"
+    if body is not None:                                       # None: the file does not exist
+        rb.write_text("i\twhatever the header says\n" + body)
+    res = []
+    for exe, name in ((_REF_EXE, "ref"), (EXE, "ours")):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, "--tbr=N", "--seed=1", "--onlycomputelowerbound=Y", "-Bf", str(rb)] + (["-q"] if quiet else []) +
+                           [str(alignment_dir / "h3.phy")], cwd=d, capture_output=True, text=True, timeout=60)
+        err = [l for l in r.stderr.splitlines() if l not in ("Single-processor version.", "B200 (CUDA) version searching on 1 GPU.")]
+        res.append((r.returncode, err, (d / "restBound.txt").read_text() if (d / "restBound.txt").exists() else None))
+    assert res[0] == res[1]
+    assert res[0][0] == (1 if body is None or "x y" in body else 0)
