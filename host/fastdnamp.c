@@ -139,7 +139,8 @@ static int parse_args(int argc, char **argv, cli *c) {
 				case 'p': c->s.options |= XMPH_OPT_USEPARTBOUND; break;
 				case 'C': case 'L':
 					if (!(c->s.options & XMPH_OPT_USEPARTBOUND)) {
-						fprintf(stderr, "To specify the '%c' option, you must have previously specified -Bp.\n", *p);
+						fprintf(stderr, "To specify the '%c' option for %s scores only, you must have previously specified -Bp.\n", *p,
+						        *p == 'C' ? "clipped" : "lower bound");
 						exit(1);
 					}
 					c->s.part_strategy = *p == 'C' ? 1 : 2;

@@ -233,3 +233,38 @@ def test_loading_rest_bound_files_like_the_reference(alignment_dir, tmp_path, bo
         res.append((r.returncode, err, (d / "restBound.txt").read_text() if (d / "restBound.txt").exists() else None))
     assert res[0] == res[1]
     assert res[0][0] == (1 if body is None or "x y" in body else 0)
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_command_line_fuzz_against_the_compiled_reference(alignment_dir, tmp_path):
+    """Random option sets -- valid, malformed and unknown -- through both programs with --onlycomputelowerbound=Y:
+    same exit code, same stderr (but for the line naming the build), same stdout, same files with the same bytes.
+    Left out on purpose: column ranges that are empty or outside the alignment (the reference reads out of bounds there)
+    and --tbr=Y (its greedy-tree line; the dive replaces it)."""
+    import random
+    import shutil
+    rnd = random.Random(int(os.environ.get("XMP_FUZZ_SEED", "5")))
+    pool = [["-b", "400"], ["-b", "0"], ["-b", "abc"], ["-m", "5"], ["-m", "0"], ["-r"], ["-d"], ["-q"], ["-Bd"], ["-Bm"], ["-Bdm"], ["-Bp"],
+            ["-BpC"], ["-BpL"], ["-Bdp"], ["-BC"], ["-BL"], ["-Bx"], ["-B"], ["--startcol=3"], ["--endcol=20"], ["--endcol=99999"],
+            ["--startcol=5", "--endcol=64"], ["--displaynewbounds=Y"], ["--displaynewbounds=N"], ["--displaynewbounds=x"],
+            ["--displaynewbounds"], ["--displaynewtrees=n"], ["--updatesecs=5"], ["--updatesecs=x"], ["--seed=7"], ["--pbmaxiters=1"],
+            ["--improveinitupperbound=N"], ["--keeptempfiles=Y"], ["--savereordereddataset=Y"], ["--bogus=1"], ["-Z"], ["-o", "res.out"]]
+    checked = 0
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "60"))):
+        flags = [x for f in rnd.sample(pool, rnd.randint(0, 4)) for x in f]
+        part = any(f.startswith("-Bp") or f == "-Bdp" for f in flags)
+        aln = "h3.phy" if part else rnd.choice(["h3.phy", "mt-10.phy"])
+        use_m = any(f.startswith("-B") and "m" in f[2:] for f in flags)
+        res = []
+        for exe, name in ((_REF_EXE + "_zinit" if use_m else _REF_EXE, "ref"), (EXE, "ours")):
+            d = tmp_path / name
+            shutil.rmtree(d, ignore_errors=True)
+            d.mkdir()
+            r = subprocess.run([exe, "--tbr=N", "--seed=1", "--onlycomputelowerbound=Y"] + flags + [str(alignment_dir / aln)], cwd=d,
+                               capture_output=True, timeout=120)
+            err = [l for l in r.stderr.decode(errors="replace").splitlines()
+                   if l not in ("Single-processor version.", "B200 (CUDA) version searching on 1 GPU.")]
+            res.append((r.returncode, err, {x: (d / x).read_bytes() for x in sorted(os.listdir(d))}, r.stdout))
+        assert res[0] == res[1], (case, flags, aln)
+        checked += 1
+    assert checked >= 50
