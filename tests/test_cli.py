@@ -268,3 +268,67 @@ def test_command_line_fuzz_against_the_compiled_reference(alignment_dir, tmp_pat
         assert res[0] == res[1], (case, flags, aln)
         checked += 1
     assert checked >= 50
+
+
+# ---- the command line end to end on the CPU, over a test double of the device library ------------------------------
+@pytest.fixture(scope="module")
+def stub_dir(tmp_path_factory):
+    """tests/stub/xmp_stub.c: the entry points host/fastdnamp.c calls, on top of the oracle's subtree search (test
+    infrastructure; the product never loads it).  Lets the host program's own logic run here: scheduler threads,
+    shared bound, job mailbox, gather, depth-first sort, -m cap, writers, final report."""
+    d = tmp_path_factory.mktemp("stub")
+    subprocess.run(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                    "-o", str(d / "libxmp_b200.so"), os.path.join(ROOT, "tests", "stub", "xmp_stub.c"),
+                    "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
+    return d
+
+
+def _run_over_stub(stub_dir, exe, args, cwd, devices=1, skew=False):
+    env = dict(os.environ, LD_LIBRARY_PATH=str(stub_dir), XMP_STUB_DEVICES=str(devices), XMP_STUB_LOG="1")
+    if skew:
+        env["XMP_STUB_SKEW"] = "1"
+    return subprocess.run([exe, "--gpus=%d" % devices] + args, cwd=cwd, capture_output=True, text=True, env=env, timeout=300)
+
+
+@pytest.mark.parametrize("name", ["its10", "quick2", "primate", "53humans.12", "its14"])
+@pytest.mark.parametrize("devices, skew", [(1, False), (3, False), (4, True)])
+def test_whole_program_over_the_test_double(stub_dir, alignment_dir, goldens, tmp_path, name, devices, skew):
+    """The reference's result file, byte for byte, from fastdnamp_b200's host side with 1, 3 and 4 scheduler threads --
+    in the last case every subtree starts on shard 0 and the other three live on work stolen through the mailbox."""
+    from tests.conftest import golden_output
+    g = goldens[name]
+    out = tmp_path / "out.nex"
+    r = _run_over_stub(stub_dir, EXE, ["--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0", "-o", str(out),
+                                       str(alignment_dir / g["alignment"])], tmp_path, devices, skew)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == golden_output(name)
+    import re
+    assert re.search(r"Optimal trees found:\s+%d\n" % g["num_trees"], r.stderr) and "Time to perform branch and bound search:" in r.stderr
+    if skew:
+        assert r.stderr.count("imports") >= 3                  # the idle shards were fed
+    # raw format, quiet, capped: the reference's first trees in its order, nothing on stderr but the test double's log
+    r = _run_over_stub(stub_dir, EXE, ["-q", "-r", "-m", "3", str(alignment_dir / g["alignment"])], tmp_path, devices, skew)
+    want = [l.split("] ")[1] for l in golden_output(name).decode().splitlines() if "TREE FASTDNAMP_" in l][:3]
+    assert r.returncode == 0 and r.stdout.splitlines() == want
+    assert all(l.startswith("stub: ") for l in r.stderr.splitlines())
+
+
+def test_scheduler_threads_under_thread_sanitizer(stub_dir, alignment_dir, goldens, tmp_path):
+    """host/fastdnamp.c (with the host library's sources) compiled with -fsanitize=thread, four scheduler threads, skewed
+    start: no data race reported in the shared bound / mailbox / termination logic, and still the reference's file."""
+    from tests.conftest import golden_output
+    exe = str(tmp_path / "cli_tsan")
+    src = [os.path.join(ROOT, "host", f) for f in ("fastdnamp.c", "phylip.c", "prep.c", "trees.c", "partbound.c")]
+    c = subprocess.run(["gcc", "-O1", "-g", "-mpopcnt", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-fsanitize=thread", "-o", exe] + src +
+                       ["-I" + os.path.join(ROOT, "host"), "-I" + os.path.join(ROOT, "include"), "-L" + str(stub_dir), "-lxmp_b200", "-lpthread"],
+                       capture_output=True, text=True)
+    if c.returncode != 0:
+        pytest.skip("no thread sanitizer runtime here: " + c.stderr[-200:])
+    for name in ("53humans.12", "its14"):
+        out = tmp_path / (name + ".nex")
+        r = _run_over_stub(stub_dir, exe, ["--tbr=N", "--seed=1", "--displaynewbounds=y", "--displaynewtrees=n", "--updatesecs=0", "-o", str(out),
+                                           str(alignment_dir / goldens[name]["alignment"])], tmp_path, 4, True)
+        if "unexpected memory mapping" in r.stderr:
+            pytest.skip("the thread sanitizer cannot map its shadow memory in this container")
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]
+        assert out.read_bytes() == golden_output(name)
