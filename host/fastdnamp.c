@@ -519,6 +519,7 @@ int main(int argc, char **argv) {
 	}
 	for (unsigned g = 0; g < c.n_gpus; ++g) xmp_cuda_destroy(ws[g].ctx);
 	free(paths);
+	free(sh.mail);
 	free(ws);
 	free(th);
 	xmph_free_problem(&p);

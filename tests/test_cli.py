@@ -332,3 +332,70 @@ def test_scheduler_threads_under_thread_sanitizer(stub_dir, alignment_dir, golde
             pytest.skip("the thread sanitizer cannot map its shadow memory in this container")
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-2000:]
         assert out.read_bytes() == golden_output(name)
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("flags", [["-b", "1"], ["-b", "694"], ["-m", "2", "-r"], ["-d"], ["-Bdm"], ["--startcol=100", "--endcol=400", "-r"]])
+def test_whole_program_with_options_against_the_compiled_reference(stub_dir, alignment_dir, tmp_path, flags):
+    """Whole runs with options that change the search or the output (a bound that is too low: an empty tree block and
+    'NO BEST TREE FOUND'; a bound equal to the optimum; a cap; -d; another lower bound; a column range): the reference's
+    program and fastdnamp_b200 over the test double write the same file and the same messages."""
+    res = []
+    zinit = any(f.startswith("-B") and "m" in f[2:] for f in flags)
+    for exe, name in ((_REF_EXE + "_zinit" if zinit else _REF_EXE, "ref"), (EXE, "ours")):
+        d = tmp_path / name
+        d.mkdir()
+        args = ["--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0", "-o", "out.txt"] + flags + [str(alignment_dir / "its10.phy")]
+        r = _run_over_stub(stub_dir, exe, args, d) if name == "ours" else subprocess.run([exe] + args, cwd=d, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        said = [l for l in r.stderr.splitlines() if l.startswith(("NO BEST TREE", "Improving", "Beginning", "Read ")) or "informative" in l]
+        res.append(((d / "out.txt").read_bytes(), (d / "restBound.txt").read_bytes(), said))
+    assert res[0] == res[1]
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_EXE), reason="oracle/_ref not built (needs /root/reference)")
+def test_whole_program_fuzz_against_the_compiled_reference(stub_dir, tmp_path):
+    """Random small alignments (ambiguity codes, repeated columns) and random option sets through the reference's program
+    and through fastdnamp_b200 over the test double, with one to three scheduler threads: same result file, same
+    restBound.txt, same number of optimal trees reported."""
+    import re
+    import shutil
+    import numpy as np
+    rng = np.random.default_rng(int(os.environ.get("XMP_FUZZ_SEED", "271828")))
+    alphabet = np.array(list("ACGTACGTACGTACGTACGTRYSWKMBDHVN-?"))
+    pool = [["-r"], ["-d"], ["-m", "1"], ["-m", "4"], ["-Bdm"], ["-Bm"], ["-Bp"], ["-BpC"], ["--startcol=2", "--endcol=30"], ["-q"]]
+    checked = 0
+    for case in range(int(os.environ.get("XMP_FUZZ_CASES", "40"))):
+        n, sites = int(rng.integers(4, 9)), int(rng.integers(32, 60))
+        picks = [pool[i] for i in rng.choice(len(pool), int(rng.integers(0, 4)), replace=False)]
+        picks = [p for i, p in enumerate(picks) if not (p[0].startswith("-B") and any(q[0].startswith("-B") for q in picks[:i]))]
+        flags = [x for p in picks for x in p]
+        # The partition bound is not a valid lower bound when ambiguity codes abound (DESIGN.md section 2): the reference's own
+        # answer then depends on its visiting order and need not be the optimum.  -Bp cases get unambiguous data.
+        part = any(x.startswith("-Bp") for x in flags)
+        base = rng.integers(0, 4 if part else len(alphabet), (n, sites))
+        for t in range(1, n):
+            keep = rng.random(sites) < 0.6
+            base[t, keep] = base[rng.integers(0, t), keep]
+        cols = rng.integers(0, sites, sites + int(rng.integers(0, sites)))
+        f = tmp_path / ("wp%d.phy" % case)
+        f.write_text("%d %d\n" % (n, len(cols)) + "".join("T%-9d%s\n" % (t, "".join(alphabet[base[t, cols]])) for t in range(n)))
+        zinit = any(x.startswith("-B") and "m" in x[2:] for x in flags)
+        res = []
+        for exe, name in ((_REF_EXE + "_zinit" if zinit else _REF_EXE, "ref"), (EXE, "ours")):
+            d = tmp_path / name
+            shutil.rmtree(d, ignore_errors=True)
+            d.mkdir()
+            args = ["--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=0", "-o", "out.txt"] + flags + [str(f)]
+            if name == "ours":
+                r = _run_over_stub(stub_dir, exe, args, d, devices=1 + case % 3, skew=case % 2 == 1)
+            else:
+                r = subprocess.run([exe] + args, cwd=d, capture_output=True, text=True, timeout=300)
+            rb = (d / "restBound.txt").read_bytes() if (d / "restBound.txt").exists() else None
+            out = (d / "out.txt").read_bytes() if (d / "out.txt").exists() else None
+            res.append((r.returncode, out, rb, "NO BEST TREE" in r.stderr))
+        if res[0][0] != 0 and res[1][0] != 0:
+            continue                                  # e.g. fewer than four taxa survive: both refuse
+        assert res[0] == res[1], (case, flags)
+        checked += 1
+    assert checked >= 30
