@@ -265,6 +265,10 @@ typedef struct {
 	unsigned n_mail, cap_mail;
 	char err[512];
 	int display_bounds;
+	/* progress reports (--updatesecs, reference src/yanbader.c:28-44, src/common.c:525-541) */
+	unsigned update_secs;
+	double t_start, t_last_update;
+	double open_share[64];     /* per worker: the share of the search space its open subtrees still stand for */
 } shared_state;
 
 typedef struct {
@@ -291,6 +295,33 @@ static void worker_fail(worker *w, const char *what) {
 	pthread_mutex_unlock(&sh->mu);
 }
 
+/* The reference reports the share of the search space its depth-first walk has left behind.  A frontier search knows
+ * the same quantity from what is still open: a partial tree on m taxa stands for 1 / (3 * 5 * ... * (2m-5)) of all trees. */
+static void report_progress(worker *w, unsigned bound) {
+	shared_state *sh = w->sh;
+	unsigned long long pending[XMP_MAX_TAXA + 1];
+	if (!sh->update_secs || w->index >= 64 || xmp_cuda_search_pending(w->ctx, pending)) return;
+	double share = 0, unit = 1;
+	for (unsigned m = 3; m <= XMP_MAX_TAXA; ++m) {
+		share += (double) pending[m] * unit;
+		unit /= (double) (2 * m - 3);
+	}
+	pthread_mutex_lock(&sh->mu);
+	sh->open_share[w->index] = share;
+	const double now = now_seconds();
+	if (now - sh->t_last_update >= (double) sh->update_secs) {
+		double open = 0;
+		for (unsigned g = 0; g < sh->n_workers && g < 64; ++g) open += sh->open_share[g];
+		if (open > 1) open = 1;           /* shards expand the shallow levels redundantly before the frontier is dealt out */
+		const double done = 1 - open, elapsed = now - sh->t_start;
+		fprintf(stderr, "%.2f%% complete.  Best length so far: %u.  Estimated time remaining: ", 100 * done, bound < sh->bound ? bound : sh->bound);
+		if (elapsed < 10 || done <= 0) fprintf(stderr, "(too early to tell)\n");
+		else fprintf(stderr, "%.0f seconds\n", (1 - done) * elapsed / done);
+		sh->t_last_update = now;
+	}
+	pthread_mutex_unlock(&sh->mu);
+}
+
 static void *worker_main(void *arg) {
 	worker *w = (worker *) arg;
 	shared_state *sh = w->sh;
@@ -312,9 +343,10 @@ static void *worker_main(void *arg) {
 		unsigned mine = 0, global;
 		/* slices give the other GPUs (and --displaynewbounds) a chance to see a new bound; a single GPU with
 		 * nothing to report runs straight through */
-		const unsigned slice = (sh->n_workers > 1 || sh->display_bounds) ? SLICE_BATCHES : 0;
+		const unsigned slice = (sh->n_workers > 1 || sh->display_bounds || sh->update_secs) ? SLICE_BATCHES : 0;
 		if (!done && xmp_cuda_search_run(w->ctx, slice, &done)) { worker_fail(w, "searching"); break; }
 		if (xmp_cuda_search_get_bound(w->ctx, &mine)) { worker_fail(w, "reading the bound"); break; }
+		report_progress(w, mine);
 
 		pthread_mutex_lock(&sh->mu);
 		if (mine < sh->bound) {
@@ -443,6 +475,7 @@ int main(int argc, char **argv) {
 	sh.bound = p.bound;
 	sh.n_workers = c.n_gpus;
 	sh.display_bounds = (c.s.options & XMPH_OPT_DISPLAYNEWBOUNDS) != 0;
+	sh.update_secs = (c.s.options & XMPH_OPT_QUIET) ? 0 : c.update_secs;
 	worker *ws = (worker *) calloc(c.n_gpus, sizeof(worker));
 	pthread_t *th = (pthread_t *) calloc(c.n_gpus, sizeof(pthread_t));
 
@@ -458,6 +491,7 @@ int main(int argc, char **argv) {
 		if (xmp_cuda_search_reserve(ws[g].ctx, p.num_taxa, p.n_blocks, c.mem_budget)) die(xmp_cuda_last_error());
 	}
 	t_search = now_seconds();
+	sh.t_start = sh.t_last_update = t_search;
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_create(&th[g], NULL, worker_main, &ws[g]);
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_join(th[g], NULL);
 	if (sh.failed) die(sh.err);

@@ -399,3 +399,20 @@ def test_whole_program_fuzz_against_the_compiled_reference(stub_dir, tmp_path):
         assert res[0] == res[1], (case, flags)
         checked += 1
     assert checked >= 30
+
+
+def test_progress_reports(stub_dir, alignment_dir, goldens, tmp_path):
+    """--updatesecs=<n> (reference src/yanbader.c:28-44): every n seconds the share of the search space already settled --
+    here 1 minus what the open subtrees stand for -- the best length so far and a time estimate; none with 0 or -q."""
+    import re
+    from tests.conftest import golden_output
+    aln = str(alignment_dir / goldens["mt-10"]["alignment"])
+    out = tmp_path / "out.nex"
+    r = _run_over_stub(stub_dir, EXE, ["--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "--updatesecs=1", "-o", str(out), aln],
+                       tmp_path, devices=2)
+    assert r.returncode == 0 and out.read_bytes() == golden_output("mt-10")
+    pct = [float(x) for x in re.findall(r"^([\d.]+)% complete\.  Best length so far: \d+\.  Estimated time remaining: ", r.stderr, re.M)]
+    assert pct and pct == sorted(pct) and 0 <= pct[0] and pct[-1] <= 100
+    for quiet in (["--updatesecs=0"], ["-q"]):
+        r = _run_over_stub(stub_dir, EXE, ["--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n", "-o", str(out)] + quiet + [aln], tmp_path)
+        assert r.returncode == 0 and "% complete" not in r.stderr
