@@ -11,7 +11,8 @@
  * scope"): the -Bi/-Bk/-BK/-Bh lower bounds (load their restBound.txt with -Bf <file>).  --tbr is
  * accepted: in the reference it lowers the bound to the greedy stepwise-addition tree's length and
  * discards the TBR result (src/common.c:2608-2632, src/greedytree.c:92-100); here a greedy beam dive
- * on the device seeds the bound, whatever --tbr says.
+ * on the device seeds the bound, whatever --tbr says.  --displaynewtrees is accepted too, but trees are not echoed
+ * one by one as they are found (src/yanbader.c:260-270): they leave the device in batches and appear in the result.
  */
 #include <limits.h>
 #include <pthread.h>
