@@ -75,3 +75,62 @@ def test_keep_first_dfs_is_the_head_of_the_depth_first_order():
         # the order itself: keys of consecutive trees are non-decreasing in the reference's job coordinates
         keys = [tuple(xh.path_to_dfs(p, n)[3:]) for p in got[:50]]
         assert keys == sorted(keys)
+
+
+def test_tree_bookkeeping_with_and_without_the_cap():
+    """xmp_cuda_selftest_tree_cap replays drains through the very functions the search uses (absorb_drained,
+    cap_host_trees, optimal_trees): records above the bound are dropped, a falling bound discards what was held (and what
+    had been cut and counted), and with a finite max_trees the first max_trees in depth-first order survive while the
+    count stays complete -- the reference's -m semantics (src/yanbader.c:248-294)."""
+    import ctypes as C
+    import numpy as np
+    from tests import oracle_lib as ol
+    from xmp_b200 import hostlib as xh
+    L = xc.lib()
+    rng = np.random.default_rng(4242)
+    n = 26
+    trec = 4 + ((n + 3) & ~3)
+
+    def records(paths, scores):
+        rec = np.zeros((len(paths), trec), np.uint8)
+        rec[:, :4] = np.asarray(scores, dtype="<u4").view(np.uint8).reshape(-1, 4)
+        rec[:, 4:4 + n] = paths
+        return rec
+
+    def replay(batches, max_trees, cap):
+        recs = np.concatenate([records(p, s) for p, s, _ in batches])
+        sizes = np.array([len(p) for p, _, _ in batches], np.uint32)
+        bounds = np.array([b for _, _, b in batches], np.uint32)
+        total, stored = C.c_ulonglong(0), C.c_ulonglong(0)
+        out = np.zeros((cap, n), np.uint8)
+        rc = L.xmp_cuda_selftest_tree_cap(recs.ctypes.data, sizes.ctypes.data, bounds.ctypes.data, len(batches), n, max_trees,
+                                          C.byref(total), C.byref(stored), out.ctypes.data, cap)
+        assert rc == 0
+        return total.value, stored.value, out[:min(cap, stored.value)]
+
+    def dfs_sorted(paths):
+        full = np.ascontiguousarray(paths).copy()
+        xh.lib().xmph_sort_paths_dfs(full.ctypes.data, len(full), n)
+        return full
+
+    all_paths = np.unique(ol.random_paths(rng, 3_400_000, n, n), axis=0)
+    rng.shuffle(all_paths)
+    a, b, c, d = np.split(all_paths[:3_200_000], [900_000, 1_500_000, 2_300_000])
+    mixed = np.where(rng.random(len(b)) < 0.5, 101, 100)                # batch 2: the bound falls to 100 inside it
+    batches = [(a, np.full(len(a), 101), 101),                           # 900 K trees of length 101
+               (b, mixed, 100),                                          # ... superseded: half of these have length 100
+               (c, np.full(len(c), 100), 100), (d, np.where(rng.random(len(d)) < 0.1, 103, 100), 100)]
+    at100 = np.concatenate([b[mixed == 100], c, d[batches[3][1] == 100]])
+    # no cap: everything at the final bound is held
+    total, stored, got = replay(batches, 0x7FFFFFFF, len(at100))
+    assert total == stored == len(at100)
+    assert (dfs_sorted(got) == dfs_sorted(at100)).all()
+    # -m 1000: the count is complete, the held paths contain exactly the first 1000 of the depth-first order
+    total, stored, got = replay(batches, 1000, 1_000_000)
+    assert total == len(at100) and 1000 <= stored < total and len(got) == stored
+    assert (dfs_sorted(got)[:1000] == dfs_sorted(at100)[:1000]).all()
+    # the cut had already happened at length 101 (900 K < 2^20 held, then 1.2 M): a later better bound forgets all of it
+    total, stored, got = replay(batches[:1] + [(b, np.full(len(b), 101), 101)] + [(c[:10], np.full(10, 99), 99)], 1000, 100)
+    assert (total, stored) == (10, 10) and (dfs_sorted(got) == dfs_sorted(c[:10])).all()
+    total, stored, _ = replay(batches[:1] + [(b, np.full(len(b), 101), 101)], 1000, 10)
+    assert total == len(a) + len(b) and stored == 1000

@@ -997,6 +997,66 @@ static void cap_host_trees(Search *S) {
 	S->dropped_score = S->bound;
 }
 
+// Records [old, end) of host_trees have just arrived.  Drop what the current bound already rules out -- only the new
+// records, unless the bound has moved since the older ones were checked -- then apply the -m cut.
+static void absorb_drained(Search *S, size_t old) {
+	size_t w = S->bound < S->host_bound ? 0 : old;
+	S->host_bound = S->bound;
+	for (size_t r = w; r < S->host_trees.size(); r += S->L.trec) {
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		if (sc <= S->bound) {
+			if (w != r) memmove(S->host_trees.data() + w, S->host_trees.data() + r, S->L.trec);
+			w += S->L.trec;
+		}
+	}
+	S->host_trees.resize(w);
+	cap_host_trees(S);
+}
+
+// Optimal trees known to this shard: how many there are, and for how many of them the path is still held.
+static unsigned long long optimal_trees(const Search *S, unsigned long long *stored) {
+	unsigned long long count = 0;
+	for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		count += sc == S->bound;
+	}
+	if (stored) *stored = count;
+	return count + (S->dropped_score == S->bound ? S->dropped : 0);
+}
+
+// Self-test hook for the host-side bookkeeping above (no device needed; tests/test_abi.py): replays a sequence of drains.
+// Batch b brings batch_records[b] records of rec_bytes = 4 + ((num_taxa + 3) & ~3) bytes (length, path) while the bound
+// stands at batch_bounds[b].  Returns what xmp_cuda_search_result / _stored would report after the last batch.
+extern "C" int xmp_cuda_selftest_tree_cap(const uint8_t *records, const unsigned *batch_records, const unsigned *batch_bounds,
+                                          unsigned n_batches, unsigned num_taxa, unsigned max_trees, unsigned long long *n_total,
+                                          unsigned long long *n_stored, uint8_t *paths, size_t cap) {
+	if (!records || num_taxa < 4 || num_taxa > XMP_MAX_TAXA || !n_total || !n_stored) return set_error(XMP_ERR_ARG, "bad arguments");
+	Search *S = new Search();
+	S->L.n = num_taxa;
+	S->L.trec = 4 + ((num_taxa + 3u) & ~3u);
+	S->prm.max_trees = max_trees;
+	size_t at = 0;
+	for (unsigned b = 0; b < n_batches; ++b) {
+		const size_t bytes = (size_t) batch_records[b] * S->L.trec, old = S->host_trees.size();
+		S->bound = batch_bounds[b];
+		S->host_trees.resize(old + bytes);
+		memcpy(S->host_trees.data() + old, records + at, bytes);
+		at += bytes;
+		absorb_drained(S, old);
+	}
+	*n_total = optimal_trees(S, n_stored);
+	size_t k = 0;
+	for (size_t r = 0; r < S->host_trees.size() && paths && k < cap; r += S->L.trec) {
+		unsigned sc;
+		memcpy(&sc, S->host_trees.data() + r, 4);
+		if (sc == S->bound) memcpy(paths + k++ * num_taxa, S->host_trees.data() + r + 4, num_taxa);
+	}
+	delete S;
+	return XMP_OK;
+}
+
 // Moves every tree record off the device into host_trees.
 static int drain_trees(xmp_ctx *ctx, Search *S) {
 	if (S->ntrees_dev) {
@@ -1004,20 +1064,7 @@ static int drain_trees(xmp_ctx *ctx, Search *S) {
 		S->host_trees.resize(old + bytes);
 		XMP_CUDA(cudaMemcpyAsync(S->host_trees.data() + old, S->d_trees[S->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		// Drop what the current bound already rules out: only the new records, unless the bound has moved
-		// since the older ones were checked.
-		size_t w = S->bound < S->host_bound ? 0 : old;
-		S->host_bound = S->bound;
-		for (size_t r = w; r < S->host_trees.size(); r += S->L.trec) {
-			unsigned sc;
-			memcpy(&sc, S->host_trees.data() + r, 4);
-			if (sc <= S->bound) {
-				if (w != r) memmove(S->host_trees.data() + w, S->host_trees.data() + r, S->L.trec);
-				w += S->L.trec;
-			}
-		}
-		S->host_trees.resize(w);
-		cap_host_trees(S);
+		absorb_drained(S, old);
 	}
 	S->ntrees_dev = 0;
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
@@ -1574,7 +1621,7 @@ extern "C" int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned lo
 		++count;
 	}
 	if (score) *score = S->bound;
-	if (n_trees) *n_trees = count + (S->dropped_score == S->bound ? S->dropped : 0);
+	if (n_trees) *n_trees = optimal_trees(S, nullptr);
 	return XMP_OK;
 }
 
@@ -1582,13 +1629,7 @@ extern "C" int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored
 	if (!ctx || !ctx->search || !n_stored) return set_error(XMP_ERR_ARG, "no search in progress");
 	Search *S = ctx->search;
 	if (!S->finished) return set_error(XMP_ERR_ARG, "the search has not finished");
-	unsigned long long count = 0;
-	for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		count += sc == S->bound;
-	}
-	*n_stored = count;
+	optimal_trees(S, n_stored);
 	return XMP_OK;
 }
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "xmp_cuda_search_reserve", "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
     "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
-    "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs",
+    "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs", "xmp_cuda_selftest_tree_cap",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
         L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
         L.xmp_cuda_search_stored.argtypes = [vp, C.POINTER(C.c_ulonglong)]
         L.xmp_cuda_paths_keep_first_dfs.argtypes = [vp, sz, u, sz]
+        L.xmp_cuda_selftest_tree_cap.argtypes = [vp, vp, vp, u, u, u, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), vp, sz]
         L.xmp_cuda_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
         for name in ("FitchBases_b2_w16_cuda",):
             getattr(L, name).restype = None
