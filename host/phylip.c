@@ -37,7 +37,7 @@ typedef struct {
 static void next_line(line_reader *r) {
 	int c;
 	r->len = 0;
-	while ((c = fgetc(r->f)) != EOF && c != '\n') {
+	while ((c = getc_unlocked(r->f)) != EOF && c != '\n') {      /* one reader per stream: no need to lock it per character */
 		if (r->len + 1 >= r->cap) {
 			r->cap = r->cap ? r->cap * 2 : 256;
 			r->buf = (char *) realloc(r->buf, r->cap);
@@ -69,6 +69,14 @@ int xmph_read_phylip(FILE *in, xmph_alignment *a) {
 	unsigned done = 0;          /* sites completed in earlier blocks */
 	unsigned line_no = 2;
 	int rc = 0;
+
+	/* character classes: the (upper-cased) state symbol, IGNORED for white space and digits, 0 for anything else */
+	enum { IGNORED = 0xFF };
+	unsigned char cls[256];
+	for (int v = 0; v < 256; ++v) {
+		const int u = toupper(v);
+		cls[v] = (unsigned char) ((u && strchr(allowed, u)) ? u : (isspace(u) || isdigit(u)) ? IGNORED : 0);
+	}
 
 	memset(a, 0, sizeof *a);
 	next_line(&r);
@@ -113,16 +121,17 @@ int xmph_read_phylip(FILE *in, xmph_alignment *a) {
 				start = r.len < 10 ? r.len : 10;
 			}
 			got = 0;
+			unsigned char *dst = a->chars + (size_t) t * a->seq_len + done;
+			const unsigned room = a->seq_len - done;
 			for (size_t i = start; i < r.len && !rc; ++i) {
-				int c = toupper((unsigned char) r.buf[i]);
-				if (c && strchr(allowed, c)) {
-					if (done + got == a->seq_len) {
-						rc = xmph_fail("Error reading input file: too many characters on line %u, aborting.", line_no);
-					} else {
-						a->chars[(size_t) t * a->seq_len + done + got++] = (unsigned char) c;
-					}
-				} else if (!isspace(c) && !isdigit(c)) {
+				const unsigned char c = cls[(unsigned char) r.buf[i]];
+				if (c == IGNORED) continue;
+				if (c == 0) {
 					rc = xmph_fail("Error reading input file: invalid character '%c' on line %u, aborting.", r.buf[i], line_no);
+				} else if (got == room) {
+					rc = xmph_fail("Error reading input file: too many characters on line %u, aborting.", line_no);
+				} else {
+					dst[got++] = c;
 				}
 			}
 			if (rc) break;
