@@ -67,19 +67,61 @@ typedef struct {
 
 /* Re-labels the states of every column by order of first appearance (taxon order, A<C<G<T inside an
  * ambiguous set), so that columns with the same partition structure become byte-identical. */
-static int recode(const xmph_alignment *a, const xmph_settings *s, columns *c) {
-	unsigned end = s->end_col > a->seq_len ? a->seq_len : s->end_col;
-	c->num_taxa = a->num_taxa;
-	c->col = (unsigned char *) malloc((size_t) a->num_taxa * (a->seq_len + 1));
-	c->n = 0;
-	for (unsigned site = s->start_col; site < end; ++site) {
+/* A tiny parallel-for over independent items (site tiles, sort runs, pair distances); threads == 0 means all cores. */
+typedef struct { void (*fn)(void *, unsigned); void *arg; unsigned n, next; } par_for;
+
+static void *par_for_thread(void *x) {
+	par_for *pf = (par_for *) x;
+	for (;;) {
+		unsigned i = __atomic_fetch_add(&pf->next, 1u, __ATOMIC_RELAXED);
+		if (i >= pf->n) return NULL;
+		pf->fn(pf->arg, i);
+	}
+}
+
+static void parallel_for(unsigned n, void (*fn)(void *, unsigned), void *arg, unsigned threads, size_t work_per_item) {
+	par_for pf = { fn, arg, n, 0 };
+	pthread_t th[64];
+	unsigned started = 0;
+	if (!threads) {
+		long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		threads = cores > 0 ? (unsigned) cores : 1;
+	}
+	if (threads > 64) threads = 64;
+	if (threads > n) threads = n;
+	if ((double) work_per_item * n < 4e6) threads = 1;           /* not worth a thread start */
+	for (; started + 1 < threads; ++started) if (pthread_create(&th[started], NULL, par_for_thread, &pf)) break;
+	par_for_thread(&pf);
+	for (unsigned i = 0; i < started; ++i) pthread_join(th[i], NULL);
+}
+
+/* Recoding is independent per site: tiles of sites go to threads, every kept or dropped site is written at its
+ * place in the range first and dropped ones (-d) are squeezed out afterwards. */
+enum { RECODE_TILE = 4096 };
+typedef struct {
+	const xmph_alignment *a;
+	const xmph_settings *s;
+	unsigned char *col, *keep;
+	unsigned start, end;
+	unsigned bad_site;          /* lowest site with a character that is no state set (UINT_MAX: none) */
+} recode_job;
+
+static void recode_tile(void *arg, unsigned tile) {
+	recode_job *j = (recode_job *) arg;
+	const xmph_alignment *a = j->a;
+	const unsigned lo = j->start + tile * RECODE_TILE, hi = lo + RECODE_TILE < j->end ? lo + RECODE_TILE : j->end;
+	for (unsigned site = lo; site < hi; ++site) {
 		int relabel[4] = { -1, -1, -1, -1 };
 		int next = 0, keep = 1;
-		unsigned char *out = c->col + (size_t) c->n * a->num_taxa;
+		unsigned char *out = j->col + (size_t) (site - j->start) * a->num_taxa;
 		for (unsigned t = 0; t < a->num_taxa; ++t) {
 			int set = base_set(a->chars[(size_t) t * a->seq_len + site]);
-			if (set < 0) return xmph_fail("Invalid character '%c' in alignment, aborting.", a->chars[(size_t) t * a->seq_len + site]);
-			if ((set & (set - 1)) && (s->options & XMPH_OPT_DISCARDMISSAMBIG)) {
+			if (set < 0) {
+				unsigned seen = __atomic_load_n(&j->bad_site, __ATOMIC_RELAXED);
+				while (site < seen && !__atomic_compare_exchange_n(&j->bad_site, &seen, site, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+				return;
+			}
+			if ((set & (set - 1)) && (j->s->options & XMPH_OPT_DISCARDMISSAMBIG)) {
 				keep = 0;
 				break;
 			}
@@ -91,8 +133,31 @@ static int recode(const xmph_alignment *a, const xmph_settings *s, columns *c) {
 			}
 			out[t] = (unsigned char) coded;
 		}
-		c->n += (unsigned) keep;
+		j->keep[site - j->start] = (unsigned char) keep;
 	}
+}
+
+static int recode(const xmph_alignment *a, const xmph_settings *s, columns *c) {
+	unsigned end = s->end_col > a->seq_len ? a->seq_len : s->end_col;
+	const unsigned start = s->start_col < end ? s->start_col : end, range = end - start;
+	c->num_taxa = a->num_taxa;
+	c->col = (unsigned char *) malloc((size_t) a->num_taxa * ((size_t) range + 1));
+	c->n = 0;
+	unsigned char *keep = (unsigned char *) malloc((size_t) range + 1);
+	recode_job job = { a, s, c->col, keep, start, end, 0xFFFFFFFFu };
+	parallel_for((range + RECODE_TILE - 1) / RECODE_TILE, recode_tile, &job, s->threads, (size_t) RECODE_TILE * a->num_taxa * 4);
+	if (job.bad_site != 0xFFFFFFFFu) {
+		unsigned t = 0;
+		while (base_set(a->chars[(size_t) t * a->seq_len + job.bad_site]) >= 0) ++t;
+		free(keep);
+		return xmph_fail("Invalid character '%c' in alignment, aborting.", a->chars[(size_t) t * a->seq_len + job.bad_site]);
+	}
+	for (unsigned i = 0; i < range; ++i) {
+		if (!keep[i]) continue;
+		if (c->n != i) memcpy(c->col + (size_t) c->n * a->num_taxa, c->col + (size_t) i * a->num_taxa, a->num_taxa);
+		++c->n;
+	}
+	free(keep);
 	c->wt = (unsigned *) malloc(((size_t) c->n + 1) * sizeof(unsigned));
 	for (unsigned i = 0; i < c->n; ++i) c->wt[i] = 1;
 	return 0;
@@ -112,7 +177,57 @@ static int by_weight_then_bytes(const void *x, const void *y) {
 	return memcmp(a->col, b->col, g_cmp_width);
 }
 
-static void sort_columns(columns *c, int (*cmp)(const void *, const void *)) {
+/* Large sets: runs sorted on all cores, then merged pairwise (also in parallel).  Both orders are total on distinct
+ * columns (and equal columns are interchangeable: they are about to be merged), so the result does not depend on how
+ * the work was cut. */
+typedef struct { keyed *k, *tmp; size_t n; unsigned runs; int (*cmp)(const void *, const void *); size_t width; } sort_job;
+
+static void sort_run(void *arg, unsigned r) {
+	sort_job *j = (sort_job *) arg;
+	const size_t lo = j->n * r / j->runs, hi = j->n * (r + 1) / j->runs;
+	qsort(j->k + lo, hi - lo, sizeof(keyed), j->cmp);
+}
+
+static void merge_pair(void *arg, unsigned pair) {
+	sort_job *j = (sort_job *) arg;
+	const unsigned r = 2 * pair * (unsigned) j->width;
+	const size_t lo = j->n * r / j->runs;
+	const size_t mid = j->n * (r + j->width < j->runs ? r + j->width : j->runs) / j->runs;
+	const size_t hi = j->n * (r + 2 * j->width < j->runs ? r + 2 * j->width : j->runs) / j->runs;
+	size_t a = lo, b = mid, o = lo;
+	while (a < mid && b < hi) j->tmp[o++] = j->cmp(&j->k[b], &j->k[a]) < 0 ? j->k[b++] : j->k[a++];
+	while (a < mid) j->tmp[o++] = j->k[a++];
+	while (b < hi) j->tmp[o++] = j->k[b++];
+}
+
+static void sort_keyed(keyed *k, size_t n, int (*cmp)(const void *, const void *), unsigned threads) {
+	if (!threads) {
+		long cores = sysconf(_SC_NPROCESSORS_ONLN);
+		threads = cores > 0 ? (unsigned) cores : 1;
+	}
+	unsigned runs = 1;
+	while (runs * 2 <= threads && runs < 32) runs *= 2;
+	if (n < 200000 || runs == 1) {
+		qsort(k, n, sizeof(keyed), cmp);
+		return;
+	}
+	sort_job job = { k, (keyed *) malloc((n + 1) * sizeof(keyed)), n, runs, cmp, 1 };
+	parallel_for(runs, sort_run, &job, threads, (size_t) 1 << 24);
+	for (job.width = 1; job.width < runs; job.width *= 2) {
+		parallel_for((runs + 2 * (unsigned) job.width - 1) / (2 * (unsigned) job.width), merge_pair, &job, threads, (size_t) 1 << 24);
+		keyed *t = job.k;
+		job.k = job.tmp;
+		job.tmp = t;
+	}
+	if (job.k != k) {
+		memcpy(k, job.k, n * sizeof(keyed));
+		free(job.k);
+	} else {
+		free(job.tmp);
+	}
+}
+
+static void sort_columns(columns *c, int (*cmp)(const void *, const void *), unsigned threads) {
 	keyed *k = (keyed *) malloc(((size_t) c->n + 1) * sizeof(keyed));
 	unsigned char *ncol = (unsigned char *) malloc((size_t) c->num_taxa * (c->n + 1));
 	unsigned *nwt = (unsigned *) malloc(((size_t) c->n + 1) * sizeof(unsigned));
@@ -121,7 +236,7 @@ static void sort_columns(columns *c, int (*cmp)(const void *, const void *)) {
 		k[i].col = c->col + (size_t) i * c->num_taxa;
 	}
 	g_cmp_width = c->num_taxa;
-	qsort(k, c->n, sizeof(keyed), cmp);
+	sort_keyed(k, c->n, cmp, threads);
 	for (unsigned i = 0; i < c->n; ++i) {
 		nwt[i] = k[i].wt;
 		memcpy(ncol + (size_t) i * c->num_taxa, k[i].col, c->num_taxa);
@@ -208,34 +323,6 @@ static unsigned strict_distance(const unsigned char *a, const unsigned char *b, 
 	unsigned d = 0;
 	for (unsigned i = 0; i < n; ++i) d += w[i] & (0u - (unsigned) (a[i] != b[i]));
 	return d;
-}
-
-/* A tiny parallel-for over independent items (pair distances); threads == 0 means all cores. */
-typedef struct { void (*fn)(void *, unsigned); void *arg; unsigned n, next; } par_for;
-
-static void *par_for_thread(void *x) {
-	par_for *pf = (par_for *) x;
-	for (;;) {
-		unsigned i = __atomic_fetch_add(&pf->next, 1u, __ATOMIC_RELAXED);
-		if (i >= pf->n) return NULL;
-		pf->fn(pf->arg, i);
-	}
-}
-
-static void parallel_for(unsigned n, void (*fn)(void *, unsigned), void *arg, unsigned threads, size_t work_per_item) {
-	par_for pf = { fn, arg, n, 0 };
-	pthread_t th[64];
-	unsigned started = 0;
-	if (!threads) {
-		long cores = sysconf(_SC_NPROCESSORS_ONLN);
-		threads = cores > 0 ? (unsigned) cores : 1;
-	}
-	if (threads > 64) threads = 64;
-	if (threads > n) threads = n;
-	if ((double) work_per_item * n < 4e6) threads = 1;           /* not worth a thread start */
-	for (; started + 1 < threads; ++started) if (pthread_create(&th[started], NULL, par_for_thread, &pf)) break;
-	par_for_thread(&pf);
-	for (unsigned i = 0; i < started; ++i) pthread_join(th[i], NULL);
 }
 
 /* All pairwise distances between `height` rows: D[i * height + j], symmetric, zero diagonal. */
@@ -353,35 +440,57 @@ static void order_taxa(xmph_problem *p, unsigned threads) {
 /* Distinct-bases bound.  For every column made only of single states: once taxa 0..k are on the
  * tree, each state that occurs among the remaining taxa but not yet on the tree must cost one more
  * step.  rest_bound[k] = weighted count of such (column, state) pairs. */
-static void distinct_bases_bound(xmph_problem *p) {
-	const unsigned n = p->num_taxa, ns = p->num_sites;
-	unsigned (*rest)[4] = (unsigned (*)[4]) calloc(ns + 1, sizeof(unsigned[4]));
-	unsigned char (*seen)[4] = (unsigned char (*)[4]) calloc(ns + 1, 4);
-	unsigned char *skip = (unsigned char *) calloc(ns + 1, 1);
-	static const signed char slot[16] = { -1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1 };
+/* Sites are independent: chunks of sites go to threads, each adds its share to a per-chunk row of totals. */
+enum { DB_CHUNK = 16384 };
+typedef struct { const xmph_problem *p; unsigned *totals; } db_job;      /* totals[chunk][taxon] */
 
+static void distinct_bases_chunk(void *arg, unsigned chunk) {
+	static const signed char slot[16] = { -1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1 };
+	db_job *j = (db_job *) arg;
+	const xmph_problem *p = j->p;
+	const unsigned n = p->num_taxa, ns = p->num_sites;
+	const unsigned lo = chunk * DB_CHUNK, hi = lo + DB_CHUNK < ns ? lo + DB_CHUNK : ns, len = hi - lo;
+	unsigned (*rest)[4] = (unsigned (*)[4]) calloc(len + 1, sizeof(unsigned[4]));
+	unsigned char (*seen)[4] = (unsigned char (*)[4]) calloc(len + 1, 4);
+	unsigned char *skip = (unsigned char *) calloc(len + 1, 1);
+	unsigned *total = j->totals + (size_t) chunk * n;
 	for (unsigned t = 0; t < n; ++t) {
-		for (unsigned i = 0; i < ns; ++i) {
-			int k = slot[p->sites[(size_t) t * ns + i] & 15];
+		const unsigned char *row = p->sites + (size_t) t * ns + lo;
+		for (unsigned i = 0; i < len; ++i) {
+			int k = slot[row[i] & 15];
 			if (k < 0) skip[i] = 1; else ++rest[i][k];
 		}
 	}
 	for (unsigned t = 0; t < n; ++t) {
-		unsigned total = 0;
-		for (unsigned i = 0; i < ns; ++i) {
+		const unsigned char *row = p->sites + (size_t) t * ns + lo;
+		unsigned sum = 0;
+		for (unsigned i = 0; i < len; ++i) {
 			if (skip[i]) continue;
-			int k = slot[p->sites[(size_t) t * ns + i] & 15];
+			int k = slot[row[i] & 15];
 			seen[i][k] = 1;
 			--rest[i][k];
 			for (int b = 0; b < 4; ++b) {
-				if (!seen[i][b] && rest[i][b] > 0) total += p->site_weights[i];
+				if (!seen[i][b] && rest[i][b] > 0) sum += p->site_weights[lo + i];
 			}
 		}
-		if (total > p->rest_bound[t]) p->rest_bound[t] = total;
+		total[t] = sum;
 	}
 	free(skip);
 	free(seen);
 	free(rest);
+}
+
+static void distinct_bases_bound(xmph_problem *p, unsigned threads) {
+	const unsigned n = p->num_taxa, ns = p->num_sites, chunks = (ns + DB_CHUNK - 1) / DB_CHUNK;
+	if (!chunks) return;
+	db_job job = { p, (unsigned *) calloc((size_t) chunks * n + 1, sizeof(unsigned)) };
+	parallel_for(chunks, distinct_bases_chunk, &job, threads, (size_t) DB_CHUNK * n * 8);
+	for (unsigned t = 0; t < n; ++t) {
+		unsigned total = 0;
+		for (unsigned c = 0; c < chunks; ++c) total += job.totals[(size_t) c * n + t];
+		if (total > p->rest_bound[t]) p->rest_bound[t] = total;
+	}
+	free(job.totals);
 }
 
 /* MST bound: half the MST weight (Fitch distances, so ambiguity never overestimates) over
@@ -472,6 +581,19 @@ void xmph_free_problem(xmph_problem *p) {
 	memset(p, 0, sizeof *p);
 }
 
+/* columns [site][taxon] -> rows [taxon][site], a tile of sites at a time */
+enum { TRANSPOSE_TILE = 8192 };
+typedef struct { const unsigned char *col; unsigned char *sites; unsigned n, num_taxa; } transpose_job;
+
+static void transpose_tile(void *arg, unsigned tile) {
+	transpose_job *j = (transpose_job *) arg;
+	const unsigned lo = tile * TRANSPOSE_TILE, hi = lo + TRANSPOSE_TILE < j->n ? lo + TRANSPOSE_TILE : j->n;
+	for (unsigned i = lo; i < hi; ++i) {
+		const unsigned char *src = j->col + (size_t) i * j->num_taxa;
+		for (unsigned t = 0; t < j->num_taxa; ++t) j->sites[(size_t) t * j->n + i] = src[t];
+	}
+}
+
 int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *p) {
 	columns c = { 0, 0, NULL, NULL };
 	const unsigned unsupported = XMPH_OPT_USEINCOMPATBOUNDREST | XMPH_OPT_USEKICKASSBOUNDREST | XMPH_OPT_USEKA2BOUNDREST |
@@ -483,16 +605,17 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 		return xmph_fail("Only the -Bd, -Bm, -Bp and -Bf lower bounds are built into this program; compute other bounds with the reference and load its restBound.txt with -Bf <file>.");
 	}
 	if (recode(a, s, &c)) { free(c.col); return -1; }
-	sort_columns(&c, by_bytes);
+	sort_columns(&c, by_bytes, s->threads);
 	merge_equal_columns(&c);
-	sort_columns(&c, by_weight_then_bytes);
+	sort_columns(&c, by_weight_then_bytes, s->threads);
 	drop_uninformative(&c, p);
 
 	p->num_taxa = a->num_taxa;
 	p->num_sites = c.n;
 	p->sites = (unsigned char *) malloc((size_t) c.n * a->num_taxa + 1);
-	for (unsigned i = 0; i < c.n; ++i) {
-		for (unsigned t = 0; t < a->num_taxa; ++t) p->sites[(size_t) t * c.n + i] = c.col[(size_t) i * a->num_taxa + t];
+	{
+		transpose_job tj = { c.col, p->sites, c.n, a->num_taxa };
+		parallel_for((c.n + TRANSPOSE_TILE - 1) / TRANSPOSE_TILE, transpose_tile, &tj, s->threads, (size_t) TRANSPOSE_TILE * a->num_taxa * 2);
 	}
 	p->site_weights = c.wt;
 	free(c.col);
@@ -505,7 +628,7 @@ int xmph_prepare(const xmph_alignment *a, const xmph_settings *s, xmph_problem *
 		p->mst_upper_bound = mst_weight(p->sites, p->num_sites, p->num_taxa, p->site_weights, 1, s->threads) + p->constant_weight;
 		if (p->mst_upper_bound < p->bound) p->bound = p->mst_upper_bound;
 	}
-	if (s->options & XMPH_OPT_USEDISTBASESBOUNDREST) distinct_bases_bound(p);
+	if (s->options & XMPH_OPT_USEDISTBASESBOUNDREST) distinct_bases_bound(p, s->threads);
 	if ((s->options & XMPH_OPT_USELOADRESTBOUND) && load_rest_bound(p, s->rest_bound_file)) {
 		/* The reference has reported the site counts and the MST bound by the time it reads this file
 		 * (src/common.c:1205-1209): leave those numbers (and nothing else) for the caller's report. */

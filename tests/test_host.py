@@ -384,3 +384,31 @@ def test_large_tree_sets_sort_and_write_like_small_ones(alignment_dir, goldens, 
     first = nx.index(b"\tTREE FASTDNAMP_1 = [&U] " + p.path_to_newick(ordered[0]).encode() + b";")
     assert nx[first + 77776].decode() == "\tTREE FASTDNAMP_77777 = [&U] " + p.path_to_newick(ordered[77776]) + ";"
     assert nx[first + len(ordered)] == b"END;"
+
+
+def test_threaded_preprocessing_equals_the_single_threaded_one(tmp_path):
+    """Recoding by site tiles, run-wise sorting with parallel merges, the distinct-bases bound by site chunks and the tiled
+    transpose only start threads on large inputs: 24 taxa x 400,000 sites with ambiguity codes and repeated columns,
+    all cores against one thread (which is what every small test runs), with and without -d and a column range."""
+    rng = np.random.default_rng(77)
+    n, sites = 24, 400_000
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTRYKMSWN-?", dtype=np.uint8)
+    base = rng.integers(0, len(alphabet), (n, 60_000))
+    for t in range(1, n):
+        keep = rng.random(base.shape[1]) < 0.7
+        base[t, keep] = base[rng.integers(0, t), keep]
+    cols = rng.integers(0, base.shape[1], sites)                      # every column ~7 times: weights > 1, a real merge
+    f = tmp_path / "big.phy"
+    with open(f, "wb") as fh:
+        fh.write(b"%d %d\n" % (n, sites))
+        for t in range(n):
+            fh.write(b"T%-9d" % t + alphabet[base[t, cols]].tobytes() + b"\n")
+    a = xh.Alignment(str(f))
+    for kw in ({}, {"options": xh.OPT_NEXUSFMT | xh.OPT_USEDISTBASESBOUNDREST | xh.OPT_IMPROVEINITUPPERBOUND | xh.OPT_DISCARDMISSAMBIG},
+               {"start_col": 1234, "end_col": 333_333, "options": xh.OPT_NEXUSFMT | xh.OPT_USEDISTBASESBOUNDREST | xh.OPT_USEMSTBOUNDREST}):
+        one, many = xh.Problem(a, threads=1, **kw), xh.Problem(a, threads=0, **kw)
+        assert one.num_sites == many.num_sites > 1000
+        for field in ("sites", "site_weights", "taxon_map", "rest_bound", "rows", "weights"):
+            assert (getattr(one, field) == getattr(many, field)).all(), field
+        assert (one.constant_weight, one.n_constant_sites, one.n_nonpi_sites, one.bound, one.mst_upper_bound) == \
+               (many.constant_weight, many.n_constant_sites, many.n_nonpi_sites, many.bound, many.mst_upper_bound)
