@@ -366,7 +366,8 @@ def test_whole_program_fuzz_against_the_compiled_reference(stub_dir, tmp_path):
     pool = [["-r"], ["-d"], ["-m", "1"], ["-m", "4"], ["-Bdm"], ["-Bm"], ["-Bp"], ["-BpC"], ["--startcol=2", "--endcol=30"], ["-q"], ["-b", "?"]]
     checked = 0
     for case in range(int(os.environ.get("XMP_FUZZ_CASES", "40"))):
-        n, sites = int(rng.integers(4, 9)), int(rng.integers(32, 60))
+        lo, hi = (int(x) for x in os.environ.get("XMP_FUZZ_TAXA", "4,9").split(","))
+        n, sites = int(rng.integers(lo, hi)), int(rng.integers(32, 60))
         picks = [pool[i] for i in rng.choice(len(pool), int(rng.integers(0, 4)), replace=False)]
         picks = [p for i, p in enumerate(picks) if not (p[0].startswith("-B") and any(q[0].startswith("-B") for q in picks[:i]))]
         flags = [x if x != "?" else str(int(rng.integers(5, 90))) for p in picks for x in p]     # -b below, at or above the optimum
