@@ -522,6 +522,11 @@ int main(int argc, char **argv) {
 		total.site_merges += st.site_merges;
 		total.launches += st.launches;
 		total.iterations += st.iterations;
+		for (unsigned m = 0; m <= XMP_MAX_TAXA; ++m) {
+			total.nodes_by_depth[m] += st.nodes_by_depth[m];
+			total.edge_evals_by_depth[m] += st.edge_evals_by_depth[m];
+			total.batches_by_depth[m] += st.batches_by_depth[m];
+		}
 		if (st.seconds > total.seconds) total.seconds = st.seconds;
 	}
 	t_output = now_seconds();
@@ -544,6 +549,12 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "Number of full trees considered:%20llu\n", total.full_trees);
 		fprintf(stderr, "Site merges                     %20llu (%.3f G/s)\n", total.site_merges, dt > 0 ? (double) total.site_merges / dt * 1e-9 : 0.0);
 		fprintf(stderr, "Kernel launches / batches       %20llu / %llu\n", total.launches, total.iterations);
+		/* the reference's per-depth counters (src/measure.c:10,79: bAndBScanEdgeCountByDepth[]), by taxa on the tree */
+		for (unsigned m = 3; m <= XMP_MAX_TAXA; ++m) {
+			if (!total.edge_evals_by_depth[m]) continue;
+			fprintf(stderr, "ScoreFitch() on trees of %3u taxa:%19llu times (%llu trees in %llu batches)\n", m, total.edge_evals_by_depth[m],
+			        total.nodes_by_depth[m], total.batches_by_depth[m]);
+		}
 		fprintf(stderr, "%-45s %11.2lfs\n", "Time to read input:", t_order - t_start);
 		fprintf(stderr, "%-45s %11.2lfs\n", "Time to order taxa:", t_upper - t_order);
 		fprintf(stderr, "%-45s %11.2lfs\n", "Time to determine initial upper bound:", t_lower - t_upper);

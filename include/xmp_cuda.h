@@ -143,6 +143,11 @@ typedef struct {
 	unsigned long long launches;       /* kernels launched by the search */
 	unsigned long long iterations;     /* frontier batches processed */
 	double   seconds;                  /* device time spent inside xmp_cuda_search_run */
+	/* per tree size m (taxa on the tree being expanded), the reference's per-depth counters
+	 * (src/measure.c:10 branchAndBoundScanEdgeCountByDepth[MAXTAXA], re-implemented as 64-bit): */
+	unsigned long long nodes_by_depth[XMP_MAX_TAXA + 1];       /* partial trees on m taxa expanded */
+	unsigned long long edge_evals_by_depth[XMP_MAX_TAXA + 1];  /* (tree, edge) pairs scored on trees of m taxa */
+	unsigned long long batches_by_depth[XMP_MAX_TAXA + 1];     /* frontier batches (launch groups) at tree size m */
 } xmp_search_stats;
 
 /* Optional: allocate the search's device memory for a problem of this shape now (mem_budget as in
@@ -173,12 +178,6 @@ int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored);
 /* Host-side utility (no device needed): moves the first `keep` of n_paths insertion paths (num_taxa bytes each)
  * in the reference's depth-first order (src/yanbader.c:103,238-243) to the front, in that order. */
 int xmp_cuda_paths_keep_first_dfs(uint8_t *paths, size_t n_paths, unsigned num_taxa, size_t keep);
-/* Self-test of the host-side tree bookkeeping behind the two calls above (no device needed): replays a sequence of
- * drains -- batch b brings batch_records[b] records of 4 + ((num_taxa + 3) & ~3) bytes (length, path) while the bound
- * stands at batch_bounds[b] -- and returns what xmp_cuda_search_result / _stored would then report. */
-int xmp_cuda_selftest_tree_cap(const uint8_t *records, const unsigned *batch_records, const unsigned *batch_bounds,
-                               unsigned n_batches, unsigned num_taxa, unsigned max_trees, unsigned long long *n_total,
-                               unsigned long long *n_stored, uint8_t *paths, size_t cap);
 int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out);
 
 /* ------------------------------------------------------------------------------------------------

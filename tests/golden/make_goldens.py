@@ -72,6 +72,9 @@ DATASETS = {
     "53humans.24": ("data/from_minmaxsqueeze/53humans.24.phy", ["-Bp", "-m", "1000"]),
     "53humans.26": ("data/from_minmaxsqueeze/53humans.26.phy", ["-Bp", "-m", "1000"]),
     "53humans.28": ("data/from_minmaxsqueeze/53humans.28.phy", ["-Bp", "-m", "1000"]),
+    # 88 M optimal trees: the search the bounded-memory -m cut exists for (10 minutes in the reference; the second,
+    # uncapped run writes all of them -- ~13 GB -- just to count the lines)
+    "53humans.29": ("data/from_minmaxsqueeze/53humans.29.phy", ["-Bp", "-m", "1000"]),
 }
 PARSER_FIXTURES = "data/phylip_format_testing"
 # inputs of other golden files (partbound.json): bundled here, not run by this script

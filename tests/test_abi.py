@@ -77,16 +77,21 @@ def test_keep_first_dfs_is_the_head_of_the_depth_first_order():
         assert keys == sorted(keys)
 
 
-def test_tree_bookkeeping_with_and_without_the_cap():
-    """xmp_cuda_selftest_tree_cap replays drains through the very functions the search uses (absorb_drained,
-    cap_host_trees, optimal_trees): records above the bound are dropped, a falling bound discards what was held (and what
+def test_tree_bookkeeping_with_and_without_the_cap(tmp_path):
+    """tests/stub/selftest_tree_cap.cpp replays drains through the very code the search uses (xmp_b200/csrc/tree_book.h,
+    compiled here into a test-only library: the product library has no such entry point): records above the bound are dropped, a falling bound discards what was held (and what
     had been cut and counted), and with a finite max_trees the first max_trees in depth-first order survive while the
     count stays complete -- the reference's -m semantics (src/yanbader.c:248-294)."""
     import ctypes as C
     import numpy as np
     from tests import oracle_lib as ol
     from xmp_b200 import hostlib as xh
-    L = xc.lib()
+    so = str(tmp_path / "libxmp_selftest.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", so,
+                    os.path.join(ROOT, "tests", "stub", "selftest_tree_cap.cpp")], check=True)
+    L = C.CDLL(so)
+    vp = C.c_void_p
+    L.xmp_selftest_tree_cap.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), vp, C.c_size_t]
     rng = np.random.default_rng(4242)
     n = 26
     trec = 4 + ((n + 3) & ~3)
@@ -103,7 +108,7 @@ def test_tree_bookkeeping_with_and_without_the_cap():
         bounds = np.array([b for _, _, b in batches], np.uint32)
         total, stored = C.c_ulonglong(0), C.c_ulonglong(0)
         out = np.zeros((cap, n), np.uint8)
-        rc = L.xmp_cuda_selftest_tree_cap(recs.ctypes.data, sizes.ctypes.data, bounds.ctypes.data, len(batches), n, max_trees,
+        rc = L.xmp_selftest_tree_cap(recs.ctypes.data, sizes.ctypes.data, bounds.ctypes.data, len(batches), n, max_trees,
                                           C.byref(total), C.byref(stored), out.ctypes.data, cap)
         assert rc == 0
         return total.value, stored.value, out[:min(cap, stored.value)]

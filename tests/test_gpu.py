@@ -280,8 +280,6 @@ def test_search_deep_with_partition_bound_and_tree_cap(xc, alignment_dir, golden
           (name, stats["seconds"], stats["nodes"], g["ref_bandb_nodes"], g["ref_bandb_seconds"], stats["iterations"]))
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent; the host side and the oracle are covered by "
-                                        "tests/test_oracle.py, the device search of such a problem has not run on a GPU yet")
 def test_search_without_informative_sites(xc, tmp_path):
     """No parsimony-informative site: every tree is optimal at the constant weight, in the reference's depth-first order."""
     from xmp_b200 import hostlib as xh
@@ -295,8 +293,6 @@ def test_search_without_informative_sites(xc, tmp_path):
     assert p.newick_list(paths) == want_trees
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent: the host-side cut (xmp_cuda_paths_keep_first_dfs) "
-                                        "is covered by tests/test_abi.py, its use inside a search has not run on a GPU yet")
 def test_search_deep_with_the_cap_applied_inside_the_library(xc, alignment_dir, goldens):
     """max_trees handed to the library: a shard that holds more than a million optimal trees cuts its set back to the
     first max_trees in the reference's depth-first order and goes on counting (src/yanbader.c:272-293), so the memory
@@ -478,6 +474,48 @@ def test_job_export_import_moves_work_between_contexts(xc, alignment_dir, golden
     c1.close()
 
 
+def test_stealing_between_shards_with_a_deep_split_level(xc, alignment_dir, goldens):
+    """Sharding and stealing together (round-1 advisor finding): with the frontier dealt out at a deep tree size and
+    one-batch slices, nodes below the split level are still open when the first steal happens.  They must never change
+    hands (they would be dealt again with the thief's index): the union of the shards is the reference's set, each tree
+    exactly once, and a job below the split level is refused on import."""
+    g = goldens["mh6"]
+    a, p = prepare(alignment_dir, goldens, "mh6")
+    ctxs = [xc.Context(0) for _ in range(3)]
+    for i, c in enumerate(ctxs):
+        c.load_problem(p)
+        c.search_begin(bound=p.bound, shard_index=i, shard_count=3, split_level=9)
+    done, moved, rounds = [False] * 3, 0, 0
+    while not all(done):
+        for i, c in enumerate(ctxs):
+            if not done[i]:
+                done[i] = c.search_run(1)
+        donor, thief = rounds % 3, (rounds + 1) % 3
+        jobs = ctxs[donor].search_export_jobs(8)
+        assert all(j[0] >= 9 for j in jobs)
+        if len(jobs):
+            ctxs[thief].search_import_jobs(jobs)
+            done[thief] = False
+            moved += len(jobs)
+        best = min(c.search_get_bound() for c in ctxs)
+        for c in ctxs:
+            c.search_set_bound(best)
+        rounds += 1
+    assert moved > 0
+    bad = np.zeros((1, p.num_taxa), np.uint8)
+    bad[0, 0] = 5
+    with pytest.raises(xc.XmpCudaError):
+        ctxs[0].search_import_jobs(bad)
+    paths = []
+    for c in ctxs:
+        score, n, ps = c.search_result()
+        assert score == g["score"]
+        paths.append(ps)
+        c.close()
+    paths = np.concatenate(paths)
+    check_against_golden("mh6", g, p, g["score"], len(paths), p.newick_list(paths))
+
+
 # ------------------------------------------------------------------------------------------ the CLI
 @pytest.mark.parametrize("name", ["mt-10", "h3", "mh6", "EukaryotesrDNA", "quick2"])
 def test_cli_writes_the_reference_result_file(alignment_dir, goldens, tmp_path, name):
@@ -564,10 +602,13 @@ def test_full_size_microbench_properties(ctx, torch):
     ctx.synchronize()
     cost = d_cost.cpu().numpy().reshape(-1, wl["E"])
     rows = wl["d_rows"].cpu().numpy()
-    # (1) oracle on three trees
-    for i in (0, 31, 63):
+    # (1) oracle on all 64 trees, and one checksum over the whole cost matrix
+    want = np.zeros_like(cost)
+    for i in range(64):
         mid, _, _, _ = ol.tree_sets(rows[:wl["m"] + 1], wl["m"], wl["paths"][i])
-        assert (cost[i] == oracle_costs(rows, None, mid, wl["m"])).all()
+        want[i] = oracle_costs(rows, None, mid, wl["m"])
+        assert (cost[i] == want[i]).all(), i
+    assert hashlib.sha256(cost.astype("<u4").tobytes()).hexdigest() == hashlib.sha256(want.astype("<u4").tobytes()).hexdigest()
     # (2) scoring a taxon against its own leaf edge costs 0; against another taxon's leaf edge it is
     #     their Hamming distance when the leaf's DOWN set does not help, never more
     d_self = torch.zeros(n_pairs, dtype=torch.int32, device="cuda")

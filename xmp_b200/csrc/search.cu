@@ -37,6 +37,7 @@
 #include "ctx.h"
 #include "walk_prog.h"
 #include "child_walk.cuh"
+#include "tree_book.h"
 
 namespace xmp {
 
@@ -256,7 +257,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
 			pw1 = pw2;
 			const unsigned d = prog_depth(wj);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
 			if (prog_size(wj) > 1u) {
 				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
 			}
@@ -347,7 +348,7 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 				if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
 				pw1 = pw2;
 				const unsigned d = prog_depth(wj);
-				const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
+				const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
 				if (prog_size(wj) > 1u) {
 					if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
 				}
@@ -450,7 +451,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
 			pw1 = pw2;
 			const unsigned d = prog_depth(wj);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1) * T], us);
+			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
 			if (prog_size(wj) > 1u) {
 				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
 			}
@@ -595,10 +596,7 @@ struct Search {
 	int cur = 0;
 	unsigned trees_cap = 0, ntrees_dev = 0;
 	unsigned *h_pin = nullptr;            // pinned copy of the device scalars: [0] bound, [1] n_surv, [2] n_trees
-	std::vector<uint8_t> host_trees;      // records (score + path) that left the device, each <= the bound at that time
-	unsigned host_bound = 0xffffffffu;    // the bound host_trees was last filtered against
-	unsigned long long dropped = 0;       // optimal trees counted but no longer held (the -m cap, see cap_host_trees)
-	unsigned dropped_score = 0;           //   ... and the length they had: they only count while that is still the bound
+	TreeBook book;                        // records (score + path) that left the device, each <= the bound at that time (tree_book.h)
 	unsigned bound = 0x7fffffffu;
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
@@ -619,6 +617,16 @@ static unsigned env_unsigned(const char *name, unsigned dflt) {
 	char *end = nullptr;
 	unsigned long x = strtoul(v, &end, 10);
 	return end != v ? (unsigned) x : dflt;
+}
+
+// Counters of one expanded batch: `nodes` partial trees on m taxa, each scored on all of its 2m-3 edges
+// (the reference's branchAndBoundCount / branchAndBoundScanEdgeCountByDepth[m], src/measure.c:8-10).
+static void count_batch(xmp_search_stats &st, unsigned m, unsigned long long nodes) {
+	st.nodes += nodes;
+	st.score_calls += nodes * (2ull * m - 3);
+	st.nodes_by_depth[m] += nodes;
+	st.edge_evals_by_depth[m] += nodes * (2ull * m - 3);
+	st.batches_by_depth[m] += 1;
 }
 
 static double odd_factorial(unsigned m) {      // number of distinct trees on m taxa: (2m-5)!!
@@ -916,155 +924,23 @@ static int fetch_counters(xmp_ctx *ctx, Search *S) {
 	return XMP_OK;
 }
 
-// ---- the -m cap in bounded memory -------------------------------------------------------------------
-// The reference keeps the first maxTrees optimal trees its depth-first search meets and goes on counting
-// (src/yanbader.c:272-293).  "First" is lexicographic order of the job coordinates: at every tree size the
-// pre-order position of the edge that received the next taxon (src/yanbader.c:103,238-243).  A path in the
-// library's append-only edge ids becomes those coordinates by replaying the insertions on a position table:
-// inserting at position P puts the new internal edge at P, the new leaf at P + 1, and moves everything that
-// sat at P or behind it two places back.
-static void dfs_key(const uint8_t *path, unsigned n, uint8_t *key) {
-	uint8_t pos[2 * XMP_MAX_TAXA];
-	pos[2] = 0;
-	pos[0] = 1;
-	pos[1] = 2;
-	key[0] = key[1] = key[2] = 0;
-	for (unsigned t = 3; t < n; ++t) {
-		const unsigned E = 2 * t - 3, P = pos[path[t]];
-		for (unsigned e = 0; e < E; ++e)
-			if (pos[e] >= P) pos[e] = (uint8_t) (pos[e] + 2);
-		pos[2 * t - 3] = (uint8_t) (P + 1);
-		pos[2 * t - 2] = (uint8_t) P;
-		key[t] = (uint8_t) P;
-	}
-}
-
-// Moves the `keep` records that come first in the reference's depth-first order to the front of recs (in that
-// order); the others follow in no particular order.  path_off = offset of the path inside a record.
-static void keep_first_dfs(uint8_t *recs, size_t n_rec, size_t stride, size_t path_off, unsigned n, size_t keep) {
-	if (n_rec == 0 || keep == 0) return;
-	keep = std::min(keep, n_rec);
-	std::vector<uint8_t> keys(n_rec * n);
-	unsigned n_thr = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-	if (n_rec < 65536) n_thr = 1;
-	auto work = [&](size_t lo, size_t hi) {
-		for (size_t i = lo; i < hi; ++i) dfs_key(recs + i * stride + path_off, n, keys.data() + i * n);
-	};
-	if (n_thr == 1) work(0, n_rec);
-	else {
-		std::vector<std::thread> th;
-		for (unsigned k = 0; k < n_thr; ++k) th.emplace_back(work, n_rec * k / n_thr, n_rec * (k + 1) / n_thr);
-		for (auto &x : th) x.join();
-	}
-	std::vector<size_t> idx(n_rec);
-	std::iota(idx.begin(), idx.end(), (size_t) 0);
-	auto less = [&](size_t a, size_t b) {
-		const int c = memcmp(keys.data() + a * n, keys.data() + b * n, n);
-		return c != 0 ? c < 0 : a < b;
-	};
-	if (keep < n_rec) std::nth_element(idx.begin(), idx.begin() + keep, idx.end(), less);
-	std::sort(idx.begin(), idx.begin() + keep, less);
-	std::vector<uint8_t> out(n_rec * stride);
-	for (size_t i = 0; i < n_rec; ++i) memcpy(out.data() + i * stride, recs + idx[i] * stride, stride);
-	memcpy(recs, out.data(), n_rec * stride);
-}
-
-// Host-side utility and test hook (no device needed): the first `keep` of n_paths insertion paths (num_taxa bytes
-// each) in the reference's depth-first order are moved to the front, in that order.
+// ---- the -m cap in bounded memory: tree_book.h ------------------------------------------------------
+// Host-side utility (no device needed): the first `keep` of n_paths insertion paths (num_taxa bytes each) in the
+// reference's depth-first order are moved to the front, in that order.
 extern "C" int xmp_cuda_paths_keep_first_dfs(uint8_t *paths, size_t n_paths, unsigned num_taxa, size_t keep) {
 	if (!paths || num_taxa < 3 || num_taxa > XMP_MAX_TAXA) return set_error(XMP_ERR_ARG, "bad path array");
 	keep_first_dfs(paths, n_paths, num_taxa, 0, num_taxa, keep);
 	return XMP_OK;
 }
 
-// With a finite max_trees the records held on the host are cut back to the max_trees that come first whenever
-// they outgrow 4 x max_trees (and a million): a search with billions of optimal trees then needs the memory of a
-// few million records instead of all of them.  What is cut is still counted (Search::dropped) as long as its
-// length stays the bound.  Every shard keeps its own first max_trees; the first max_trees overall are among them.
-static void cap_host_trees(Search *S) {
-	const size_t trec = S->L.trec, n_rec = S->host_trees.size() / trec, keep = S->prm.max_trees;
-	if (S->prm.max_trees >= 0x7fffffffu || keep == 0) return;
-	if (n_rec <= std::max<size_t>(4 * keep, (size_t) 1 << 20)) return;
-	for (size_t r = 0; r < S->host_trees.size(); r += trec) {       // all at the bound? (they are, once filtered)
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		if (sc != S->bound) return;
-	}
-	if (S->dropped_score != S->bound) S->dropped = 0;
-	keep_first_dfs(S->host_trees.data(), n_rec, trec, 4, S->L.n, keep);
-	S->host_trees.resize(keep * trec);
-	S->dropped += n_rec - keep;
-	S->dropped_score = S->bound;
-}
-
-// Records [old, end) of host_trees have just arrived.  Drop what the current bound already rules out -- only the new
-// records, unless the bound has moved since the older ones were checked -- then apply the -m cut.
-static void absorb_drained(Search *S, size_t old) {
-	size_t w = S->bound < S->host_bound ? 0 : old;
-	S->host_bound = S->bound;
-	for (size_t r = w; r < S->host_trees.size(); r += S->L.trec) {
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		if (sc <= S->bound) {
-			if (w != r) memmove(S->host_trees.data() + w, S->host_trees.data() + r, S->L.trec);
-			w += S->L.trec;
-		}
-	}
-	S->host_trees.resize(w);
-	cap_host_trees(S);
-}
-
-// Optimal trees known to this shard: how many there are, and for how many of them the path is still held.
-static unsigned long long optimal_trees(const Search *S, unsigned long long *stored) {
-	unsigned long long count = 0;
-	for (size_t r = 0; r < S->host_trees.size(); r += S->L.trec) {
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		count += sc == S->bound;
-	}
-	if (stored) *stored = count;
-	return count + (S->dropped_score == S->bound ? S->dropped : 0);
-}
-
-// Self-test hook for the host-side bookkeeping above (no device needed; tests/test_abi.py): replays a sequence of drains.
-// Batch b brings batch_records[b] records of rec_bytes = 4 + ((num_taxa + 3) & ~3) bytes (length, path) while the bound
-// stands at batch_bounds[b].  Returns what xmp_cuda_search_result / _stored would report after the last batch.
-extern "C" int xmp_cuda_selftest_tree_cap(const uint8_t *records, const unsigned *batch_records, const unsigned *batch_bounds,
-                                          unsigned n_batches, unsigned num_taxa, unsigned max_trees, unsigned long long *n_total,
-                                          unsigned long long *n_stored, uint8_t *paths, size_t cap) {
-	if (!records || num_taxa < 4 || num_taxa > XMP_MAX_TAXA || !n_total || !n_stored) return set_error(XMP_ERR_ARG, "bad arguments");
-	Search *S = new Search();
-	S->L.n = num_taxa;
-	S->L.trec = 4 + ((num_taxa + 3u) & ~3u);
-	S->prm.max_trees = max_trees;
-	size_t at = 0;
-	for (unsigned b = 0; b < n_batches; ++b) {
-		const size_t bytes = (size_t) batch_records[b] * S->L.trec, old = S->host_trees.size();
-		S->bound = batch_bounds[b];
-		S->host_trees.resize(old + bytes);
-		memcpy(S->host_trees.data() + old, records + at, bytes);
-		at += bytes;
-		absorb_drained(S, old);
-	}
-	*n_total = optimal_trees(S, n_stored);
-	size_t k = 0;
-	for (size_t r = 0; r < S->host_trees.size() && paths && k < cap; r += S->L.trec) {
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		if (sc == S->bound) memcpy(paths + k++ * num_taxa, S->host_trees.data() + r + 4, num_taxa);
-	}
-	delete S;
-	return XMP_OK;
-}
-
-// Moves every tree record off the device into host_trees.
+// Moves every tree record off the device into the host-side book.
 static int drain_trees(xmp_ctx *ctx, Search *S) {
 	if (S->ntrees_dev) {
-		const size_t bytes = (size_t) S->ntrees_dev * S->L.trec, old = S->host_trees.size();
-		S->host_trees.resize(old + bytes);
-		XMP_CUDA(cudaMemcpyAsync(S->host_trees.data() + old, S->d_trees[S->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		const size_t bytes = (size_t) S->ntrees_dev * S->L.trec, old = S->book.recs.size();
+		S->book.recs.resize(old + bytes);
+		XMP_CUDA(cudaMemcpyAsync(S->book.recs.data() + old, S->d_trees[S->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		absorb_drained(S, old);
+		S->book.absorb(old, S->bound);
 	}
 	S->ntrees_dev = 0;
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
@@ -1136,8 +1012,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 	if (!last) XMP_CUDA(cudaMemsetAsync(S->d_nsurv, 0, sizeof(unsigned), ctx->stream));
 	int rc = launch_expand(ctx, S, m, first, chunk, shard, S->d_surv, S->d_nsurv);
 	if (rc) return rc;
-	S->st.nodes += chunk;
-	S->st.score_calls += chunk * P.E;
+	count_batch(S->st, m, chunk);
 	S->st.iterations += 1;
 	if (last) {
 		rc = fetch_counters(ctx, S);
@@ -1151,6 +1026,9 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		rc = fetch_counters(ctx, S);
 		if (rc) return rc;
 		unsigned ns = S->h_pin[1];
+		// never more children than the next pool can take (a small memory budget on many taxa: capacity < beam)
+		if (!(S->fused_last && m + 2 == S->n)) keep_best = (unsigned) std::min<unsigned long long>(keep_best, S->pool[m + 1].cap - S->pool[m + 1].count);
+		if (keep_best == 0) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m + 1, S->pool[m + 1].cap);
 		if (ns > keep_best) {
 			std::vector<uint4> h(ns);
 			XMP_CUDA(cudaMemcpyAsync(h.data(), S->d_surv, (size_t) ns * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1182,8 +1060,7 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 			S->ntrees_dev = S->h_pin[2];
 		}
 		S->st.children += ns;
-		S->st.nodes += ns;
-		S->st.score_calls += (unsigned long long) ns * (P.E + 2);
+		count_batch(S->st, m + 1, ns);
 		P.count -= chunk;
 		return tidy_trees(ctx, S);
 	}
@@ -1310,15 +1187,13 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 			continue;
 		}
 		const unsigned ns = S->h_pin[8 + m];
-		S->st.nodes += items[i].chunk;
-		S->st.score_calls += items[i].chunk * P.E;
+		count_batch(S->st, m, items[i].chunk);
 		S->rate[m] = std::max((double) ns / ((double) items[i].chunk * P.E), 0.5 * S->rate[m]);
 		if (items[i].fused) {
 			P.head = P.slot(items[i].chunk);
 			P.count -= items[i].chunk;
 			S->st.children += ns;
-			S->st.nodes += ns;
-			S->st.score_calls += (unsigned long long) ns * (P.E + 2);
+			count_batch(S->st, m + 1, ns);
 			if (S->h_pin[2] > S->trees_cap) {
 				rc = redo_fused(ctx, S, m, ns, S->d_surv_lvl[m], S->d_nsurv_lvl + m, before);
 				if (rc) return rc;
@@ -1365,10 +1240,7 @@ static int dive(xmp_ctx *ctx, Search *S) {
 	for (unsigned m = 3; m < S->n; ++m) S->pool[m].count = S->pool[m].head = 0;
 	// Trees found by the dive will be found again by the search proper.
 	S->ntrees_dev = 0;
-	S->host_trees.clear();
-	S->dropped = 0;
-	S->dropped_score = 0;
-	S->host_bound = 0xffffffffu;
+	S->book.reset();
 	XMP_CUDA(cudaMemsetAsync(S->d_ntrees, 0, sizeof(unsigned), ctx->stream));
 	return fetch_counters(ctx, S);
 }
@@ -1381,6 +1253,30 @@ static void init_knobs(xmp_ctx *ctx, Search *S) {
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
+}
+
+// The two halves of xmp_cuda_search_begin that talk to the device (split out so that every failure takes the same
+// tear-down path in the caller).
+static int begin_bound(xmp_ctx *ctx, Search *S) {
+	XMP_CUDA(cudaMemcpyAsync(S->d_bound, &S->bound, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	return XMP_OK;
+}
+
+static int begin_timed(xmp_ctx *ctx, Search *S) {
+	XMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+	if (!(S->prm.flags & XMP_SEARCH_NO_DIVE)) {
+		int rc = dive(ctx, S);
+		if (rc) return rc;
+	}
+	int rc = push_root(ctx, S);
+	if (rc) return rc;
+	XMP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+	XMP_CUDA(cudaEventSynchronize(ctx->ev1));
+	float ms = 0;
+	XMP_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	S->st.seconds += ms * 1e-3;
+	return XMP_OK;
 }
 
 }  // namespace xmp
@@ -1411,19 +1307,25 @@ extern "C" int xmp_cuda_search_reserve(xmp_ctx *ctx, unsigned num_taxa, unsigned
 extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *params) {
 	if (!ctx || !ctx->d_rows || !params) return set_error(XMP_ERR_ARG, "no problem loaded");
 	if (ctx->num_taxa < 4) return set_error(XMP_ERR_ARG, "the search needs at least four taxa");
+	const unsigned shard_count = params->shard_count ? params->shard_count : 1u;
+	if (params->shard_index >= shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", params->shard_index, shard_count);
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	search_destroy(ctx);
 	Search *S = new Search();
 	ctx->search = S;
 	S->prm = *params;
-	if (S->prm.shard_count == 0) S->prm.shard_count = 1;
-	if (S->prm.shard_index >= S->prm.shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", S->prm.shard_index, S->prm.shard_count);
+	S->prm.shard_count = shard_count;
 	init_knobs(ctx, S);
+	// a search that fails to start leaves no half-built state behind: later calls then report "no search in progress"
+	auto fail = [&](int rc) { search_destroy(ctx); return rc; };
 	int rc = alloc_search(ctx, S, ctx->n_blocks);
-	if (rc) { search_destroy(ctx); return rc; }
+	if (rc) return fail(rc);
+	S->book.trec = S->L.trec;
+	S->book.n = S->L.n;
+	S->book.max_trees = S->prm.max_trees;
 	S->bound = params->bound;
-	XMP_CUDA(cudaMemcpyAsync(S->d_bound, &S->bound, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	rc = begin_bound(ctx, S);
+	if (rc) return fail(rc);
 
 	// Where the frontier is dealt out to shards: the first tree size with >= 64 subtrees per shard.
 	S->split_level = 0;
@@ -1437,18 +1339,8 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 		if (s > S->n - 1) s = S->n - 1;
 		S->split_level = s;
 	}
-	XMP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-	if (!(S->prm.flags & XMP_SEARCH_NO_DIVE)) {
-		rc = dive(ctx, S);
-		if (rc) return rc;
-	}
-	rc = push_root(ctx, S);
-	if (rc) return rc;
-	XMP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-	XMP_CUDA(cudaEventSynchronize(ctx->ev1));
-	float ms = 0;
-	XMP_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-	S->st.seconds += ms * 1e-3;
+	rc = begin_timed(ctx, S);
+	if (rc) return fail(rc);
 	return XMP_OK;
 }
 
@@ -1565,7 +1457,11 @@ extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uin
 	const Layout &L = S->L;
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	*n_jobs = 0;
-	for (unsigned m = 3; m < S->n; ++m) {
+	// A sharded search deals the frontier out by hash when it expands the level below split_level; a node from a
+	// shallower level would be dealt again -- with the thief's index -- on the other side.  So only subtrees that are
+	// past the deal ever change hands (the shallow prefix is a handful of nodes, gone after the first sweeps).
+	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
+	for (unsigned m = m0; m < S->n; ++m) {
 		Pool &P = S->pool[m];
 		if (P.count == 0) continue;
 		// Like the reference's thief (src/mpiworker.c:169-181): take from the shallowest open level.
@@ -1600,6 +1496,7 @@ extern "C" int xmp_cuda_search_import_jobs(xmp_ctx *ctx, const uint8_t *jobs, un
 	for (unsigned j = 0; j < n_jobs; ++j) {
 		unsigned m = jobs[(size_t) j * S->L.n];
 		if (m < 3 || m >= S->n) return set_error(XMP_ERR_ARG, "job %u has tree size %u, expected 3..%u", j, m, S->n - 1);
+		if (S->prm.shard_count > 1 && m < S->split_level) return set_error(XMP_ERR_ARG, "job %u has tree size %u, below the split level %u of this sharded search", j, m, S->split_level);
 	}
 	S->done = false;       // an idle shard that receives stolen work is searching again
 	S->finished = false;
@@ -1613,15 +1510,13 @@ extern "C" int xmp_cuda_search_result(xmp_ctx *ctx, unsigned *score, unsigned lo
 	// Filter here, not when the frontier ran dry: a peer shard may have lowered the bound since.
 	const Layout &L = S->L;
 	unsigned long long count = 0;
-	for (size_t r = 0; r < S->host_trees.size(); r += L.trec) {
-		unsigned sc;
-		memcpy(&sc, S->host_trees.data() + r, 4);
-		if (sc != S->bound) continue;
-		if (paths && count < cap) memcpy(paths + (size_t) count * L.n, S->host_trees.data() + r + 4, L.n);
+	for (size_t r = 0; r < S->book.recs.size(); r += L.trec) {
+		if (S->book.length_of(r) != S->bound) continue;
+		if (paths && count < cap) memcpy(paths + (size_t) count * L.n, S->book.recs.data() + r + 4, L.n);
 		++count;
 	}
 	if (score) *score = S->bound;
-	if (n_trees) *n_trees = optimal_trees(S, nullptr);
+	if (n_trees) *n_trees = S->book.optimal(S->bound, nullptr);
 	return XMP_OK;
 }
 
@@ -1629,7 +1524,7 @@ extern "C" int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored
 	if (!ctx || !ctx->search || !n_stored) return set_error(XMP_ERR_ARG, "no search in progress");
 	Search *S = ctx->search;
 	if (!S->finished) return set_error(XMP_ERR_ARG, "the search has not finished");
-	optimal_trees(S, n_stored);
+	S->book.optimal(S->bound, n_stored);
 	return XMP_OK;
 }
 

@@ -16,6 +16,7 @@ NO_LIMIT = 0x7FFFFFFF
 SEARCH_NO_DIVE = 1
 SEARCH_NO_FUSE = 2
 SEARCH_NO_EAGER = 4
+MAX_TAXA = 100
 
 EXPORTS = [
     "xmp_cuda_last_error", "xmp_cuda_device_count", "xmp_cuda_init", "xmp_cuda_destroy", "xmp_cuda_set_stream",
@@ -28,7 +29,7 @@ EXPORTS = [
     "xmp_cuda_search_reserve", "xmp_cuda_search_begin", "xmp_cuda_search_run", "xmp_cuda_search_get_bound", "xmp_cuda_search_set_bound",
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
     "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
-    "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs", "xmp_cuda_selftest_tree_cap",
+    "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs",
 ]
 
 
@@ -44,10 +45,12 @@ class SearchParams(C.Structure):
 class SearchStats(C.Structure):
     _fields_ = [("nodes", C.c_ulonglong), ("score_calls", C.c_ulonglong), ("children", C.c_ulonglong),
                 ("full_trees", C.c_ulonglong), ("site_merges", C.c_ulonglong), ("launches", C.c_ulonglong),
-                ("iterations", C.c_ulonglong), ("seconds", C.c_double)]
+                ("iterations", C.c_ulonglong), ("seconds", C.c_double),
+                ("nodes_by_depth", C.c_ulonglong * (MAX_TAXA + 1)), ("edge_evals_by_depth", C.c_ulonglong * (MAX_TAXA + 1)),
+                ("batches_by_depth", C.c_ulonglong * (MAX_TAXA + 1))]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k.endswith("_by_depth") else getattr(self, k)) for k, _ in self._fields_}
 
 
 def lib():
@@ -82,7 +85,6 @@ def lib():
         L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
         L.xmp_cuda_search_stored.argtypes = [vp, C.POINTER(C.c_ulonglong)]
         L.xmp_cuda_paths_keep_first_dfs.argtypes = [vp, sz, u, sz]
-        L.xmp_cuda_selftest_tree_cap.argtypes = [vp, vp, vp, u, u, u, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), vp, sz]
         L.xmp_cuda_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
         for name in ("FitchBases_b2_w16_cuda",):
             getattr(L, name).restype = None
