@@ -6,8 +6,8 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --use_fast_math
 CFLAGS    := -O3 -mpopcnt -std=c99 -D_POSIX_C_SOURCE=200809L -Wall -Wextra -fPIC
 
-CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu xmp_b200/csrc/microbench.cu
-CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh xmp_b200/csrc/child_walk.cuh xmp_b200/csrc/walk_prog.h include/xmp_cuda.h
+CUDA_SRCS := xmp_b200/csrc/api.cu xmp_b200/csrc/kernels.cu xmp_b200/csrc/search.cu xmp_b200/csrc/exchange.cu xmp_b200/csrc/microbench.cu
+CUDA_HDRS := xmp_b200/csrc/ctx.h xmp_b200/csrc/fitch_dev.cuh xmp_b200/csrc/child_walk.cuh xmp_b200/csrc/walk_prog.h xmp_b200/csrc/tree_book.h xmp_b200/csrc/exchange_proto.h include/xmp_cuda.h
 HOST_SRCS := host/phylip.c host/prep.c host/trees.c host/partbound.c
 
 .PHONY: all host cuda cli oracle ref checks clean

@@ -247,24 +247,22 @@ static void save_reordered(const xmph_problem *p) {
 }
 
 /* ---- the search across GPUs -------------------------------------------------------------------- */
-/* Replaces Boss()/Worker() (reference src/mpiboss.c:30-429, src/mpiworker.c:214-380).  There is no
- * boss: every GPU searches.  Shards start from a hashed deal of the frontier at a shallow tree size
- * (the library's shard_index/shard_count), then
- *   - the upper bound is a shared word: after every slice of batches a worker folds its own bound in
- *     and adopts the minimum (the reference relays MSG_NEWBOUND through the boss, src/mpiboss.c:162-171);
- *   - a worker that runs dry asks for work; busy workers then detach open subtrees from their shallowest
- *     level as job descriptors into a mailbox (the reference's "steal the last edge at the shallowest
- *     level", src/mpiworker.c:169-181), and the idle worker replays them (src/yanbader.c:136-143);
- *   - the search ends when every worker is idle and the mailbox is empty. */
+/* Replaces Boss()/Worker() (reference src/mpiboss.c:30-429, src/mpiworker.c:214-380).  There is no boss: every GPU
+ * searches, one host thread each.  Shards start from a hashed deal of the frontier at a shallow tree size (the
+ * library's shard_index/shard_count); everything the GPUs tell each other afterwards goes through their exchange
+ * blocks in peer-mapped device memory (include/xmp_cuda.h 2d):
+ *   - the upper bound: the kernel that finds a better tree lowers every GPU's bound word itself (the reference relays
+ *     MSG_NEWBOUND through the boss, src/mpiboss.c:162-171);
+ *   - a GPU that runs dry asks one peer, which detaches open subtrees from its shallowest level (the reference's
+ *     "steal the last edge at the shallowest level", src/mpiworker.c:169-181) into the thief's mailbox;
+ *   - the search ends when no GPU holds work (xmp_cuda_search_steal reports it).
+ * What the threads share on the host is only what the user sees: the best length for --displaynewbounds and the
+ * progress report. */
 typedef struct {
 	pthread_mutex_t mu;
-	pthread_cond_t cv;
+	pthread_barrier_t start;   /* every exchange block is reset before any search begins */
 	unsigned bound;
-	unsigned n_workers, n_idle;
-	int finished, failed;
-	unsigned char *mail;       /* job descriptors, num_taxa bytes each */
-	unsigned n_mail, cap_mail;
-	char err[512];
+	unsigned n_workers;
 	int display_bounds;
 	/* progress reports (--updatesecs, reference src/yanbader.c:28-44, src/common.c:525-541) */
 	unsigned update_secs;
@@ -278,22 +276,16 @@ typedef struct {
 	const cli *c;
 	unsigned index;
 	xmp_ctx *ctx;
-	unsigned char *paths;
-	unsigned long long n_trees;
-	unsigned score;
-	xmp_search_stats stats;
+	xmp_ctx **all;             /* every worker's context (for the exchange) */
 } worker;
 
 #define SLICE_BATCHES 8
-#define STEAL_NODES 256
 
+/* A failing GPU cannot be waited for by the others (they would wait for its share of the work): fatal, like every
+ * error of the reference. */
 static void worker_fail(worker *w, const char *what) {
-	shared_state *sh = w->sh;
-	pthread_mutex_lock(&sh->mu);
-	if (!sh->failed) snprintf(sh->err, sizeof sh->err, "GPU %u: %s: %s", w->index, what, xmp_cuda_last_error());
-	sh->failed = sh->finished = 1;
-	pthread_cond_broadcast(&sh->cv);
-	pthread_mutex_unlock(&sh->mu);
+	fprintf(stderr, "GPU %u: %s: %s\n", w->index, what, xmp_cuda_last_error());
+	exit(1);
 }
 
 /* The reference reports the share of the search space its depth-first walk has left behind.  A frontier search knows
@@ -328,83 +320,51 @@ static void *worker_main(void *arg) {
 	shared_state *sh = w->sh;
 	const xmph_problem *p = w->p;
 	xmp_search_params prm;
-	unsigned char *jobs = (unsigned char *) malloc((size_t) STEAL_NODES * p->num_taxa);
 	int done = 0;
 
-	if (xmp_cuda_load(w->ctx, p->rows, p->weights, p->num_taxa, p->n_blocks, p->rest_bound, p->constant_weight)) { worker_fail(w, "uploading the problem"); return NULL; }
+	if (xmp_cuda_load(w->ctx, p->rows, p->weights, p->num_taxa, p->n_blocks, p->rest_bound, p->constant_weight)) worker_fail(w, "uploading the problem");
+	if (sh->n_workers > 1) {
+		if (xmp_cuda_exchange_connect_local(w->ctx, w->index, sh->n_workers, w->all)) worker_fail(w, "connecting the GPUs");
+		if (xmp_cuda_exchange_reset(w->ctx)) worker_fail(w, "resetting the exchange");
+		pthread_barrier_wait(&sh->start);
+	}
 	memset(&prm, 0, sizeof prm);
 	prm.bound = p->bound;
 	prm.max_trees = w->c->s.max_trees;
 	prm.mem_budget = w->c->mem_budget;
 	prm.shard_index = w->index;
 	prm.shard_count = sh->n_workers;
-	if (xmp_cuda_search_begin(w->ctx, &prm)) { worker_fail(w, "starting the search"); return NULL; }
+	if (xmp_cuda_search_begin(w->ctx, &prm)) worker_fail(w, "starting the search");
 
 	for (;;) {
-		unsigned mine = 0, global;
-		/* slices give the other GPUs (and --displaynewbounds) a chance to see a new bound; a single GPU with
-		 * nothing to report runs straight through */
-		const unsigned slice = (sh->n_workers > 1 || sh->display_bounds || sh->update_secs) ? SLICE_BATCHES : 0;
-		if (!done && xmp_cuda_search_run(w->ctx, slice, &done)) { worker_fail(w, "searching"); break; }
-		if (xmp_cuda_search_get_bound(w->ctx, &mine)) { worker_fail(w, "reading the bound"); break; }
+		unsigned mine = 0;
+		/* slices only serve the user (--displaynewbounds, progress reports): the GPUs need no host round to learn a
+		 * new bound or to hand over work */
+		const unsigned slice = (sh->display_bounds || sh->update_secs) ? SLICE_BATCHES : 0;
+		if (!done && xmp_cuda_search_run(w->ctx, slice, &done)) worker_fail(w, "searching");
+		if (xmp_cuda_search_get_bound(w->ctx, &mine)) worker_fail(w, "reading the bound");
 		report_progress(w, mine);
-
 		pthread_mutex_lock(&sh->mu);
 		if (mine < sh->bound) {
 			sh->bound = mine;
 			if (sh->display_bounds) fprintf(stderr, "New bound = %u\n", mine);
 		}
-		global = sh->bound;
-		int give = !done && sh->n_idle > 0 && sh->n_mail == 0;
-		int stop = sh->finished;
 		pthread_mutex_unlock(&sh->mu);
-		if (stop) break;
-		if (global < mine && xmp_cuda_search_set_bound(w->ctx, global)) { worker_fail(w, "lowering the bound"); break; }
-
-		if (give) {
-			unsigned n = 0;
-			if (xmp_cuda_search_export_jobs(w->ctx, STEAL_NODES, jobs, &n)) { worker_fail(w, "exporting jobs"); break; }
-			if (n) {
-				pthread_mutex_lock(&sh->mu);
-				if (sh->n_mail + n > sh->cap_mail) {
-					sh->cap_mail = (sh->n_mail + n) * 2;
-					sh->mail = (unsigned char *) realloc(sh->mail, (size_t) sh->cap_mail * p->num_taxa);
-				}
-				memcpy(sh->mail + (size_t) sh->n_mail * p->num_taxa, jobs, (size_t) n * p->num_taxa);
-				sh->n_mail += n;
-				pthread_cond_broadcast(&sh->cv);
-				pthread_mutex_unlock(&sh->mu);
-			}
-		}
 		if (!done) continue;
-
-		/* Out of work: wait for jobs or for everybody to be idle. */
-		unsigned n = 0;
-		pthread_mutex_lock(&sh->mu);
-		++sh->n_idle;
-		while (!sh->finished && sh->n_mail == 0) {
-			if (sh->n_idle == sh->n_workers) {
-				sh->finished = 1;
-				pthread_cond_broadcast(&sh->cv);
-				break;
-			}
-			pthread_cond_wait(&sh->cv, &sh->mu);
-		}
-		if (!sh->finished && sh->n_mail) {
-			/* Take a fair share of the mailbox. */
-			n = (sh->n_mail + sh->n_idle - 1) / sh->n_idle;
-			if (n > STEAL_NODES) n = STEAL_NODES;
-			memcpy(jobs, sh->mail + (size_t) (sh->n_mail - n) * p->num_taxa, (size_t) n * p->num_taxa);
-			sh->n_mail -= n;
-			--sh->n_idle;
-		}
-		stop = sh->finished;
-		pthread_mutex_unlock(&sh->mu);
-		if (stop) break;
-		if (xmp_cuda_search_import_jobs(w->ctx, jobs, n)) { worker_fail(w, "importing jobs"); break; }
+		/* Out of work: ask a peer, or learn that everybody is done. */
+		int state = 0;
+		if (xmp_cuda_search_steal(w->ctx, &state)) worker_fail(w, "asking for work");
+		if (state != XMP_STEAL_GOT_WORK) break;
 		done = 0;
 	}
-	free(jobs);
+	unsigned mine = 0;
+	if (xmp_cuda_search_get_bound(w->ctx, &mine)) worker_fail(w, "reading the bound");
+	pthread_mutex_lock(&sh->mu);
+	if (mine < sh->bound) {
+		sh->bound = mine;
+		if (sh->display_bounds) fprintf(stderr, "New bound = %u\n", mine);
+	}
+	pthread_mutex_unlock(&sh->mu);
 	return NULL;
 }
 
@@ -472,30 +432,34 @@ int main(int argc, char **argv) {
 	shared_state sh;
 	memset(&sh, 0, sizeof sh);
 	pthread_mutex_init(&sh.mu, NULL);
-	pthread_cond_init(&sh.cv, NULL);
+	pthread_barrier_init(&sh.start, NULL, c.n_gpus);
 	sh.bound = p.bound;
 	sh.n_workers = c.n_gpus;
 	sh.display_bounds = (c.s.options & XMPH_OPT_DISPLAYNEWBOUNDS) != 0;
 	sh.update_secs = (c.s.options & XMPH_OPT_QUIET) ? 0 : c.update_secs;
 	worker *ws = (worker *) calloc(c.n_gpus, sizeof(worker));
 	pthread_t *th = (pthread_t *) calloc(c.n_gpus, sizeof(pthread_t));
+	xmp_ctx **all = (xmp_ctx **) calloc(c.n_gpus, sizeof(xmp_ctx *));
 
-	/* Device contexts and the search's device memory are set up before the clock starts, like the
-	 * reference's arena (InitTreeData, src/common.c:1113-1224); the upload of the problem is inside the
-	 * timed search. */
+	/* Device contexts, the search's device memory and the exchange blocks are set up before the clock starts, like
+	 * the reference's arena (InitTreeData, src/common.c:1113-1224) and its MPI_Init; the upload of the problem is
+	 * inside the timed search. */
 	for (unsigned g = 0; g < c.n_gpus; ++g) {
+		unsigned char handle[XMP_EXCHANGE_HANDLE_BYTES];
 		ws[g].sh = &sh;
 		ws[g].p = &p;
 		ws[g].c = &c;
 		ws[g].index = g;
+		ws[g].all = all;
 		if (xmp_cuda_init((int) g, &ws[g].ctx)) die(xmp_cuda_last_error());
+		all[g] = ws[g].ctx;
 		if (xmp_cuda_search_reserve(ws[g].ctx, p.num_taxa, p.n_blocks, c.mem_budget)) die(xmp_cuda_last_error());
+		if (c.n_gpus > 1 && xmp_cuda_exchange_handle(ws[g].ctx, handle)) die(xmp_cuda_last_error());
 	}
 	t_search = now_seconds();
 	sh.t_start = sh.t_last_update = t_search;
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_create(&th[g], NULL, worker_main, &ws[g]);
 	for (unsigned g = 0; g < c.n_gpus; ++g) pthread_join(th[g], NULL);
-	if (sh.failed) die(sh.err);
 
 	/* Gather: every shard reports the trees it holds at the final bound. */
 	unsigned char *paths = NULL;
@@ -522,6 +486,8 @@ int main(int argc, char **argv) {
 		total.site_merges += st.site_merges;
 		total.launches += st.launches;
 		total.iterations += st.iterations;
+		total.steals_served += st.steals_served;
+		total.steals_received += st.steals_received;
 		for (unsigned m = 0; m <= XMP_MAX_TAXA; ++m) {
 			total.nodes_by_depth[m] += st.nodes_by_depth[m];
 			total.edge_evals_by_depth[m] += st.edge_evals_by_depth[m];
@@ -549,6 +515,7 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "Number of full trees considered:%20llu\n", total.full_trees);
 		fprintf(stderr, "Site merges                     %20llu (%.3f G/s)\n", total.site_merges, dt > 0 ? (double) total.site_merges / dt * 1e-9 : 0.0);
 		fprintf(stderr, "Kernel launches / batches       %20llu / %llu\n", total.launches, total.iterations);
+		if (c.n_gpus > 1) fprintf(stderr, "Steals served / received        %20llu / %llu\n", total.steals_served, total.steals_received);
 		/* the reference's per-depth counters (src/measure.c:10,79: bAndBScanEdgeCountByDepth[]), by taxa on the tree */
 		for (unsigned m = 3; m <= XMP_MAX_TAXA; ++m) {
 			if (!total.edge_evals_by_depth[m]) continue;
@@ -565,7 +532,7 @@ int main(int argc, char **argv) {
 	}
 	for (unsigned g = 0; g < c.n_gpus; ++g) xmp_cuda_destroy(ws[g].ctx);
 	free(paths);
-	free(sh.mail);
+	free(all);
 	free(ws);
 	free(th);
 	xmph_free_problem(&p);

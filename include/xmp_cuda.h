@@ -148,6 +148,8 @@ typedef struct {
 	unsigned long long nodes_by_depth[XMP_MAX_TAXA + 1];       /* partial trees on m taxa expanded */
 	unsigned long long edge_evals_by_depth[XMP_MAX_TAXA + 1];  /* (tree, edge) pairs scored on trees of m taxa */
 	unsigned long long batches_by_depth[XMP_MAX_TAXA + 1];     /* frontier batches (launch groups) at tree size m */
+	unsigned long long steals_served;  /* steal requests of other ranks answered with work (reference: stealCount) */
+	unsigned long long steals_received; /* times this rank ran dry and obtained work from a peer */
 } xmp_search_stats;
 
 /* Optional: allocate the search's device memory for a problem of this shape now (mem_budget as in
@@ -179,6 +181,36 @@ int xmp_cuda_search_stored(xmp_ctx *ctx, unsigned long long *n_stored);
  * in the reference's depth-first order (src/yanbader.c:103,238-243) to the front, in that order. */
 int xmp_cuda_paths_keep_first_dfs(uint8_t *paths, size_t n_paths, unsigned num_taxa, size_t keep);
 int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2d) several GPUs of one node on one search.  Replaces the reference's MPI boss / worker pair
+ *      (src/mpiboss.c:30-429, src/mpiworker.c:19-41,117-181,214-380) by words in peer-mapped DEVICE memory:
+ *      every context owns an exchange block that the other ranks' GPUs address over NVLink.
+ *        - the upper bound: the search kernels lower the bound word of every peer with a system-scope atomicMin
+ *          in the launch that finds a better tree (the reference relays MSG_NEWBOUND through the boss);
+ *        - work stealing: a rank whose frontier ran dry asks ONE peer (a compare-and-swap on that peer's request
+ *          word); the donor answers between two sweeps of its own search by copying job descriptors (insertion
+ *          paths) into the thief's mailbox, device to device.  No collective, no lock step;
+ *        - termination: a counter of ranks that hold work; whoever brings it to zero raises every rank's flag.
+ *      Use: shard the search with shard_index / shard_count = rank / world as before, and
+ *          xmp_cuda_exchange_handle   on every rank; exchange the 64-byte handles (any side channel),
+ *          xmp_cuda_exchange_connect  (ranks are processes: CUDA IPC) or _connect_local (ranks are threads),
+ *          xmp_cuda_exchange_reset    before every search, then a barrier of your own, then xmp_cuda_search_begin;
+ *          loop { xmp_cuda_search_run(ctx, 0, &done); xmp_cuda_search_steal(ctx, &state); } until state is
+ *          XMP_STEAL_FINISHED; then xmp_cuda_search_result on every rank (each tree is held by exactly one).
+ *      A context that is not connected behaves as before (one rank).
+ * ---------------------------------------------------------------------------------------------- */
+#define XMP_EXCHANGE_HANDLE_BYTES 64
+#define XMP_STEAL_GOT_WORK 1
+#define XMP_STEAL_FINISHED 2
+int xmp_cuda_exchange_handle(xmp_ctx *ctx, unsigned char *handle /* [XMP_EXCHANGE_HANDLE_BYTES] */);
+int xmp_cuda_exchange_connect(xmp_ctx *ctx, unsigned rank, unsigned world, const unsigned char *handles /* [world][64] */);
+int xmp_cuda_exchange_connect_local(xmp_ctx *ctx, unsigned rank, unsigned world, xmp_ctx *const *peers /* [world] */);
+int xmp_cuda_exchange_disconnect(xmp_ctx *ctx);
+int xmp_cuda_exchange_reset(xmp_ctx *ctx);
+/* Call when xmp_cuda_search_run reported done: waits until a peer hands over open subtrees (*state =
+ * XMP_STEAL_GOT_WORK: call xmp_cuda_search_run again) or until no rank holds work (XMP_STEAL_FINISHED). */
+int xmp_cuda_search_steal(xmp_ctx *ctx, int *state);
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement aid: what the integer pipe sustains on the Fitch instruction mixes with operands in

@@ -42,23 +42,25 @@ def main():
         p = xh.Problem(a)
         ctx = xc.Context(local)
         ctx.load_problem(p)
+        connected = xd.connect_exchange(ctx, dev)
         dist.barrier()
         t0 = time.perf_counter()
-        ctx.search_begin(bound=p.bound, shard_index=rank, shard_count=world)
-        log = []
-        score, total, paths, rounds = xd.sharded_search(ctx, p.num_taxa, dev, on_round=lambda r, c, b: log.append(c))
+        score, total, paths, info = xd.sharded_search(ctx, p.num_taxa, dev, begin={"bound": p.bound}, connected=connected)
         wall = time.perf_counter() - t0
         allpaths = xd.gather_paths(paths, p.num_taxa, dev)
         st = ctx.search_stats()
+        xd.disconnect_exchange(ctx)
         ctx.close()
         canon = sorted(canonical_newick(t) for t in p.newick_list(allpaths))
         blob = ("\n".join(canon) + "\n").encode() if canon else b""
         good = (score == g["score"] and total == g["num_trees"] == len(allpaths)
                 and hashlib.sha256(blob).hexdigest() == g["canonical_sha256"])
+        if os.environ.get("XMP_REQUIRE_PEER") and info["transport"] != "peer":
+            good = False
         ok &= good
-        print("rank %d %s: %s score %d trees %d (mine %d) %.3f s, %d rounds, %d nodes here, steals seen %d" %
-              (rank, name, "OK" if good else "MISMATCH", score, total, len(paths), wall, rounds, st["nodes"],
-               sum(1 for c in log if 0 in c and sum(c) > 0)), flush=True)
+        print("rank %d %s: %s score %d trees %d (mine %d) %.3f s, transport %s, %d waits, %d nodes here, steals served %d received %d" %
+              (rank, name, "OK" if good else "MISMATCH", score, total, len(paths), wall, info["transport"], info["rounds"], st["nodes"],
+               st["steals_served"], st["steals_received"]), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

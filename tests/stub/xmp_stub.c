@@ -15,26 +15,15 @@
 #include "xmp_cuda.h"
 #include "oracle.h"
 
-struct xmp_ctx {
-	int device;
-	unsigned n, n_blocks, constant_weight;
-	uint8_t *rows;
-	unsigned *weights, *rest_bound, *taxon_map;
-	unsigned bound;
-	uint8_t *jobs;            /* n bytes each, byte 0 = tree size */
-	size_t n_jobs, cap_jobs, head;
-	uint8_t *trees;           /* n bytes each, all of length `bound` */
-	size_t n_trees, cap_trees;
-	xmp_search_stats st;
-	int begun;
-};
+#include "xmp_stub.h"
 
 static char g_err[256] = "";
 const char *xmp_cuda_last_error(void) { return g_err; }
-static int fail(int code, const char *msg) {
+int stub_fail(int code, const char *msg) {
 	snprintf(g_err, sizeof g_err, "%s", msg);
 	return code;
 }
+#define fail stub_fail
 int xmp_cuda_device_count(void) {
 	const char *e = getenv("XMP_STUB_DEVICES");
 	return e ? atoi(e) : 1;
@@ -47,7 +36,7 @@ int xmp_cuda_init(int device, xmp_ctx **out) {
 }
 void xmp_cuda_destroy(xmp_ctx *c) {
 	if (!c) return;
-	free(c->rows); free(c->weights); free(c->rest_bound); free(c->taxon_map); free(c->jobs); free(c->trees);
+	free(c->rows); free(c->weights); free(c->rest_bound); free(c->taxon_map); free(c->jobs); free(c->trees); free(c->staged);
 	free(c);
 }
 int xmp_cuda_search_reserve(xmp_ctx *c, unsigned num_taxa, unsigned n_blocks, size_t mem_budget) {
@@ -71,7 +60,8 @@ int xmp_cuda_load(xmp_ctx *c, const void *rows, const unsigned *weights, unsigne
 	for (unsigned i = 0; i < num_taxa; ++i) c->taxon_map[i] = i;
 	return XMP_OK;
 }
-static void push_job(xmp_ctx *c, const uint8_t *path, unsigned m) {
+#define push_job stub_push_job
+void stub_push_job(xmp_ctx *c, const uint8_t *path, unsigned m) {
 	if (c->n_jobs == c->cap_jobs) {
 		c->cap_jobs = c->cap_jobs ? 2 * c->cap_jobs : 256;
 		c->jobs = (uint8_t *) realloc(c->jobs, c->cap_jobs * c->n);
@@ -107,6 +97,8 @@ int xmp_cuda_search_begin(xmp_ctx *c, const xmp_search_params *prm) {
 		if (L == 3 || t == 0) break;
 	}
 	c->begun = 1;
+	c->steals_served = c->steals_received = 0;
+	if (c->xch_connected) stub_xch_bound_local(c, c->bound);
 	return XMP_OK;
 }
 int xmp_cuda_search_run(xmp_ctx *c, unsigned max_batches, int *done) {
@@ -114,6 +106,10 @@ int xmp_cuda_search_run(xmp_ctx *c, unsigned max_batches, int *done) {
 	unsigned batches = 0;
 	while (c->n_jobs > c->head && (max_batches == 0 || batches < max_batches)) {
 		uint8_t path[XMP_MAX_TAXA + 1];
+		if (c->xch_connected) {                       /* what the kernels do: read the (peer-lowered) bound word per launch */
+			const unsigned b = stub_xch_bound_in(c);
+			if (b < c->bound) { c->bound = b; c->n_trees = 0; }
+		}
 		memcpy(path, c->jobs + --c->n_jobs * c->n, c->n);
 		const unsigned m = path[0];
 		path[0] = 0;
@@ -124,6 +120,7 @@ int xmp_cuda_search_run(xmp_ctx *c, unsigned max_batches, int *done) {
 		if (r.score < c->bound) {
 			c->bound = r.score;
 			c->n_trees = 0;
+			if (c->xch_connected) stub_xch_bound_out(c, r.score);
 		}
 		const size_t k = r.paths_len / c->n;
 		if (k && r.score == c->bound) {
@@ -140,6 +137,7 @@ int xmp_cuda_search_run(xmp_ctx *c, unsigned max_batches, int *done) {
 		c->st.iterations += 1;
 		xo_result_free(&r);
 		++batches;
+		if (c->xch_connected && stub_xch_after_job(c)) return fail(XMP_ERR_ARG, "exchange failed");
 	}
 	if (done) *done = c->n_jobs == c->head;
 	return XMP_OK;
@@ -174,4 +172,9 @@ int xmp_cuda_search_result(xmp_ctx *c, unsigned *score, unsigned long long *n_tr
 	return XMP_OK;
 }
 int xmp_cuda_search_stored(xmp_ctx *c, unsigned long long *n_stored) { *n_stored = c->n_trees; return XMP_OK; }
-int xmp_cuda_search_stats(xmp_ctx *c, xmp_search_stats *out) { *out = c->st; return XMP_OK; }
+int xmp_cuda_search_stats(xmp_ctx *c, xmp_search_stats *out) {
+	*out = c->st;
+	out->steals_served = c->steals_served;
+	out->steals_received = c->steals_received;
+	return XMP_OK;
+}

@@ -271,16 +271,24 @@ def test_command_line_fuzz_against_the_compiled_reference(alignment_dir, tmp_pat
 
 
 # ---- the command line end to end on the CPU, over a test double of the device library ------------------------------
+def build_stub(d, extra=()):
+    """tests/stub: the entry points host/fastdnamp.c calls, on top of the oracle's subtree search, plus the exchange
+    entry points running the product's protocol source (xmp_b200/csrc/exchange_proto.h) over host memory.  Test
+    infrastructure; the product never loads it."""
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"), "-I" + os.path.join(ROOT, "tests", "stub")]
+    subprocess.run(["gcc", "-O2", "-std=c99", "-fPIC", "-c", *extra, *inc, "-o", str(d / "xmp_stub.o"), os.path.join(ROOT, "tests", "stub", "xmp_stub.c")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-c", *extra, *inc, "-o", str(d / "xmp_stub_exchange.o"),
+                    os.path.join(ROOT, "tests", "stub", "xmp_stub_exchange.cpp")], check=True)
+    subprocess.run(["g++", "-shared", *extra, "-o", str(d / "libxmp_b200.so"), str(d / "xmp_stub.o"), str(d / "xmp_stub_exchange.o"),
+                    "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-lpthread"], check=True)
+    return d
+
+
 @pytest.fixture(scope="module")
 def stub_dir(tmp_path_factory):
-    """tests/stub/xmp_stub.c: the entry points host/fastdnamp.c calls, on top of the oracle's subtree search (test
-    infrastructure; the product never loads it).  Lets the host program's own logic run here: scheduler threads,
-    shared bound, job mailbox, gather, depth-first sort, -m cap, writers, final report."""
-    d = tmp_path_factory.mktemp("stub")
-    subprocess.run(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
-                    "-o", str(d / "libxmp_b200.so"), os.path.join(ROOT, "tests", "stub", "xmp_stub.c"),
-                    "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
-    return d
+    """Lets the host program's own logic run here: scheduler threads over the exchange protocol (shared bound, steal
+    requests, termination), gather, depth-first sort, -m cap, writers, final report."""
+    return build_stub(tmp_path_factory.mktemp("stub"))
 
 
 def _run_over_stub(stub_dir, exe, args, cwd, devices=1, skew=False):
@@ -305,7 +313,8 @@ def test_whole_program_over_the_test_double(stub_dir, alignment_dir, goldens, tm
     import re
     assert re.search(r"Optimal trees found:\s+%d\n" % g["num_trees"], r.stderr) and "Time to perform branch and bound search:" in r.stderr
     if skew:
-        assert r.stderr.count("imports") >= 3                  # the idle shards were fed
+        assert r.stderr.count("imports") >= 1                  # idle shards were fed (how many depends on how long the search lasts)
+        assert re.search(r"Steals served / received\s+[1-9]\d* / [1-9]", r.stderr)
     # raw format, quiet, capped: the reference's first trees in its order, nothing on stderr but the test double's log
     r = _run_over_stub(stub_dir, EXE, ["-q", "-r", "-m", "3", str(alignment_dir / g["alignment"])], tmp_path, devices, skew)
     want = [l.split("] ")[1] for l in golden_output(name).decode().splitlines() if "TREE FASTDNAMP_" in l][:3]
@@ -319,6 +328,11 @@ def test_scheduler_threads_under_thread_sanitizer(stub_dir, alignment_dir, golde
     from tests.conftest import golden_output
     exe = str(tmp_path / "cli_tsan")
     src = [os.path.join(ROOT, "host", f) for f in ("fastdnamp.c", "phylip.c", "prep.c", "trees.c", "partbound.c")]
+    try:
+        # the test double is instrumented too: the exchange protocol (steal requests, replies, the busy counter) runs in it
+        stub_dir = build_stub(tmp_path, extra=("-fsanitize=thread", "-g"))
+    except subprocess.CalledProcessError:
+        pytest.skip("no thread sanitizer runtime here")
     c = subprocess.run(["gcc", "-O1", "-g", "-mpopcnt", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-fsanitize=thread", "-o", exe] + src +
                        ["-I" + os.path.join(ROOT, "host"), "-I" + os.path.join(ROOT, "include"), "-L" + str(stub_dir), "-lxmp_b200", "-lpthread"],
                        capture_output=True, text=True)

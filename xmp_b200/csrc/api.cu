@@ -150,6 +150,7 @@ extern "C" void xmp_cuda_destroy(xmp_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	search_destroy(ctx);
 	free_problem(ctx);
+	xch_release(ctx);
 	if (ctx->arena) cudaFree(ctx->arena);
 	if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
 	ctx->scratch.release();

@@ -20,6 +20,18 @@ int cuda_failed(cudaError_t e, const char *what, const char *file, int line);
 
 struct Search;
 
+// The exchange block of a context: 256 KiB of device memory that peers can map (exchange.cu, exchange_proto.h).
+//   [0, 1024)      the search's counter block; word 0 is the upper bound, words 112-119 the protocol's control words
+//   [1024, 1280)   XchPeerTable: every rank's block as THIS device addresses it (read by the kernels and by k_xch_gather)
+//   [2048, ...)    mailbox: job descriptors (insertion paths) written by a donor over NVLink
+struct XchPeerTable {
+	unsigned *blk[16];
+	unsigned world, rank;
+};
+#define XCH_BLOCK_BYTES ((size_t) 256 << 10)
+#define XCH_TABLE_OFF 1024
+#define XCH_MAILBOX_BYTE_OFF 2048
+
 // Grow-only device scratch buffer.
 struct Scratch {
 	void *ptr = nullptr;
@@ -67,6 +79,14 @@ struct xmp_ctx {
 	void *arena = nullptr;         // the search's device memory (frontier pools, survivor lists, tree buffers), kept between searches
 	size_t arena_bytes = 0;
 	unsigned *h_pin = nullptr;     // pinned scalars the search polls
+
+	// multi-GPU exchange (exchange.cu)
+	unsigned *xch = nullptr;               // this context's exchange block (device memory, cudaMalloc'ed on first use)
+	unsigned xch_rank = 0, xch_world = 1;
+	unsigned *xch_peer[16] = {nullptr};    // every rank's block as this device sees it (own included)
+	bool xch_ipc[16] = {false};            // mapped with cudaIpcOpenMemHandle (closed on disconnect)
+	bool xch_connected = false;
+	unsigned *h_xres = nullptr;            // pinned: results of control operations, the published hint
 };
 
 namespace xmp {
@@ -86,4 +106,7 @@ int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride,
 int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
                             unsigned taxon, unsigned *d_cost);
 void search_destroy(xmp_ctx *ctx);
+// exchange.cu
+int xch_ensure_block(xmp_ctx *ctx);
+void xch_release(xmp_ctx *ctx);
 }  // namespace xmp

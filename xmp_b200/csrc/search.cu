@@ -38,6 +38,7 @@
 #include "walk_prog.h"
 #include "child_walk.cuh"
 #include "tree_book.h"
+#include "exchange_proto.h"
 
 namespace xmp {
 
@@ -60,6 +61,18 @@ __device__ __forceinline__ void emit_tree(uint8_t *rec, const Layout &L, const u
 	}
 }
 
+// A better complete tree was found: lower this GPU's bound word and, if that really lowered it, every peer's
+// (system-scope atomics on peer-mapped memory, exchange.cu).  Replaces the reference's MSG_NEWBOUND relay through
+// the boss (src/yanbader.c:200-211, src/mpiboss.c:162-171, src/mpiworker.c:19-41).  Improvements are rare -- a handful
+// per search -- so the peer traffic is a few words; what matters is that no host is in the path.
+__device__ __forceinline__ void lower_bound(unsigned *bound_ptr, unsigned v, const XchPeerTable *pt) {
+	if (atomicMin(bound_ptr, v) > v && pt) {
+		const unsigned world = pt->world, me = pt->rank;
+		for (unsigned r = 0; r < world; ++r)
+			if (r != me) atomicMin_system(pt->blk[r], v);          // word 0 of a block is its bound
+	}
+}
+
 __device__ __forceinline__ unsigned path_hash(const unsigned *h, unsigned m, unsigned e) {
 	unsigned x = 2166136261u;
 	for (unsigned t = 3; t < m; ++t) x = (x ^ path_byte(h, t)) * 16777619u;
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(256)
 k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes,
                const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned rest, unsigned *bound_ptr, int last,
                uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
-               unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
+               unsigned trees_cap, unsigned shard_count, unsigned shard_index, const XchPeerTable *peers) {
 	__shared__ unsigned s_bound, s_warp[9];
 	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
 	const unsigned E = 2 * m - 3, ts = L.ts_shift, tmask = (1u << ts) - 1u;
@@ -110,7 +123,7 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 		if (keep && shard_count > 1) keep = (path_hash(hdr, m, prog_edge(hdr[(L.off_prog + pos) * 32u])) % shard_count) == shard_index;
 	}
 	if (last) {
-		if (keep && new_score < s_bound) atomicMin(bound_ptr, new_score);
+		if (keep && new_score < s_bound) lower_bound(bound_ptr, new_score, peers);
 		unsigned slot = block_append(keep, n_trees, s_warp);
 		if (keep && slot < trees_cap) {
 			emit_tree(trees + (size_t) slot * L.trec, L, hdr, new_score, m, prog_edge(hdr[(L.off_prog + pos) * 32u]), 0u, false);
@@ -131,7 +144,7 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes, unsigned rest,
          unsigned *bound_ptr, int last, uint4 *__restrict__ surv, unsigned *n_surv, uint8_t *__restrict__ trees, unsigned *n_trees,
-         unsigned trees_cap, unsigned shard_count, unsigned shard_index) {
+         unsigned trees_cap, unsigned shard_count, unsigned shard_index, const XchPeerTable *peers) {
 	__shared__ unsigned s_bound, s_warp[8], s_base;
 	if (threadIdx.x == 0) s_bound = *(volatile unsigned *) bound_ptr;   // one read of the hot word per CTA
 	const unsigned E = 2 * m - 3, tile_pairs = E * 32u;
@@ -168,7 +181,7 @@ k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned
 			best = min(best, score[i] + cost[i]);
 		}
 	}
-	if (last && best < bound) atomicMin(bound_ptr, best);
+	if (last && best < bound) lower_bound(bound_ptr, best, peers);
 	// place in the list: exclusive scan of the per-thread counts over the CTA, one atomic per CTA
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cnt = (unsigned) __popc(mask);
 	unsigned incl = cnt;
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
                     unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
                     unsigned *bound_ptr, uint8_t *__restrict__ trees, unsigned *n_trees, unsigned trees_cap,
-                    unsigned long long *merges, unsigned D, unsigned *overflow_flag) {
+                    unsigned long long *merges, unsigned D, unsigned *overflow_flag, const XchPeerTable *peers) {
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
@@ -459,7 +472,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
 			if (sub == 0 && accept_insertion(c, bound, score, rest_last)) {
-				if (score + c < bound) atomicMin(bound_ptr, score + c);
+				if (score + c < bound) lower_bound(bound_ptr, score + c, peers);
 				const unsigned slot = atomicAdd(n_trees, 1u);
 				if (slot < trees_cap) {
 					emit_tree(trees + (size_t) slot * L.trec, L, ph, score + c, m, cw.sp.xv, prog_edge(wj), true);
@@ -540,11 +553,14 @@ __global__ void k_stage_costs(PoolView pool, Layout L, unsigned m, unsigned long
 }
 
 // Insertion paths of nodes first .. first + n - 1 as plain byte records (job descriptors for export).
-__global__ void k_read_paths(PoolView pool, Layout L, unsigned long long first, unsigned n, uint8_t *__restrict__ out) {
+__global__ void k_read_paths(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n, uint8_t *__restrict__ out) {
 	const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const unsigned *h = hdr_of(pool, L, first + i);
-	for (unsigned t = 0; t < L.n; ++t) out[(size_t) i * L.n + t] = (uint8_t) path_byte(h, t);
+	uint8_t *job = out + (size_t) i * L.n;
+	job[0] = (uint8_t) m;                        // a job descriptor: byte 0 = tree size, byte t = path[t] for 3 <= t < m
+	job[1] = job[2] = 0;
+	for (unsigned t = 3; t < L.n; ++t) job[t] = (uint8_t) path_byte(h, t);
 }
 
 __global__ void k_filter_trees(const uint8_t *__restrict__ src, unsigned n_src, unsigned trec, const unsigned *bound_ptr,
@@ -579,6 +595,8 @@ struct Search {
 	unsigned n = 0, split_level = 0;
 	Pool pool[XMP_MAX_TAXA + 2];
 	unsigned *d_bound = nullptr, *d_nsurv = nullptr, *d_ntrees = nullptr, *d_len = nullptr;
+	const XchPeerTable *d_peers = nullptr;   // non-null when this search is one rank of a multi-GPU search (exchange.cu)
+	unsigned steals_served = 0, steals_got = 0, open_published = 0xffffffffu;
 	unsigned long long *d_merges = nullptr;
 	uint4 *d_surv = nullptr;
 	unsigned long long surv_cap = 0;
@@ -710,7 +728,6 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 			S->surv_cap_lvl[m] = (S->fused_last && m + 2 == n) ? 4 * S->surv_cap : 4 * S->pool[m + 1].cap;
 			S->d_surv_lvl[m] = (uint4 *) take((size_t) S->surv_cap_lvl[m] * 16);
 		}
-		S->d_bound = (unsigned *) take(1024);
 		S->d_len = (unsigned *) take(65536 * sizeof(unsigned));
 		return off + 256;
 	};
@@ -729,13 +746,25 @@ static int alloc_search(xmp_ctx *ctx, Search *S, unsigned W) {
 		ctx->arena_bytes = need;
 	}
 	layout(lo, (char *) ctx->arena);
+	// The counter block (bound, survivor and tree counters, per-level depths) lives in the context's exchange block,
+	// where peer GPUs can reach the bound word.  Its protocol words (bound, steal request / reply, busy counter) belong
+	// to the exchange once ranks are connected: peers may already have written them.
+	int xrc = xch_ensure_block(ctx);
+	if (xrc) return xrc;
+	S->d_bound = ctx->xch;
+	S->d_peers = ctx->xch_connected ? (const XchPeerTable *) ((const char *) ctx->xch + XCH_TABLE_OFF) : nullptr;
 	S->d_nsurv = S->d_bound + 1;
 	S->d_ntrees = S->d_bound + 2;
 	S->d_merges = (unsigned long long *) (S->d_bound + 4);
 	S->d_nsurv_lvl = S->d_bound + 8;
 	S->d_overflow = S->d_bound + 6;
 	S->d_maxdepth = S->d_bound + 128;          // [XMP_MAX_TAXA + 2]
-	XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 1024, ctx->stream));
+	if (ctx->xch_connected) {
+		XMP_CUDA(cudaMemsetAsync(S->d_bound + 1, 0, (XW_FIRST - 1) * sizeof(unsigned), ctx->stream));
+		XMP_CUDA(cudaMemsetAsync(S->d_bound + XW_FIRST + XW_COUNT, 0, (256 - XW_FIRST - XW_COUNT) * sizeof(unsigned), ctx->stream));
+	} else {
+		XMP_CUDA(cudaMemsetAsync(S->d_bound, 0, 1024, ctx->stream));
+	}
 	if (!ctx->h_pin) XMP_CUDA(cudaMallocHost(&ctx->h_pin, 1024));
 	S->h_pin = ctx->h_pin;
 	return XMP_OK;
@@ -830,7 +859,7 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 		const unsigned long long tiles32 = ((first & 31ull) + chunk + 31ull) >> 5;
 		const unsigned long long pairs32 = tiles32 * 32ull * P.E;
 		k_select<8><<<(unsigned) ((pairs32 + 2047) / 2048), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, rest, S->d_bound, last, surv, nsurv, trees,
-		                                                                        S->d_ntrees, room, sc, si);
+		                                                                        S->d_ntrees, room, sc, si, S->d_peers);
 		XMP_CUDA(cudaGetLastError());
 		S->st.launches += 1;
 		return XMP_OK;
@@ -838,7 +867,7 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 #define XMP_EXPAND(G)                                                                                                   \
 	k_expand_score<G><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
 	                                                                              S->d_bound, last, surv, nsurv, trees,             \
-	                                                                              S->d_ntrees, room, sc, si)
+	                                                                              S->d_ntrees, room, sc, si, S->d_peers)
 	const unsigned W = L.W;
 	if (W > 16) XMP_EXPAND(32);
 	else if (W > 8) XMP_EXPAND(16);
@@ -900,7 +929,7 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
 		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
 		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D, \
-		                                                            S->d_overflow);                                               \
+		                                                            S->d_overflow, S->d_peers);                                   \
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
@@ -1255,9 +1284,113 @@ static void init_knobs(xmp_ctx *ctx, Search *S) {
 	memset(&S->st, 0, sizeof S->st);
 }
 
+// Detaches open partial trees of the shallowest level that has any -- the reference's thief takes "the last unprocessed
+// edge at the victim's shallowest open level" (src/mpiworker.c:169-181) -- and stages their job descriptors (insertion
+// paths, byte 0 = tree size) in S->pathbuf on the device.  keep_half: leave at least half of that level (and never the
+// only open tree) to the owner; otherwise up to max_nodes are taken.
+static int detach_jobs(xmp_ctx *ctx, Search *S, unsigned max_nodes, bool keep_half, unsigned *n_out) {
+	const Layout &L = S->L;
+	*n_out = 0;
+	// A sharded search deals the frontier out by hash when it expands the level below split_level; a node from a
+	// shallower level would be dealt again -- with the thief's index -- on the other side.  So only subtrees that are
+	// past the deal ever change hands (the shallow prefix is a handful of nodes, gone after the first sweeps).
+	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
+	unsigned long long open = 0;
+	for (unsigned m = m0; m < S->n; ++m) open += S->pool[m].count;
+	if (keep_half && open < 2) return XMP_OK;
+	for (unsigned m = m0; m < S->n; ++m) {
+		Pool &P = S->pool[m];
+		if (P.count == 0) continue;
+		if (S->pend[m].active) continue;      // its oldest nodes are half expanded; newer ones sit behind them in the ring
+		unsigned long long want = keep_half ? std::max<unsigned long long>(1, P.count / 2) : P.count;
+		unsigned k = (unsigned) std::min<unsigned long long>(want, max_nodes);
+		const unsigned long long tail = P.slot(P.count);         // one past the newest node
+		if (tail != 0) k = (unsigned) std::min<unsigned long long>(k, tail);   // stay on this side of the wrap
+		const unsigned long long from = (tail == 0 ? P.cap : tail) - k;
+		int rc = S->pathbuf.reserve((size_t) std::max<unsigned>(k, 256) * L.n);
+		if (rc) return rc;
+		k_read_paths<<<(k + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, from, k, (uint8_t *) S->pathbuf.ptr);
+		XMP_CUDA(cudaGetLastError());
+		S->st.launches += 1;
+		P.count -= k;
+		*n_out = k;
+		return XMP_OK;
+	}
+	return XMP_OK;
+}
+
+// ---- the engine side of the exchange protocol (exchange_proto.h, exchange.cu) -------------------------
+// Open subtrees this rank could give away right now, published as a hint for idle ranks.
+static int publish_open(xmp_ctx *ctx, Search *S) {
+	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
+	unsigned long long open = 0;
+	for (unsigned m = m0; m < S->n; ++m)
+		if (!S->pend[m].active) open += S->pool[m].count;
+	const unsigned v = (unsigned) std::min<unsigned long long>(open, 0x7fffffffu);
+	if (v == S->open_published) return XMP_OK;
+	S->open_published = v;
+	ctx->h_xres[8] = v;           // pinned; a later value overtaking this copy is just as good a hint
+	XMP_CUDA(cudaMemcpyAsync(S->d_bound + XW_OPEN, ctx->h_xres + 8, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+	return XMP_OK;
+}
+
+int search_export_for_steal(xmp_ctx *ctx, unsigned *n) {
+	Search *S = ctx->search;
+	int rc = detach_jobs(ctx, S, XCH_MAX_JOBS, true, n);
+	if (rc == XMP_OK && *n) {
+		S->steals_served += 1;
+		rc = publish_open(ctx, S);
+	}
+	return rc;
+}
+
+// Donor -> thief: the staged descriptors go straight from this GPU's memory into the thief's mailbox (a peer-to-peer
+// copy over NVLink; the addresses are peer-mapped, cudaMemcpyDefault resolves them).
+int search_send_staged(xmp_ctx *ctx, unsigned thief, unsigned n) {
+	Search *S = ctx->search;
+	XMP_CUDA(cudaMemcpyAsync((char *) ctx->xch_peer[thief] + XCH_MAILBOX_BYTE_OFF, S->pathbuf.ptr, (size_t) n * S->L.n, cudaMemcpyDefault, ctx->stream));
+	return XMP_OK;
+}
+
+// Thief: the descriptors in this rank's mailbox become open subtrees (the reference's fast-forward,
+// src/yanbader.c:95-99,136-143, as one batched set construction).
+int search_import_mailbox(xmp_ctx *ctx, unsigned n) {
+	Search *S = ctx->search;
+	if (n > XCH_MAX_JOBS) return set_error(XMP_ERR_ARG, "a reply announces %u jobs, the mailbox holds %u", n, (unsigned) XCH_MAX_JOBS);
+	std::vector<uint8_t> jobs((size_t) n * S->L.n);
+	XMP_CUDA(cudaMemcpyAsync(jobs.data(), (const char *) ctx->xch + XCH_MAILBOX_BYTE_OFF, jobs.size(), cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	S->done = false;
+	S->finished = false;
+	S->steals_got += 1;
+	int rc = import_nodes(ctx, S, jobs.data(), n);
+	if (rc) return rc;
+	return publish_open(ctx, S);
+}
+
+// After xmp_cuda_search_steal: either the search goes on, or it is over everywhere -- then the bound word holds the
+// minimum over all ranks (every peer's atomicMin landed before that peer could go idle).
+int search_after_steal(xmp_ctx *ctx, bool finished) {
+	Search *S = ctx->search;
+	if (!finished) return XMP_OK;
+	int rc = drain_trees(ctx, S);
+	if (rc == XMP_OK) rc = fetch_counters(ctx, S);
+	if (rc == XMP_OK) S->done = S->finished = true;
+	return rc;
+}
+
+int xch_service_request(xmp_ctx *ctx, unsigned request);
+
 // The two halves of xmp_cuda_search_begin that talk to the device (split out so that every failure takes the same
 // tear-down path in the caller).
 static int begin_bound(xmp_ctx *ctx, Search *S) {
+	if (ctx->xch_connected) {
+		// the word was set to "no bound" by xmp_cuda_exchange_reset before the ranks' barrier; a peer that started
+		// earlier may already have lowered it
+		k_lower_bound<<<1, 1, 0, ctx->stream>>>(S->d_bound, S->bound);
+		XMP_CUDA(cudaGetLastError());
+		return fetch_counters(ctx, S);
+	}
 	XMP_CUDA(cudaMemcpyAsync(S->d_bound, &S->bound, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	return XMP_OK;
@@ -1367,6 +1500,13 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 			break;
 		}
 		++batches;
+		if (S->d_peers) {
+			// one rank of a multi-GPU search: publish what could be given away, answer a waiting thief
+			// (the request word came back with this sweep's counters)
+			rc = publish_open(ctx, S);
+			if (rc == XMP_OK && S->h_pin[XW_REQUEST]) rc = xch_service_request(ctx, S->h_pin[XW_REQUEST]);
+			if (rc) break;
+		}
 	}
 	while (!S->sweep && !S->done && (max_batches == 0 || batches < max_batches)) {
 		// XMP_SWEEP=0 (kept for A/B measurements, profiles/r01_search_tuning.md): one level per host
@@ -1405,6 +1545,11 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		rc = run_batch(ctx, S, (unsigned) pick, pick_chunk, 0);
 		if (rc) break;
 		++batches;
+		if (S->d_peers) {
+			rc = publish_open(ctx, S);
+			if (rc == XMP_OK && S->h_pin[XW_REQUEST]) rc = xch_service_request(ctx, S->h_pin[XW_REQUEST]);
+			if (rc) break;
+		}
 	}
 	if (rc == XMP_OK && !S->done) {
 		// A slice that stopped on max_batches may have emptied the frontier with its last sweep: report it
@@ -1414,6 +1559,7 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		for (unsigned m = 3; m < S->n; ++m) open |= S->pool[m].count != 0;
 		if (!open) S->done = true;
 	}
+	if (rc == XMP_OK && S->d_peers) rc = publish_open(ctx, S);      // an empty frontier is published too: nothing to steal here
 	if (rc == XMP_OK && S->done && !S->finished) {
 		rc = drain_trees(ctx, S);
 		if (rc == XMP_OK) rc = fetch_counters(ctx, S);
@@ -1454,37 +1600,14 @@ extern "C" int xmp_cuda_search_pending(xmp_ctx *ctx, unsigned long long *per_lev
 extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uint8_t *jobs, unsigned *n_jobs) {
 	if (!ctx || !ctx->search || !jobs || !n_jobs) return set_error(XMP_ERR_ARG, "no search in progress");
 	Search *S = ctx->search;
-	const Layout &L = S->L;
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	*n_jobs = 0;
-	// A sharded search deals the frontier out by hash when it expands the level below split_level; a node from a
-	// shallower level would be dealt again -- with the thief's index -- on the other side.  So only subtrees that are
-	// past the deal ever change hands (the shallow prefix is a handful of nodes, gone after the first sweeps).
-	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
-	for (unsigned m = m0; m < S->n; ++m) {
-		Pool &P = S->pool[m];
-		if (P.count == 0) continue;
-		// Like the reference's thief (src/mpiworker.c:169-181): take from the shallowest open level.
-		if (S->pend[m].active) continue;      // its oldest nodes are half expanded; newer ones sit behind them in the ring
-		unsigned k = (unsigned) std::min<unsigned long long>(P.count, max_nodes);
-		const unsigned long long tail = P.slot(P.count);         // one past the newest node
-		if (tail != 0) k = (unsigned) std::min<unsigned long long>(k, tail);   // stay on this side of the wrap
-		const unsigned long long from = (tail == 0 ? P.cap : tail) - k;
-		int rc = S->pathbuf.reserve((size_t) k * L.n);
-		if (rc) return rc;
-		k_read_paths<<<(k + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, from, k, (uint8_t *) S->pathbuf.ptr);
-		XMP_CUDA(cudaGetLastError());
-		XMP_CUDA(cudaMemcpyAsync(jobs, S->pathbuf.ptr, (size_t) k * L.n, cudaMemcpyDeviceToHost, ctx->stream));
-		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		for (unsigned i = 0; i < k; ++i) {
-			uint8_t *job = jobs + (size_t) i * L.n;
-			job[0] = (uint8_t) m;
-			job[1] = job[2] = 0;
-		}
-		P.count -= k;
-		*n_jobs = k;
-		return XMP_OK;
-	}
+	unsigned k = 0;
+	int rc = detach_jobs(ctx, S, max_nodes, false, &k);
+	if (rc || k == 0) return rc;
+	XMP_CUDA(cudaMemcpyAsync(jobs, S->pathbuf.ptr, (size_t) k * S->L.n, cudaMemcpyDeviceToHost, ctx->stream));
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
+	*n_jobs = k;
 	return XMP_OK;
 }
 
@@ -1536,6 +1659,8 @@ extern "C" int xmp_cuda_search_stats(xmp_ctx *ctx, xmp_search_stats *out) {
 	XMP_CUDA(cudaMemcpyAsync(&merges, S->d_merges, sizeof merges, cudaMemcpyDeviceToHost, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	*out = S->st;
+	out->steals_served = S->steals_served;
+	out->steals_received = S->steals_got;
 	out->site_merges = (S->st.score_calls + merges) * ctx->real_sites;
 	return XMP_OK;
 }

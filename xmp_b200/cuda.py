@@ -30,7 +30,12 @@ EXPORTS = [
     "xmp_cuda_search_pending", "xmp_cuda_search_export_jobs", "xmp_cuda_search_import_jobs",
     "xmp_cuda_search_result", "xmp_cuda_search_stats", "xmp_cuda_int_pipe_peak",
     "xmp_cuda_search_stored", "xmp_cuda_paths_keep_first_dfs",
+    "xmp_cuda_exchange_handle", "xmp_cuda_exchange_connect", "xmp_cuda_exchange_connect_local", "xmp_cuda_exchange_disconnect",
+    "xmp_cuda_exchange_reset", "xmp_cuda_search_steal",
 ]
+EXCHANGE_HANDLE_BYTES = 64
+STEAL_GOT_WORK = 1
+STEAL_FINISHED = 2
 
 
 class XmpCudaError(RuntimeError):
@@ -47,7 +52,8 @@ class SearchStats(C.Structure):
                 ("full_trees", C.c_ulonglong), ("site_merges", C.c_ulonglong), ("launches", C.c_ulonglong),
                 ("iterations", C.c_ulonglong), ("seconds", C.c_double),
                 ("nodes_by_depth", C.c_ulonglong * (MAX_TAXA + 1)), ("edge_evals_by_depth", C.c_ulonglong * (MAX_TAXA + 1)),
-                ("batches_by_depth", C.c_ulonglong * (MAX_TAXA + 1))]
+                ("batches_by_depth", C.c_ulonglong * (MAX_TAXA + 1)),
+                ("steals_served", C.c_ulonglong), ("steals_received", C.c_ulonglong)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.endswith("_by_depth") else getattr(self, k)) for k, _ in self._fields_}
@@ -60,46 +66,46 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise XmpCudaError("xmp_b200/libxmp_b200.so is missing: run `make cuda` (or __graft_entry__.build()). "
                                "There is no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
-        L.xmp_cuda_last_error.restype = C.c_char_p
-        vp, u, sz = C.c_void_p, C.c_uint, C.c_size_t
-        L.xmp_cuda_init.argtypes = [C.c_int, C.POINTER(vp)]
-        L.xmp_cuda_destroy.argtypes = [vp]
-        L.xmp_cuda_destroy.restype = None
-        L.xmp_cuda_set_stream.argtypes = [vp, vp]
-        L.xmp_cuda_synchronize.argtypes = [vp]
-        L.xmp_cuda_load.argtypes = [vp, vp, vp, u, u, vp, u]
-        L.xmp_cuda_load_device_rows.argtypes = [vp, vp, vp, u, u, vp, u]
-        L.xmp_cuda_build_midpoints.argtypes = [vp, vp, sz, u, u, vp, vp]
-        L.xmp_cuda_score_batch.argtypes = [vp, vp, sz, u, u, vp, u, vp, vp, vp]
-        L.xmp_cuda_score_insertions_host.argtypes = [vp, vp, sz, u, u, vp]
-        L.xmp_cuda_search_reserve.argtypes = [vp, u, u, sz]
-        L.xmp_cuda_search_begin.argtypes = [vp, C.POINTER(SearchParams)]
-        L.xmp_cuda_search_run.argtypes = [vp, u, C.POINTER(C.c_int)]
-        L.xmp_cuda_search_get_bound.argtypes = [vp, C.POINTER(u)]
-        L.xmp_cuda_search_set_bound.argtypes = [vp, u]
-        L.xmp_cuda_search_pending.argtypes = [vp, vp]
-        L.xmp_cuda_search_export_jobs.argtypes = [vp, u, vp, C.POINTER(u)]
-        L.xmp_cuda_search_import_jobs.argtypes = [vp, vp, u]
-        L.xmp_cuda_search_result.argtypes = [vp, C.POINTER(u), C.POINTER(C.c_ulonglong), vp, sz]
-        L.xmp_cuda_search_stats.argtypes = [vp, C.POINTER(SearchStats)]
-        L.xmp_cuda_search_stored.argtypes = [vp, C.POINTER(C.c_ulonglong)]
-        L.xmp_cuda_paths_keep_first_dfs.argtypes = [vp, sz, u, sz]
-        L.xmp_cuda_int_pipe_peak.argtypes = [vp, C.POINTER(C.c_double)]
-        for name in ("FitchBases_b2_w16_cuda",):
-            getattr(L, name).restype = None
-        L.FitchBases_b2_w16_cuda.argtypes = [vp, vp, vp, u]
-        L.FitchBasesAndCompare_b2_w16_cuda.argtypes = [vp, vp, vp, vp, u]
-        L.FitchScoreWeight1_b2_w16_cuda.argtypes = [vp, vp, u]
-        L.FitchScoreWeight1_stopearly_b2_w16_cuda.argtypes = [vp, vp, u, u]
-        L.FitchScore_b2_w16_cuda.argtypes = [vp, vp, vp, u]
-        L.FitchScore_stopearly_b2_w16_cuda.argtypes = [vp, vp, vp, u, u]
-        L.FitchScore_fw1_b2_w16_cuda.argtypes = [vp, vp, vp, u]
-        L.FitchScore_fw1_stopearly_b2_w16_cuda.argtypes = [vp, vp, vp, u, u]
-        for name in EXPORTS[7:14]:
-            getattr(L, name).restype = C.c_uint
-        _LIB = L
+        _LIB = bind(C.CDLL(LIB_PATH))
     return _LIB
+
+
+def bind(L, partial=False):
+    """Declares the argument types of every entry point of include/xmp_cuda.h on a loaded library.  partial: skip what
+    the library does not export (the CPU tests bind their test double of the search entry points this way)."""
+    vp, u, sz, ull = C.c_void_p, C.c_uint, C.c_size_t, C.c_ulonglong
+    pu = C.POINTER(u)
+    sig = {
+        "xmp_cuda_last_error": ([], C.c_char_p), "xmp_cuda_device_count": ([], C.c_int),
+        "xmp_cuda_init": ([C.c_int, C.POINTER(vp)], C.c_int), "xmp_cuda_destroy": ([vp], None),
+        "xmp_cuda_set_stream": ([vp, vp], C.c_int), "xmp_cuda_synchronize": ([vp], C.c_int),
+        "xmp_cuda_load": ([vp, vp, vp, u, u, vp, u], C.c_int), "xmp_cuda_load_device_rows": ([vp, vp, vp, u, u, vp, u], C.c_int),
+        "xmp_cuda_build_midpoints": ([vp, vp, sz, u, u, vp, vp], C.c_int),
+        "xmp_cuda_score_batch": ([vp, vp, sz, u, u, vp, u, vp, vp, vp], C.c_int),
+        "xmp_cuda_score_insertions_host": ([vp, vp, sz, u, u, vp], C.c_int),
+        "xmp_cuda_search_reserve": ([vp, u, u, sz], C.c_int), "xmp_cuda_search_begin": ([vp, C.POINTER(SearchParams)], C.c_int),
+        "xmp_cuda_search_run": ([vp, u, C.POINTER(C.c_int)], C.c_int),
+        "xmp_cuda_search_get_bound": ([vp, pu], C.c_int), "xmp_cuda_search_set_bound": ([vp, u], C.c_int),
+        "xmp_cuda_search_pending": ([vp, vp], C.c_int), "xmp_cuda_search_export_jobs": ([vp, u, vp, pu], C.c_int),
+        "xmp_cuda_search_import_jobs": ([vp, vp, u], C.c_int),
+        "xmp_cuda_search_result": ([vp, pu, C.POINTER(ull), vp, sz], C.c_int),
+        "xmp_cuda_search_stats": ([vp, C.POINTER(SearchStats)], C.c_int), "xmp_cuda_search_stored": ([vp, C.POINTER(ull)], C.c_int),
+        "xmp_cuda_paths_keep_first_dfs": ([vp, sz, u, sz], C.c_int), "xmp_cuda_int_pipe_peak": ([vp, C.POINTER(C.c_double)], C.c_int),
+        "xmp_cuda_exchange_handle": ([vp, vp], C.c_int), "xmp_cuda_exchange_connect": ([vp, u, u, vp], C.c_int),
+        "xmp_cuda_exchange_connect_local": ([vp, u, u, vp], C.c_int), "xmp_cuda_exchange_disconnect": ([vp], C.c_int),
+        "xmp_cuda_exchange_reset": ([vp], C.c_int), "xmp_cuda_search_steal": ([vp, C.POINTER(C.c_int)], C.c_int),
+        "FitchBases_b2_w16_cuda": ([vp, vp, vp, u], None), "FitchBasesAndCompare_b2_w16_cuda": ([vp, vp, vp, vp, u], u),
+        "FitchScoreWeight1_b2_w16_cuda": ([vp, vp, u], u), "FitchScoreWeight1_stopearly_b2_w16_cuda": ([vp, vp, u, u], u),
+        "FitchScore_b2_w16_cuda": ([vp, vp, vp, u], u), "FitchScore_stopearly_b2_w16_cuda": ([vp, vp, vp, u, u], u),
+        "FitchScore_fw1_b2_w16_cuda": ([vp, vp, vp, u], u), "FitchScore_fw1_stopearly_b2_w16_cuda": ([vp, vp, vp, u, u], u),
+    }
+    assert sorted(sig) == sorted(EXPORTS)
+    for name, (args, res) in sig.items():
+        if partial and not hasattr(L, name):
+            continue
+        f = getattr(L, name)
+        f.argtypes, f.restype = args, res
+    return L
 
 
 def _ptr(x):
@@ -238,6 +244,28 @@ class Context:
         if stored.value:
             _check(lib().xmp_cuda_search_result(self._h, C.byref(score), C.byref(n), _ptr(paths), stored.value))
         return score.value, n.value, paths
+
+    # ---- several GPUs on one search (include/xmp_cuda.h 2d) ----
+    def exchange_handle(self):
+        h = np.zeros(EXCHANGE_HANDLE_BYTES, dtype=np.uint8)
+        _check(lib().xmp_cuda_exchange_handle(self._h, _ptr(h)))
+        return h
+
+    def exchange_connect(self, rank, world, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert handles.size == world * EXCHANGE_HANDLE_BYTES
+        _check(lib().xmp_cuda_exchange_connect(self._h, rank, world, _ptr(handles)))
+
+    def exchange_disconnect(self):
+        _check(lib().xmp_cuda_exchange_disconnect(self._h))
+
+    def exchange_reset(self):
+        _check(lib().xmp_cuda_exchange_reset(self._h))
+
+    def search_steal(self):
+        st = C.c_int(0)
+        _check(lib().xmp_cuda_search_steal(self._h, C.byref(st)))
+        return st.value
 
     def search_stats(self):
         st = SearchStats()

@@ -1,19 +1,22 @@
-"""One-process-per-GPU exact search over torch.distributed: the replacement for the reference's MPI
-boss/worker scheduler (reference src/mpiboss.c:30-429, src/mpiworker.c:214-380) when the host is
-Python (bench.py under torchrun).  The C host (host/fastdnamp.c) does the same with threads.
+"""One-process-per-GPU exact search under torchrun: the replacement for the reference's MPI boss/worker scheduler
+(reference src/mpiboss.c:30-429, src/mpiworker.c:214-380) when the host is Python (bench.py).  The C host
+(host/fastdnamp.c) does the same with threads.
 
-Differences from the reference, by design:
-  * no boss: every rank searches (the reference's rank 0 only relays, src/fastdnamp.c:112-118);
-  * the upper bound is kept consistent by an all-reduce(min) of one word every round instead of
-    worker -> boss -> all workers point-to-point relays (src/mpiboss.c:162-171, src/mpiworker.c:19-41);
-  * work stealing is decided collectively from an all-gather of the open-node counts: ranks that ran
-    dry receive job descriptors (insertion paths, a few hundred bytes) from the ranks holding the most
-    open subtrees through one more all-gather (over NVLink with the nccl backend); the thief rebuilds the
-    subtree state from the descriptor alone, as the reference's fast-forward does (src/yanbader.c:136-143);
-  * termination: the all-gathered counts are all zero.
+torch.distributed is plumbing here: it carries the 64-byte exchange handles once, provides the barrier before a
+search and the sums / gathers after it.  The search itself exchanges nothing through it:
 
-The engine is any object with the search_* methods of xmp_b200.cuda.Context; the CPU tests drive the
-same protocol over gloo with a CPU stand-in engine (tests/test_distributed.py).
+  * the upper bound lives in peer-mapped device memory; the kernels that find a better tree lower every rank's word
+    with a system-scope atomicMin over NVLink (the reference relays MSG_NEWBOUND through the boss,
+    src/mpiboss.c:162-171, src/mpiworker.c:19-41);
+  * a rank whose frontier ran dry asks one peer for open subtrees and receives job descriptors (insertion paths) in
+    its device mailbox; the thief rebuilds the subtree state from the descriptor alone, as the reference's
+    fast-forward does (src/yanbader.c:136-143).  No collective and no lock step in the loop
+    (include/xmp_cuda.h 2d, xmp_b200/csrc/exchange_proto.h);
+  * termination: a counter of ranks holding work, kept in rank 0's block.
+
+Fallback transport ("collective"): the round-1 scheme -- one all-gather of [bound, open subtrees] per round and a
+second one for job descriptors -- for engines without an exchange (the CPU stand-in of tests/test_distributed.py)
+and for nodes where the GPUs cannot map each other's memory.  It is lock-step and is reported as such.
 """
 import numpy as np
 import torch
@@ -24,15 +27,90 @@ def _t(x, device, dtype=torch.int64):
     return torch.tensor(x, dtype=dtype, device=device)
 
 
-def sharded_search(engine, num_taxa, device="cpu", slice_batches=8, steal_nodes=256, group=None, on_round=None):
-    """Runs engine (already search_begin()'ed with this rank's shard_index / shard_count) to completion
-    together with the other ranks.  Returns (score, total number of optimal trees, this rank's optimal
-    paths, number of rounds).  Every rank returns the same score and total.
+def connect_exchange(engine, device="cpu", group=None):
+    """Maps every rank's exchange block into this rank (once per engine / context).  Returns True when ALL ranks
+    succeeded; otherwise every rank is left disconnected and the caller uses the collective transport."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if not hasattr(engine, "exchange_handle"):
+        ok = 0
+    else:
+        try:
+            mine = np.asarray(engine.exchange_handle(), dtype=np.uint8)
+            ok = 1
+        except Exception:  # noqa: BLE001
+            mine, ok = np.zeros(64, np.uint8), 0
+    flag = _t([ok], device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        return False
+    handles = torch.zeros(world * 64, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(handles, torch.from_numpy(mine).to(device), group=group)
+    try:
+        engine.exchange_connect(rank, world, handles.cpu().numpy())
+        ok = 1
+    except Exception as e:  # noqa: BLE001
+        engine._exchange_error = repr(e)
+        ok = 0
+    flag = _t([ok], device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        if ok:
+            engine.exchange_disconnect()
+        return False
+    return True
 
-    One collective per round (an all-gather of [bound, open subtrees] per rank) plus, only in rounds
-    where some rank ran dry, one all-gather of job descriptors.  Point-to-point send/recv is avoided on
-    purpose: with NCCL every new (donor, thief) pair pays a connection set-up of ~100 ms, more than a
-    whole search of the hard datasets takes."""
+
+def disconnect_exchange(engine, group=None):
+    """Unmaps the peers' blocks on every rank, then a barrier: only after it may a rank free its own block (close its
+    context) -- memory that a peer still has mapped must not be freed."""
+    if hasattr(engine, "exchange_disconnect"):
+        engine.exchange_disconnect()
+    dist.barrier(group=group)
+
+
+def sharded_search(engine, num_taxa, device="cpu", group=None, begin=None, connected=None, slice_batches=8, steal_nodes=256,
+                   on_round=None):
+    """Runs one search over all ranks.  begin: keyword arguments for engine.search_begin (bound, max_trees, ...);
+    shard_index / shard_count are filled in.  connected: the result of connect_exchange (None = call it here).
+    Returns (score, total number of optimal trees, this rank's optimal paths, info) with info = {"transport": "peer" |
+    "collective", "rounds": host rounds (collective) or steal waits (peer)}.  Every rank returns the same score and total."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    kw = dict(begin or {})
+    kw.setdefault("shard_index", rank)
+    kw.setdefault("shard_count", world)
+    if connected is None:
+        connected = world > 1 and connect_exchange(engine, device, group)
+    if connected:
+        engine.exchange_reset()
+        dist.barrier(group=group)                 # nobody writes into a block that has not been reset yet
+        engine.search_begin(**kw)
+        waits = 0
+        while True:
+            while not engine.search_run(0):
+                pass
+            waits += 1
+            if engine.search_steal() != 1:        # 1 = got work, 2 = finished everywhere
+                break
+        info = {"transport": "peer", "rounds": waits}
+    else:
+        engine.search_begin(**kw)
+        info = {"transport": "collective", "rounds": _collective_rounds(engine, num_taxa, device, group, slice_batches, steal_nodes, on_round)}
+    # belt and braces: the bound every rank filters its trees against is the minimum over ranks
+    b = _t([engine.search_get_bound()], device)
+    dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
+    engine.search_set_bound(int(b.item()))
+    score, n, paths = engine.search_result()
+    tot = _t([n], device)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return score, int(tot.item()), paths, info
+
+
+def _collective_rounds(engine, num_taxa, device, group, slice_batches, steal_nodes, on_round):
+    """Lock-step fallback: one all-gather of [bound, open subtrees] per round plus, only in rounds where some rank ran
+    dry, one all-gather of job descriptors.  (Point-to-point send/recv is avoided on purpose: with NCCL every new
+    (donor, thief) pair pays a connection set-up of ~100 ms.)"""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     rounds = 0
@@ -82,10 +160,7 @@ def sharded_search(engine, num_taxa, device="cpu", slice_batches=8, steal_nodes=
                 done = False
     if not done:
         engine.search_run(0)      # nothing is pending anywhere; lets an engine that had not noticed yet wrap up
-    score, n, paths = engine.search_result()
-    tot = _t([n], device)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    return score, int(tot.item()), paths, rounds
+    return rounds
 
 
 def gather_paths(paths, num_taxa, device="cpu", group=None):
