@@ -341,7 +341,8 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
                    "busy_fraction": float(t[1]) / (world * wall),      # sum over ranks of device-busy seconds / (N x wall)
                    "nodes": int(t[2]), "nodes_per_s": float(t[2]) / wall, "edge_evals_per_s": float(t[3]) / wall,
                    "gsite_merges_per_s": float(t[4]) / wall / 1e9, "launches": int(t[6]),
-                   "transport": info["transport"], "steals": int(t[5]),
+                   "transport": info["transport"], "steals": int(t[5]), "rank0_host_seconds": info.get("host_seconds"),
+                   "rank0_begin_device_s": st["begin_seconds"],
                    "reference_cpu_bandb_s": g["ref_bandb_seconds"] if name not in BANDB_GOLDEN else None,
                    "reference_cpu_nodes": g["ref_bandb_nodes"] if name not in BANDB_GOLDEN else None,
                    "reference_cpu_source": "golden-time (measured when tests/golden/datasets.json was generated, another machine)"

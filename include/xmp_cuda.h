@@ -150,6 +150,7 @@ typedef struct {
 	unsigned long long batches_by_depth[XMP_MAX_TAXA + 1];     /* frontier batches (launch groups) at tree size m */
 	unsigned long long steals_served;  /* steal requests of other ranks answered with work (reference: stealCount) */
 	unsigned long long steals_received; /* times this rank ran dry and obtained work from a peer */
+	double   begin_seconds;            /* part of `seconds` spent in xmp_cuda_search_begin (the greedy dive, the root) */
 } xmp_search_stats;
 
 /* Optional: allocate the search's device memory for a problem of this shape now (mem_budget as in

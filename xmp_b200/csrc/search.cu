@@ -578,6 +578,48 @@ __global__ void k_filter_trees(const uint8_t *__restrict__ src, unsigned n_src, 
 
 __global__ void k_lower_bound(unsigned *bound_ptr, unsigned value) { atomicMin(bound_ptr, value); }
 
+// The beam of the greedy dive: keeps the `keep` cheapest entries of a survivor list (by the length of the child tree,
+// surv[i].z), on the device -- one CTA, a histogram of lengths above the minimum, a threshold, a compaction.  Ties at
+// the threshold are taken in arrival order.  (This used to be a device-to-host copy, a host sort and a copy back per
+// tree size: most of the ~10 ms a search spent in the dive.)
+__global__ void __launch_bounds__(1024)
+k_beam_select(const uint4 *__restrict__ surv, const unsigned *n_ptr, unsigned keep, uint4 *__restrict__ out, unsigned *n_out) {
+	__shared__ unsigned hist[2048];
+	__shared__ unsigned s_min, s_T, s_quota, s_count, s_ties;
+	const unsigned n = *n_ptr, tid = threadIdx.x;
+	if (tid == 0) { s_min = 0xffffffffu; s_count = 0; s_ties = 0; }
+	for (unsigned i = tid; i < 2048; i += 1024) hist[i] = 0;
+	__syncthreads();
+	unsigned lo = 0xffffffffu;
+	for (unsigned i = tid; i < n; i += 1024) lo = min(lo, surv[i].z);
+	lo = __reduce_min_sync(0xffffffffu, lo);
+	if ((tid & 31u) == 0) atomicMin(&s_min, lo);
+	__syncthreads();
+	const unsigned smin = s_min;
+	for (unsigned i = tid; i < n; i += 1024) atomicAdd(&hist[min(surv[i].z - smin, 2047u)], 1u);
+	__syncthreads();
+	if (tid == 0) {
+		unsigned cum = 0, T = 2048;
+		for (unsigned b = 0; b < 2048; ++b) {
+			if (cum + hist[b] >= keep) { T = b; break; }
+			cum += hist[b];
+		}
+		s_T = T;
+		s_quota = keep - cum;                    // entries at the threshold that still fit
+	}
+	__syncthreads();
+	const unsigned T = s_T, quota = s_quota;
+	for (unsigned i = tid; i < n; i += 1024) {
+		const uint4 e = surv[i];
+		const unsigned bin = min(e.z - smin, 2047u);
+		bool take = bin < T;
+		if (bin == T) take = atomicAdd(&s_ties, 1u) < quota;
+		if (take) out[atomicAdd(&s_count, 1u)] = e;
+	}
+	__syncthreads();
+	if (tid == 0) *n_out = s_count;
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 struct Pool {
 	unsigned *hdr = nullptr;
@@ -1051,38 +1093,33 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		P.count -= chunk;
 		return tidy_trees(ctx, S);
 	}
+	const uint4 *surv = S->d_surv;
+	const unsigned *nsurv = S->d_nsurv;
+	unsigned ns_word = 1;                       // which word of the counter block holds the length of the list used
 	if (keep_best) {
-		rc = fetch_counters(ctx, S);
-		if (rc) return rc;
-		unsigned ns = S->h_pin[1];
 		// never more children than the next pool can take (a small memory budget on many taxa: capacity < beam)
 		if (!(S->fused_last && m + 2 == S->n)) keep_best = (unsigned) std::min<unsigned long long>(keep_best, S->pool[m + 1].cap - S->pool[m + 1].count);
 		if (keep_best == 0) return set_error(XMP_ERR_NOMEM, "frontier pool for %u taxa is full (%llu nodes)", m + 1, S->pool[m + 1].cap);
-		if (ns > keep_best) {
-			std::vector<uint4> h(ns);
-			XMP_CUDA(cudaMemcpyAsync(h.data(), S->d_surv, (size_t) ns * 16, cudaMemcpyDeviceToHost, ctx->stream));
-			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-			std::sort(h.begin(), h.end(), [](const uint4 &x, const uint4 &y) {
-				if (x.z != y.z) return x.z < y.z;
-				if (x.x != y.x) return x.x < y.x;
-				return x.y < y.y;
-			});
-			ns = keep_best;
-			XMP_CUDA(cudaMemcpyAsync(S->d_surv, h.data(), (size_t) ns * 16, cudaMemcpyHostToDevice, ctx->stream));
-			XMP_CUDA(cudaMemcpyAsync(S->d_nsurv, &ns, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		}
+		// the beam, cut on the device into the tail of the survivor buffer (the list itself is at most beam x (2m-3)
+		// entries, the buffer beam x (2n-3)); no host round between scoring and building
+		uint4 *beam_out = S->d_surv + (S->surv_cap - keep_best);
+		k_beam_select<<<1, 1024, 0, ctx->stream>>>(S->d_surv, S->d_nsurv, keep_best, beam_out, S->d_bound + 7);
+		XMP_CUDA(cudaGetLastError());
+		S->st.launches += 1;
+		surv = beam_out;
+		nsurv = S->d_bound + 7;
+		ns_word = 7;
 	}
 	if (S->fused_last && m + 2 == S->n) {
 		// Children of this level are scored against the last taxon without ever being stored.
 		const unsigned before = S->ntrees_dev;
-		rc = launch_fused(ctx, S, m, 0, 0xffffffffu, S->d_surv, S->d_nsurv);
+		rc = launch_fused(ctx, S, m, 0, 0xffffffffu, surv, nsurv);
 		if (rc) return rc;
 		rc = fetch_counters(ctx, S);
 		if (rc) return rc;
-		const unsigned ns = S->h_pin[1];
+		const unsigned ns = S->h_pin[ns_word];
 		if (S->h_pin[2] > S->trees_cap) {
-			rc = redo_fused(ctx, S, m, ns, S->d_surv, S->d_nsurv, before);
+			rc = redo_fused(ctx, S, m, ns, surv, nsurv, before);
 			if (rc) return rc;
 		} else {
 			S->st.full_trees += S->h_pin[2] - before;
@@ -1093,11 +1130,11 @@ static int run_batch(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long chu
 		P.count -= chunk;
 		return tidy_trees(ctx, S);
 	}
-	rc = launch_children(ctx, S, m, S->d_surv, S->d_nsurv, S->pool[m + 1].slot(S->pool[m + 1].count));
+	rc = launch_children(ctx, S, m, surv, nsurv, S->pool[m + 1].slot(S->pool[m + 1].count));
 	if (rc) return rc;
 	rc = fetch_counters(ctx, S);
 	if (rc) return rc;
-	const unsigned ns = S->h_pin[1];
+	const unsigned ns = S->h_pin[ns_word];
 	S->pool[m + 1].count += ns;
 	S->st.children += ns;
 	P.count -= chunk;
@@ -1409,6 +1446,7 @@ static int begin_timed(xmp_ctx *ctx, Search *S) {
 	float ms = 0;
 	XMP_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
 	S->st.seconds += ms * 1e-3;
+	S->st.begin_seconds = ms * 1e-3;
 	return XMP_OK;
 }
 

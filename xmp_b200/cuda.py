@@ -53,7 +53,7 @@ class SearchStats(C.Structure):
                 ("iterations", C.c_ulonglong), ("seconds", C.c_double),
                 ("nodes_by_depth", C.c_ulonglong * (MAX_TAXA + 1)), ("edge_evals_by_depth", C.c_ulonglong * (MAX_TAXA + 1)),
                 ("batches_by_depth", C.c_ulonglong * (MAX_TAXA + 1)),
-                ("steals_served", C.c_ulonglong), ("steals_received", C.c_ulonglong)]
+                ("steals_served", C.c_ulonglong), ("steals_received", C.c_ulonglong), ("begin_seconds", C.c_double)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k.endswith("_by_depth") else getattr(self, k)) for k, _ in self._fields_}

@@ -82,18 +82,28 @@ def sharded_search(engine, num_taxa, device="cpu", group=None, begin=None, conne
     kw.setdefault("shard_count", world)
     if connected is None:
         connected = world > 1 and connect_exchange(engine, device, group)
+    import time
+    t0 = time.perf_counter()
     if connected:
         engine.exchange_reset()
         dist.barrier(group=group)                 # nobody writes into a block that has not been reset yet
+        t1 = time.perf_counter()
         engine.search_begin(**kw)
-        waits = 0
+        t2 = time.perf_counter()
+        waits, t_run, t_steal = 0, 0.0, 0.0
         while True:
+            ta = time.perf_counter()
             while not engine.search_run(0):
                 pass
+            tb = time.perf_counter()
             waits += 1
-            if engine.search_steal() != 1:        # 1 = got work, 2 = finished everywhere
+            state = engine.search_steal()         # 1 = got work, 2 = finished everywhere
+            t_run += tb - ta
+            t_steal += time.perf_counter() - tb
+            if state != 1:
                 break
-        info = {"transport": "peer", "rounds": waits}
+        info = {"transport": "peer", "rounds": waits,
+                "host_seconds": {"reset_barrier": t1 - t0, "begin": t2 - t1, "run": t_run, "steal_wait": t_steal}}
     else:
         engine.search_begin(**kw)
         info = {"transport": "collective", "rounds": _collective_rounds(engine, num_taxa, device, group, slice_batches, steal_nodes, on_round)}
@@ -101,10 +111,13 @@ def sharded_search(engine, num_taxa, device="cpu", group=None, begin=None, conne
     b = _t([engine.search_get_bound()], device)
     dist.all_reduce(b, op=dist.ReduceOp.MIN, group=group)
     engine.search_set_bound(int(b.item()))
+    t3 = time.perf_counter()
     score, n, paths = engine.search_result()
     tot = _t([n], device)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
-    return score, int(tot.item()), paths, info
+    total = int(tot.item())
+    info.setdefault("host_seconds", {})["finish"] = time.perf_counter() - t3
+    return score, total, paths, info
 
 
 def _collective_rounds(engine, num_taxa, device, group, slice_batches, steal_nodes, on_round):
