@@ -286,6 +286,15 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
     bundle = json.loads(gzip.open(os.path.join(gold, "alignments.json.gz")).read())
     dev = torch.device("cuda", local)
     out = []
+    # Untimed warm-up on every rank: the first search of a process loads the search kernels' code (lazy module
+    # loading, several milliseconds) -- at N > 1 only rank 0 would have paid that in its solo pass.
+    _, p = _bandb_problem(xh, goldens, bundle, "mt-10")
+    ctx = xc.Context(local)
+    ctx.load_problem(p)
+    ctx.search_begin(bound=p.bound)
+    while not ctx.search_run(0):
+        pass
+    ctx.close()
     for name in names:
         g, p = _bandb_problem(xh, goldens, bundle, name)
         ctx = xc.Context(local)
@@ -293,7 +302,7 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
         ctx.search_reserve(p.num_taxa, p.n_blocks)      # device memory set up before the clock, like the reference's arena
         solo = None
         if world > 1:
-            if rank == 0:
+            if rank == 0 and not os.environ.get("XMP_BENCH_NO_SOLO"):      # A/B runs: skip the one-GPU pass
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 ctx.search_begin(bound=p.bound)
@@ -319,8 +328,14 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
         st = ctx.search_stats()
         t = torch.tensor([wall, st["seconds"], float(st["nodes"]), float(st["score_calls"]), float(st["site_merges"]),
                           float(st["steals_received"]), float(st["launches"])], dtype=torch.float64, device=dev)
-        set_hash = None
+        set_hash, per_rank = None, None
         if dist:
+            hs = info.get("host_seconds") or {}
+            mine = torch.tensor([hs.get("run", 0.0), hs.get("steal_wait", 0.0), float(st["nodes"]), float(st["steals_received"]),
+                                 float(st["steals_served"]), float(st["launches"])], dtype=torch.float64, device=dev)
+            allr = torch.zeros(world * mine.numel(), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allr, mine)
+            per_rank = allr.cpu().numpy().reshape(world, -1)
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -347,6 +362,10 @@ def run_bandb(torch, xc, dist, rank, world, local, names):
                    "reference_cpu_nodes": g["ref_bandb_nodes"] if name not in BANDB_GOLDEN else None,
                    "reference_cpu_source": "golden-time (measured when tests/golden/datasets.json was generated, another machine)"
                    if name not in BANDB_GOLDEN else "not available: the reference does not finish this search in 45 CPU-minutes"}
+            if per_rank is not None:
+                rec["per_rank"] = {"run_s": [round(float(x), 4) for x in per_rank[:, 0]], "steal_wait_s": [round(float(x), 4) for x in per_rank[:, 1]],
+                                   "nodes": [int(x) for x in per_rank[:, 2]], "steals_received": [int(x) for x in per_rank[:, 3]],
+                                   "steals_served": [int(x) for x in per_rank[:, 4]], "launches": [int(x) for x in per_rank[:, 5]]}
             if solo:
                 rec.update({"one_gpu_same_run_s": solo["s"], "one_gpu_same_run_nodes": solo["nodes"], "one_gpu_same_run_ok": solo["ok"],
                             "speedup_vs_one_gpu": solo["s"] / wall, "efficiency": solo["s"] / wall / world,

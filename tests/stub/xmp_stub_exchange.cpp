@@ -53,12 +53,6 @@ struct HostOps {
 		if (old) *old = o;
 		return 0;
 	}
-	int cas(unsigned r, unsigned w, unsigned expect, unsigned v, unsigned *old) {
-		unsigned e = expect;
-		region()->word[r][w].compare_exchange_strong(e, v);
-		*old = e;
-		return 0;
-	}
 	int gather(unsigned w, unsigned *out) {
 		for (unsigned r = 0; r < c->xch_world; ++r) out[r] = region()->word[r][w].load();
 		return 0;
@@ -68,10 +62,14 @@ struct HostOps {
 
 struct HostEng {
 	xmp_ctx *c;
-	// half of the open subtrees, oldest (shallowest) first, never the only one
-	int export_for_steal(unsigned *n) {
+	// the share t / (t + 1) of the open subtrees for t thieves, oldest (shallowest) first, never the only one
+	int export_for_steal(unsigned thieves, unsigned *n) {
 		const size_t open = c->n_jobs - c->head;
-		unsigned k = open < 2 ? 0 : (unsigned) (open / 2);
+		unsigned k = 0;
+		if (open >= 2) {
+			k = (unsigned) ((open * thieves + thieves) / (thieves + 1));
+			if (k >= open) k = (unsigned) open - 1;
+		}
 		if (k > XCH_MAX_JOBS) k = XCH_MAX_JOBS;
 		c->staged = (uint8_t *) realloc(c->staged, (size_t) (k ? k : 1) * c->n);
 		for (unsigned i = 0; i < k; ++i) memcpy(c->staged + (size_t) i * c->n, c->jobs + c->head++ * c->n, c->n);
@@ -80,8 +78,9 @@ struct HostEng {
 		*n = k;
 		return 0;
 	}
-	int send_staged(unsigned thief, unsigned n) {
-		memcpy(region()->mail[thief], c->staged, (size_t) n * c->n);
+	int send_staged(unsigned thief, unsigned i, unsigned k, unsigned n) {
+		unsigned out = 0;
+		for (unsigned j = i; j < n; j += k) memcpy(region()->mail[thief] + (size_t) out++ * c->n, c->staged + (size_t) j * c->n, c->n);
 		return 0;
 	}
 	int import_mailbox(unsigned n) {
@@ -146,7 +145,9 @@ int stub_xch_after_job(xmp_ctx *c) {
 	HostEng eng{c};
 	const size_t open = c->n_jobs - c->head;
 	region()->word[c->xch_rank][XW_OPEN].store((unsigned) open);
-	const int rc = xch_service(ops, eng, c->xch_rank, region()->word[c->xch_rank][XW_REQUEST].load(), false);
+	unsigned w[XW_COUNT];
+	ops.snapshot(w);
+	const int rc = xch_service(ops, eng, c->xch_rank, c->xch_world, w, false);
 	region()->word[c->xch_rank][XW_OPEN].store((unsigned) (c->n_jobs - c->head));
 	return rc;
 }

@@ -20,7 +20,7 @@ int cuda_failed(cudaError_t e, const char *what, const char *file, int line);
 
 struct Search;
 
-// The exchange block of a context: 256 KiB of device memory that peers can map (exchange.cu, exchange_proto.h).
+// The exchange block of a context: 2 MiB of device memory that peers can map (exchange.cu, exchange_proto.h).
 //   [0, 1024)      the search's counter block; word 0 is the upper bound, words 112-119 the protocol's control words
 //   [1024, 1280)   XchPeerTable: every rank's block as THIS device addresses it (read by the kernels and by k_xch_gather)
 //   [2048, ...)    mailbox: job descriptors (insertion paths) written by a donor over NVLink
@@ -28,7 +28,7 @@ struct XchPeerTable {
 	unsigned *blk[16];
 	unsigned world, rank;
 };
-#define XCH_BLOCK_BYTES ((size_t) 256 << 10)
+#define XCH_BLOCK_BYTES ((size_t) 2 << 20)
 #define XCH_TABLE_OFF 1024
 #define XCH_MAILBOX_BYTE_OFF 2048
 

@@ -28,8 +28,7 @@ __global__ void k_xch_rmw(unsigned *word, int op, unsigned a, unsigned b, unsign
 		old = atomicExch_system(word, a);
 		break;
 	case 1: old = atomicAdd_system(word, a); break;
-	case 2: old = atomicCAS_system(word, a, b); break;
-	default: old = atomicMin_system(word, a); break;
+	default: old = atomicMin_system(word, a + 0u * b); break;
 	}
 	__threadfence_system();
 	*result = old;                           // pinned host memory
@@ -82,6 +81,11 @@ static int xch_finish_connect(xmp_ctx *ctx, unsigned rank, unsigned world) {
 	ctx->xch_rank = rank;
 	ctx->xch_world = world;
 	ctx->xch_connected = world > 1;
+	// first launches load the kernels' code (lazy module loading, milliseconds): not inside somebody's search
+	k_xch_rmw<<<1, 1, 0, ctx->stream>>>(ctx->xch + 7, 1, 0u, 0u, ctx->h_xres);
+	k_xch_gather<<<1, 32, 0, ctx->stream>>>((const XchPeerTable *) ((char *) ctx->xch + XCH_TABLE_OFF), XW_OPEN, ctx->h_xres + 40);
+	XMP_CUDA(cudaGetLastError());
+	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
 	return XMP_OK;
 }
 
@@ -97,41 +101,41 @@ struct DevOps {
 	}
 	int store(unsigned r, unsigned w, unsigned v) { return rmw(r, w, 0, v, 0, nullptr); }
 	int add(unsigned r, unsigned w, unsigned delta, unsigned *old) { return rmw(r, w, 1, delta, 0, old); }
-	int cas(unsigned r, unsigned w, unsigned expect, unsigned v, unsigned *old) { return rmw(r, w, 2, expect, v, old); }
 	int snapshot(unsigned *out) {
 		XMP_CUDA(cudaMemcpyAsync(ctx->h_xres + 16, ctx->xch + XW_FIRST, XW_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		memcpy(out, ctx->h_xres + 16, XW_COUNT * sizeof(unsigned));
+		memcpy(out, ctx->h_xres + 16, XW_COUNT * sizeof(unsigned));           // h_xres: [0] rmw result, [8] hint, [16, 40) snapshot, [40, 56) gather
 		return XMP_OK;
 	}
 	int gather(unsigned w, unsigned *out) {
-		k_xch_gather<<<1, 32, 0, ctx->stream>>>((const XchPeerTable *) ((char *) ctx->xch + XCH_TABLE_OFF), w, ctx->h_xres + 32);
+		k_xch_gather<<<1, 32, 0, ctx->stream>>>((const XchPeerTable *) ((char *) ctx->xch + XCH_TABLE_OFF), w, ctx->h_xres + 40);
 		XMP_CUDA(cudaGetLastError());
 		XMP_CUDA(cudaStreamSynchronize(ctx->stream));
-		memcpy(out, ctx->h_xres + 32, ctx->xch_world * sizeof(unsigned));
+		memcpy(out, ctx->h_xres + 40, ctx->xch_world * sizeof(unsigned));
 		return XMP_OK;
 	}
 	void pause() { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
 };
 
 // search.cu: the engine side of the protocol
-int search_export_for_steal(xmp_ctx *ctx, unsigned *n);
-int search_send_staged(xmp_ctx *ctx, unsigned thief, unsigned n);
+int search_export_for_steal(xmp_ctx *ctx, unsigned k, unsigned *n);
+int search_send_staged(xmp_ctx *ctx, unsigned thief, unsigned i, unsigned k, unsigned n);
 int search_import_mailbox(xmp_ctx *ctx, unsigned n);
 int search_after_steal(xmp_ctx *ctx, bool finished);
 
 struct DevEng {
 	xmp_ctx *ctx;
-	int export_for_steal(unsigned *n) { return search_export_for_steal(ctx, n); }
-	int send_staged(unsigned thief, unsigned n) { return search_send_staged(ctx, thief, n); }
+	int export_for_steal(unsigned k, unsigned *n) { return search_export_for_steal(ctx, k, n); }
+	int send_staged(unsigned thief, unsigned i, unsigned k, unsigned n) { return search_send_staged(ctx, thief, i, k, n); }
 	int import_mailbox(unsigned n) { return search_import_mailbox(ctx, n); }
 };
 
-// Called by the search between sweeps: answers a pending request out of the open frontier.
-int xch_service_request(xmp_ctx *ctx, unsigned request) {
+// Called by the search between sweeps: answers the pending requests out of the open frontier.
+// words = this rank's protocol words (XW_FIRST ...) as they came back with the sweep's counters.
+int xch_service_requests(xmp_ctx *ctx, const unsigned *words) {
 	DevOps ops{ctx};
 	DevEng eng{ctx};
-	return xch_service(ops, eng, ctx->xch_rank, request, false);
+	return xch_service(ops, eng, ctx->xch_rank, ctx->xch_world, words, false);
 }
 
 }  // namespace xmp

@@ -11,53 +11,63 @@
 // and across processes.  No collectives, no lock-step rounds: a steal involves the idle rank and one donor.
 //
 // Words of a rank's block (indices into its 1 KiB counter block, see search.cu for the others):
-//   XW_BOUND     the upper bound.  Written by local kernels (atomicMin) and by peers (system-scope atomicMin).
-//   XW_REQUEST   0 = free, r + 1 = rank r asks this rank for work (set by the thief's compare-and-swap).
-//   XW_REPLY     0 = waiting, 1 + k = the donor put k jobs into this rank's mailbox (k = 0: it had none to give).
-//   XW_FINISHED  1 = the search is over everywhere (written into every block by the rank that went idle last).
-//   XW_BUSY      rank 0's block only: ranks that hold work, plus jobs travelling.  A donor adds the thief BEFORE the
-//                jobs leave, a rank subtracts itself when its frontier runs dry; 0 is reached exactly once.
-//   XW_OPEN      hint, published by the owner: open subtrees it could give away right now.
+//   XW_BOUND       the upper bound.  Written by local kernels (atomicMin) and by peers (system-scope atomicMin).
+//   XW_REQUEST + r 1 = rank r asks this rank for work (one slot per thief: a plain store, and a donor can serve every
+//                  waiting thief between two sweeps).
+//   XW_REPLY       0 = waiting, 1 + k = the donor put k jobs into this rank's mailbox (k = 0: it had none to give).
+//   XW_FINISHED    1 = the search is over everywhere (written into every block by the rank that went idle last).
+//   XW_BUSY        rank 0's block only: ranks that hold work, plus jobs travelling.  A donor adds the thief BEFORE the
+//                  jobs leave, a rank subtracts itself when its frontier runs dry; 0 is reached exactly once.
+//   XW_OPEN        hint, published by the owner: 0 = nothing to give, 1 = a single open subtree (kept), larger = an
+//                  estimate of the work behind what it could give away (thieves ask the largest).
 // Invariants (the ones the reference model-checked for its MPI protocol, spin/fastdnamp.mpiprom): every job is held
 // by exactly one rank or is in exactly one mailbox whose owner is waiting for it; a rank only stops after XW_BUSY
-// reached 0, i.e. when no rank holds work and nothing travels; no request is left unanswered while the search runs
-// (idle ranks answer "nothing" from their waiting loop).
+// reached 0, i.e. when no rank holds work and nothing travels; a thief has at most one request out and waits for its
+// reply; no request is left unanswered while the search runs (idle ranks answer "nothing" from their waiting loop).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
 
 namespace xmp {
 
-enum : unsigned { XW_BOUND = 0, XW_REQUEST = 112, XW_REPLY = 113, XW_FINISHED = 114, XW_BUSY = 115, XW_OPEN = 116, XW_FIRST = 112, XW_COUNT = 8 };
-enum : unsigned { XCH_MAX_RANKS = 16, XCH_MAX_JOBS = 2048 };
+enum : unsigned { XCH_MAX_RANKS = 16, XCH_MAX_JOBS = 16384 };
+enum : unsigned { XW_BOUND = 0, XW_FIRST = 232, XW_REQUEST = 232, XW_REPLY = 248, XW_FINISHED = 249, XW_BUSY = 250, XW_OPEN = 251, XW_COUNT = 24 };
 enum : int { XCH_GOT_WORK = 1, XCH_FINISHED = 2 };
 
 // Ops (all return 0 or an error code; `r` is a rank, `w` a word index):
 //   snapshot(unsigned out[XW_COUNT])            this rank's words XW_FIRST .. XW_FIRST + XW_COUNT - 1
 //   store(r, w, v)                              release store (everything this rank wrote before is visible first)
 //   add(r, w, delta, unsigned *old)             atomic add, returns the previous value
-//   cas(r, w, expect, v, unsigned *old)         atomic compare-and-swap, returns the previous value
 //   gather(w, unsigned out[world])              word w of every rank's block
 //   pause()                                     a short wait between polls
 // Eng:
-//   export_for_steal(unsigned *n)               detaches up to XCH_MAX_JOBS open subtrees into a staging buffer (n = 0: none to spare)
-//   send_staged(thief, n)                       copies the staged job descriptors into the thief's mailbox
+//   export_for_steal(k, unsigned *n)            detaches open subtrees for k thieves into a staging buffer (n = 0: none to
+//                                               spare); thief i of k is meant to get staged jobs i, i + k, i + 2k, ...
+//   send_staged(thief, i, k, n)                 copies that share of the n staged descriptors into the thief's mailbox
 //   import_mailbox(n)                           turns n job descriptors in this rank's mailbox into open subtrees
 
-// Answers a pending steal request.  `idle`: this rank has nothing to give (it is waiting for work itself).
+// Answers every pending steal request (words = this rank's snapshot).  `idle`: this rank has nothing to give (it is
+// waiting for work itself).
 template <class Ops, class Eng>
-int xch_service(Ops &ops, Eng &eng, unsigned rank, unsigned request, bool idle) {
-	if (request == 0) return 0;
-	const unsigned thief = request - 1;
+int xch_service(Ops &ops, Eng &eng, unsigned rank, unsigned world, const unsigned *words, bool idle) {
+	unsigned thieves[XCH_MAX_RANKS], k = 0;
+	for (unsigned r = 0; r < world; ++r)
+		if (r != rank && words[XW_REQUEST - XW_FIRST + r]) thieves[k++] = r;
+	if (k == 0) return 0;
 	unsigned n = 0;
-	int rc = idle ? 0 : eng.export_for_steal(&n);
+	int rc = idle ? 0 : eng.export_for_steal(k, &n);
 	if (rc) return rc;
-	if ((rc = ops.store(rank, XW_REQUEST, 0)) != 0) return rc;             // the slot is free for the next thief
-	if (n) {
-		if ((rc = ops.add(0, XW_BUSY, 1u, nullptr)) != 0) return rc;        // the thief counts as busy before the jobs travel
-		if ((rc = eng.send_staged(thief, n)) != 0) return rc;
+	for (unsigned i = 0; i < k; ++i) {
+		const unsigned thief = thieves[i];
+		const unsigned share = n > i ? (n - i + k - 1) / k : 0;            // jobs i, i + k, ... of n
+		if ((rc = ops.store(rank, XW_REQUEST + thief, 0)) != 0) return rc; // the slot is free again
+		if (share) {
+			if ((rc = ops.add(0, XW_BUSY, 1u, nullptr)) != 0) return rc;    // the thief counts as busy before the jobs travel
+			if ((rc = eng.send_staged(thief, i, k, n)) != 0) return rc;
+		}
+		if ((rc = ops.store(thief, XW_REPLY, 1u + share)) != 0) return rc;
 	}
-	return ops.store(thief, XW_REPLY, 1u + n);
+	return 0;
 }
 
 // Called when this rank's frontier has run dry.  Returns with *result = XCH_GOT_WORK (stolen subtrees are open in
@@ -77,7 +87,7 @@ int xch_steal(Ops &ops, Eng &eng, unsigned rank, unsigned world, int *result) {
 	for (;;) {
 		if ((rc = ops.snapshot(w)) != 0) return rc;
 		if (w[XW_FINISHED - XW_FIRST]) break;
-		if ((rc = xch_service(ops, eng, rank, w[XW_REQUEST - XW_FIRST], true)) != 0) return rc;
+		if ((rc = xch_service(ops, eng, rank, world, w, true)) != 0) return rc;
 		if ((rc = ops.gather(XW_OPEN, open)) != 0) return rc;
 		unsigned victim = world, best = 1;
 		for (unsigned k = 0; k < world; ++k) {
@@ -86,16 +96,11 @@ int xch_steal(Ops &ops, Eng &eng, unsigned rank, unsigned world, int *result) {
 		}
 		if (victim == world) { ops.pause(); continue; }                    // nobody has anything to spare right now
 		if ((rc = ops.store(rank, XW_REPLY, 0u)) != 0) return rc;
-		if ((rc = ops.cas(victim, XW_REQUEST, 0u, rank + 1u, &old)) != 0) return rc;
-		if (old != 0) {                                                    // another thief is being served there
-			first = (victim + 1) % world;
-			ops.pause();
-			continue;
-		}
+		if ((rc = ops.store(victim, XW_REQUEST + rank, 1u)) != 0) return rc;
 		for (;;) {                                                         // one request, one reply
 			if ((rc = ops.snapshot(w)) != 0) return rc;
 			if (w[XW_REPLY - XW_FIRST] || w[XW_FINISHED - XW_FIRST]) break;
-			if ((rc = xch_service(ops, eng, rank, w[XW_REQUEST - XW_FIRST], true)) != 0) return rc;
+			if ((rc = xch_service(ops, eng, rank, world, w, true)) != 0) return rc;
 			ops.pause();
 		}
 		const unsigned reply = w[XW_REPLY - XW_FIRST];

@@ -30,6 +30,7 @@
 // Results are independent of batch order: ties are kept (<=), the bound only decreases, every tree
 // recorded carries its length and the final filter keeps those equal to the final bound.
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 #include <thread>
 #include <stdlib.h>
@@ -661,7 +662,7 @@ struct Search {
 	bool done = false, finished = false;
 	bool fused_last = false;      // the deepest pool is never materialised (k_expand_last_fused)
 	bool eager = false;           // nodes carry their insertion costs instead of MIDPOINT sets (Layout::off_cost)
-	unsigned min_batch = 32768, beam = 512;
+	unsigned min_batch = 32768, beam = 4096;
 	unsigned maxdepth[XMP_MAX_TAXA + 2] = {0};   // deepest tree seen so far per tree size (sizes the walk kernels' stacks)
 	unsigned *d_maxdepth = nullptr, *d_overflow = nullptr;
 	xmp_search_stats st;
@@ -1196,6 +1197,12 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 		if (chunk >= std::min<unsigned long long>(S->min_batch, S->pool[m].cap)) worthwhile = true;
 		if (chunk > best_chunk) { best_chunk = chunk; best_level = m; }
 	}
+	// A sparse frontier (fewer open trees in all than one worthwhile batch: the tail of a search, or a thief that has
+	// just been handed a few subtrees) is a chain of latencies whatever is done; then every level goes in the same sweep,
+	// so that the chain is as long as the remaining subtrees are deep, not as their levels are many.
+	unsigned long long open_total = 0;
+	for (unsigned m = 3; m + 1 < n; ++m) open_total += S->pool[m].count;
+	const bool sparse = open_total < S->min_batch;
 	// pass 0 applies the selection above; pass 1 (only if pass 0 launched nothing) lets every level go that can
 	for (int pass = 0; pass < 2 && n_items == 0; ++pass) {
 		for (unsigned m = n - 2; m >= 3; --m) {
@@ -1218,7 +1225,7 @@ static int run_sweep(xmp_ctx *ctx, Search *S, bool *any) {
 			if (pass == 0) {
 				if (worthwhile) {
 					if (chunk < std::min<unsigned long long>(S->min_batch, P.cap)) continue;
-				} else if (S->sweep_fallback == 1 && m != best_level) {
+				} else if (S->sweep_fallback == 1 && !sparse && m != best_level) {
 					continue;
 				}
 			}
@@ -1314,18 +1321,31 @@ static int dive(xmp_ctx *ctx, Search *S) {
 static void init_knobs(xmp_ctx *ctx, Search *S) {
 	S->n = ctx->num_taxa;
 	S->min_batch = std::max(env_unsigned("XMP_MIN_BATCH", 32768), 1u);
-	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 512), 4096u), 1u);
+	// the dive costs about a millisecond whatever its width now that the beam is cut on the device; a wider beam finds
+	// the optimum (or a length next to it) more often: mh1 55 M -> 28 M nodes, h4 ~260 M -> 217 M (profiles/r02_beam_ab.md)
+	S->beam = std::max(std::min(env_unsigned("XMP_BEAM", 4096), 65536u), 1u);
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
 }
 
-// Detaches open partial trees of the shallowest level that has any -- the reference's thief takes "the last unprocessed
-// edge at the victim's shallowest open level" (src/mpiworker.c:169-181) -- and stages their job descriptors (insertion
-// paths, byte 0 = tree size) in S->pathbuf on the device.  keep_half: leave at least half of that level (and never the
-// only open tree) to the owner; otherwise up to max_nodes are taken.
-static int detach_jobs(xmp_ctx *ctx, Search *S, unsigned max_nodes, bool keep_half, unsigned *n_out) {
+// How much work a tree on m + 1 taxa stands for, relative to one on m taxa, when a donor decides what to give away and
+// a thief whom to ask.  Unpruned it would be 1 / (2m - 3); under the bound the search trees measured here grow by a
+// factor of 1 to 2.5 per tree size in their busy middle (profiles/r02_probe_long_workloads_raw.txt), so most of the
+// remaining work sits deep, and a share of it means a share of the deeper levels too.
+static const double STEAL_LEVEL_WEIGHT = 0.5;
+
+// Detaches open partial trees and stages their job descriptors (insertion paths, byte 0 = tree size) in S->pathbuf on
+// the device.  The reference's thief takes "the last unprocessed edge at the victim's shallowest open level"
+// (src/mpiworker.c:169-181); here
+//   thieves == 0  (xmp_cuda_search_export_jobs): up to max_nodes trees of the shallowest open level;
+//   thieves == k  (a donor serving k idle ranks at once): the share k / (k + 1) of the WORK behind the open trees
+//                 (STEAL_LEVEL_WEIGHT per tree size), taken from the shallowest levels down -- never the only open tree,
+//                 at least one tree per thief, at most XCH_MAX_JOBS.  Handing out one shallow tree per request was
+//                 measured on 8 GPUs: the rank with the largest share of its36 served 256 requests, each good for
+//                 ~1.5 ms of work, and was still the last to finish.
+static int detach_jobs(xmp_ctx *ctx, Search *S, unsigned max_nodes, unsigned thieves, unsigned *n_out) {
 	const Layout &L = S->L;
 	*n_out = 0;
 	// A sharded search deals the frontier out by hash when it expands the level below split_level; a node from a
@@ -1333,37 +1353,65 @@ static int detach_jobs(xmp_ctx *ctx, Search *S, unsigned max_nodes, bool keep_ha
 	// past the deal ever change hands (the shallow prefix is a handful of nodes, gone after the first sweeps).
 	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
 	unsigned long long open = 0;
-	for (unsigned m = m0; m < S->n; ++m) open += S->pool[m].count;
-	if (keep_half && open < 2) return XMP_OK;
+	double work = 0, unit = 1;
 	for (unsigned m = m0; m < S->n; ++m) {
+		if (!S->pend[m].active) {
+			open += S->pool[m].count;
+			work += (double) S->pool[m].count * unit;
+		}
+		unit *= STEAL_LEVEL_WEIGHT;
+	}
+	if (thieves && open < 2) return XMP_OK;
+	const double target = work * (double) thieves / (double) (thieves + 1);
+	int rc = S->pathbuf.reserve((size_t) std::max<unsigned>(max_nodes, 256) * L.n);
+	if (rc) return rc;
+	unsigned total = 0;
+	double got = 0;
+	unit = 1;
+	for (unsigned m = m0; m < S->n && total < max_nodes; unit *= STEAL_LEVEL_WEIGHT, ++m) {
 		Pool &P = S->pool[m];
-		if (P.count == 0) continue;
-		if (S->pend[m].active) continue;      // its oldest nodes are half expanded; newer ones sit behind them in the ring
-		unsigned long long want = keep_half ? std::max<unsigned long long>(1, P.count / 2) : P.count;
-		unsigned k = (unsigned) std::min<unsigned long long>(want, max_nodes);
+		if (P.count == 0 || S->pend[m].active) continue;      // pending: its oldest nodes are half expanded; newer ones sit behind them in the ring
+		unsigned long long want = P.count;
+		if (thieves) {
+			if (got >= target && total >= thieves) break;
+			const double need = std::max((target - got) / unit, (double) (total < thieves ? thieves - total : 0));
+			want = (unsigned long long) std::min((double) P.count, std::ceil(need));
+			if (want >= open) want = open - 1;                                  // keep one tree to work on
+		}
+		unsigned k = (unsigned) std::min<unsigned long long>(want, max_nodes - total);
 		const unsigned long long tail = P.slot(P.count);         // one past the newest node
 		if (tail != 0) k = (unsigned) std::min<unsigned long long>(k, tail);   // stay on this side of the wrap
+		if (k == 0) continue;
 		const unsigned long long from = (tail == 0 ? P.cap : tail) - k;
-		int rc = S->pathbuf.reserve((size_t) std::max<unsigned>(k, 256) * L.n);
-		if (rc) return rc;
-		k_read_paths<<<(k + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, from, k, (uint8_t *) S->pathbuf.ptr);
+		k_read_paths<<<(k + 127) / 128, 128, 0, ctx->stream>>>(P.view(), L, m, from, k, (uint8_t *) S->pathbuf.ptr + (size_t) total * L.n);
 		XMP_CUDA(cudaGetLastError());
 		S->st.launches += 1;
 		P.count -= k;
-		*n_out = k;
-		return XMP_OK;
+		open -= k;
+		total += k;
+		got += (double) k * unit;
+		if (!thieves) break;
 	}
+	*n_out = total;
 	return XMP_OK;
 }
 
 // ---- the engine side of the exchange protocol (exchange_proto.h, exchange.cu) -------------------------
-// Open subtrees this rank could give away right now, published as a hint for idle ranks.
+// What this rank could give away right now, published as a hint for idle ranks: 0 = nothing, 1 = a single open tree
+// (not given away), otherwise 2 + an estimate of the work behind its open trees (STEAL_LEVEL_WEIGHT per tree size),
+// which ranks a rank holding shallow trees above one holding as many deep ones -- that is where thieves should go.
 static int publish_open(xmp_ctx *ctx, Search *S) {
 	const unsigned m0 = S->prm.shard_count > 1 ? std::max(3u, S->split_level) : 3u;
 	unsigned long long open = 0;
-	for (unsigned m = m0; m < S->n; ++m)
-		if (!S->pend[m].active) open += S->pool[m].count;
-	const unsigned v = (unsigned) std::min<unsigned long long>(open, 0x7fffffffu);
+	double work = 0, unit = (double) (1u << 20);
+	for (unsigned m = m0; m < S->n; ++m) {
+		if (!S->pend[m].active) {
+			open += S->pool[m].count;
+			work += (double) S->pool[m].count * unit;
+		}
+		unit *= STEAL_LEVEL_WEIGHT;
+	}
+	const unsigned v = open < 2 ? (unsigned) open : 2u + (unsigned) std::min(work, 2.0e9);
 	if (v == S->open_published) return XMP_OK;
 	S->open_published = v;
 	ctx->h_xres[8] = v;           // pinned; a later value overtaking this copy is just as good a hint
@@ -1371,9 +1419,9 @@ static int publish_open(xmp_ctx *ctx, Search *S) {
 	return XMP_OK;
 }
 
-int search_export_for_steal(xmp_ctx *ctx, unsigned *n) {
+int search_export_for_steal(xmp_ctx *ctx, unsigned k, unsigned *n) {
 	Search *S = ctx->search;
-	int rc = detach_jobs(ctx, S, XCH_MAX_JOBS, true, n);
+	int rc = detach_jobs(ctx, S, XCH_MAX_JOBS, k, n);
 	if (rc == XMP_OK && *n) {
 		S->steals_served += 1;
 		rc = publish_open(ctx, S);
@@ -1381,11 +1429,14 @@ int search_export_for_steal(xmp_ctx *ctx, unsigned *n) {
 	return rc;
 }
 
-// Donor -> thief: the staged descriptors go straight from this GPU's memory into the thief's mailbox (a peer-to-peer
-// copy over NVLink; the addresses are peer-mapped, cudaMemcpyDefault resolves them).
-int search_send_staged(xmp_ctx *ctx, unsigned thief, unsigned n) {
+// Donor -> thief: staged descriptors i, i + k, i + 2k, ... (a mix of shallow and deeper subtrees for every thief) go
+// straight from this GPU's memory into the thief's mailbox -- a strided peer-to-peer copy over NVLink; the addresses
+// are peer-mapped, cudaMemcpyDefault resolves them.
+int search_send_staged(xmp_ctx *ctx, unsigned thief, unsigned i, unsigned k, unsigned n) {
 	Search *S = ctx->search;
-	XMP_CUDA(cudaMemcpyAsync((char *) ctx->xch_peer[thief] + XCH_MAILBOX_BYTE_OFF, S->pathbuf.ptr, (size_t) n * S->L.n, cudaMemcpyDefault, ctx->stream));
+	const size_t rec = S->L.n, share = (n - i + k - 1) / k;
+	XMP_CUDA(cudaMemcpy2DAsync((char *) ctx->xch_peer[thief] + XCH_MAILBOX_BYTE_OFF, rec, (const char *) S->pathbuf.ptr + (size_t) i * rec, (size_t) k * rec,
+	                           rec, share, cudaMemcpyDefault, ctx->stream));
 	return XMP_OK;
 }
 
@@ -1416,7 +1467,12 @@ int search_after_steal(xmp_ctx *ctx, bool finished) {
 	return rc;
 }
 
-int xch_service_request(xmp_ctx *ctx, unsigned request);
+int xch_service_requests(xmp_ctx *ctx, const unsigned *words);
+static bool requests_pending(const Search *S, const xmp_ctx *ctx) {
+	for (unsigned r = 0; r < ctx->xch_world; ++r)
+		if (S->h_pin[XW_REQUEST + r]) return true;
+	return false;
+}
 
 // The two halves of xmp_cuda_search_begin that talk to the device (split out so that every failure takes the same
 // tear-down path in the caller).
@@ -1498,13 +1554,18 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	rc = begin_bound(ctx, S);
 	if (rc) return fail(rc);
 
-	// Where the frontier is dealt out to shards: the first tree size with >= 64 subtrees per shard.
+	// Where the frontier is dealt out to shards: the first tree size with >= 4096 subtrees per shard.  The deal is the
+	// load balance: subtree sizes are heavy-tailed, and only thousands of them per shard even out (measured on 8 GPUs
+	// with 64 per shard: its36 under -Bd left one GPU with twice the work of the others, and stealing cannot repair that
+	// cheaply -- a thief only ever gets what is open between two sweeps).  The shallow prefix that every shard expands
+	// redundantly stays a few thousand trees (XMP_SPLIT_PER_SHARD overrides the 4096).
 	S->split_level = 0;
 	if (S->prm.shard_count > 1) {
 		unsigned s = S->prm.split_level;
 		if (s == 0) {
+			const double per_shard = (double) std::max(env_unsigned("XMP_SPLIT_PER_SHARD", 4096), 1u);
 			s = 4;
-			while (s + 1 < S->n && odd_factorial(s) < 64.0 * S->prm.shard_count) ++s;
+			while (s + 2 < S->n && odd_factorial(s) < per_shard * S->prm.shard_count) ++s;
 		}
 		if (s < 4) s = 4;
 		if (s > S->n - 1) s = S->n - 1;
@@ -1542,7 +1603,7 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 			// one rank of a multi-GPU search: publish what could be given away, answer a waiting thief
 			// (the request word came back with this sweep's counters)
 			rc = publish_open(ctx, S);
-			if (rc == XMP_OK && S->h_pin[XW_REQUEST]) rc = xch_service_request(ctx, S->h_pin[XW_REQUEST]);
+			if (rc == XMP_OK && requests_pending(S, ctx)) rc = xch_service_requests(ctx, S->h_pin + XW_FIRST);
 			if (rc) break;
 		}
 	}
@@ -1585,7 +1646,7 @@ extern "C" int xmp_cuda_search_run(xmp_ctx *ctx, unsigned max_batches, int *done
 		++batches;
 		if (S->d_peers) {
 			rc = publish_open(ctx, S);
-			if (rc == XMP_OK && S->h_pin[XW_REQUEST]) rc = xch_service_request(ctx, S->h_pin[XW_REQUEST]);
+			if (rc == XMP_OK && requests_pending(S, ctx)) rc = xch_service_requests(ctx, S->h_pin + XW_FIRST);
 			if (rc) break;
 		}
 	}
@@ -1641,7 +1702,7 @@ extern "C" int xmp_cuda_search_export_jobs(xmp_ctx *ctx, unsigned max_nodes, uin
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	*n_jobs = 0;
 	unsigned k = 0;
-	int rc = detach_jobs(ctx, S, max_nodes, false, &k);
+	int rc = detach_jobs(ctx, S, max_nodes, 0, &k);
 	if (rc || k == 0) return rc;
 	XMP_CUDA(cudaMemcpyAsync(jobs, S->pathbuf.ptr, (size_t) k * S->L.n, cudaMemcpyDeviceToHost, ctx->stream));
 	XMP_CUDA(cudaStreamSynchronize(ctx->stream));
