@@ -582,7 +582,7 @@ def run_ours(args):
                         "n_gpus": world, "datasets": bandb}
     if bandb_error is not None:
         out["bandb"] = {"error": bandb_error}
-    if world == 1:
+    if world == 1 and not os.environ.get("XMP_BENCH_SKIP_CPU"):       # A/B runs: skip the 12-second CPU leg
         rows = rows_np
         threads = os.cpu_count() or 1
         done, secs, kind, score_s, cpu_costs = cpu_cost_of_trees(wl["paths"], rows, M, threads, 12.0)

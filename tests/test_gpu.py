@@ -293,11 +293,12 @@ def test_search_without_informative_sites(xc, tmp_path):
     assert p.newick_list(paths) == want_trees
 
 
-def test_search_deep_with_the_cap_applied_inside_the_library(xc, alignment_dir, goldens):
+@pytest.mark.parametrize("name", ["53humans.26", "53humans.29"])
+def test_search_deep_with_the_cap_applied_inside_the_library(xc, alignment_dir, goldens, name):
     """max_trees handed to the library: a shard that holds more than a million optimal trees cuts its set back to the
     first max_trees in the reference's depth-first order and goes on counting (src/yanbader.c:272-293), so the memory
-    of a capped search stays bounded.  53humans.26: 9.8 M optimal trees, the reference's first 1000."""
-    name = "53humans.26"
+    of a capped search stays bounded.  53humans.26: 9.8 M optimal trees; 53humans.29: 88.4 M (seven minutes in the
+    reference, seventeen to count them all) -- the reference's first 1000 and its total count."""
     g = goldens[name]
     a, p = prepare(alignment_dir, goldens, name)
     cap = int(g["flags"][g["flags"].index("-m") + 1])

@@ -9,6 +9,7 @@
 // No tensor cores; the design points are coalesced 128-bit loads, enough independent loads in flight
 // per SM to cover HBM latency, and one reduction per (pair, tile).
 #include <stdlib.h>
+#include <algorithm>
 #include "ctx.h"
 
 namespace xmp {
@@ -360,73 +361,146 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Topologies -> insertion costs in one pass, for wide state sets: the MIDPOINT sets are formed in
-// registers / local arrays and scored at once, never written to HBM (saves 1.5 B written + 0.5 B read
-// per site-merge against k_build_sets followed by k_score_wide).  One CTA = one tree x 256 columns, so
-// every lane of a warp follows the same topology (coalesced local arrays); per-edge costs are summed by
-// warp shuffle, then shared-memory atomics, then one global RED per (tree, edge, tile).
+// Topologies -> insertion costs in one pass, for wide state sets: the MIDPOINT sets are formed on the fly and scored
+// at once, never written to HBM (saves 1.5 B written + 0.5 B read per site-merge against k_build_sets followed by
+// k_score_wide).  A CTA owns a tile of blockDim.x columns and walks a chunk of trees over it; every lane follows the
+// same topology, every branch is uniform.
+//
+// All per-thread state with dynamic indexing lives in SHARED memory as "slots" of one 128-bit block per thread (slot s
+// of thread t at sm[s * blockDim.x + t]: conflict-free):
+//     [0, m]        the rows of taxa 0 .. m for this column tile -- loaded once per CTA, shared by all its trees
+//     m + 1         all ones (the neutral element: F(x, ones) = x), so that the root's child needs no special case
+//     then m - 2    UP sets of the internal edges, m - 2 DOWN sets of the internal edges, one slot nobody reads
+// Per tree the first 2m-3 threads turn the topology into two small step tables of slot numbers (shared memory,
+// read back as broadcasts), so the walk itself is branch-free: per pre-order position three slot loads, one store,
+// two merges, one cost, one warp reduction (REDUX).  History (profiles/r02_ncu_k_score_trees_wide.md): the first
+// version kept `uint4 up[2m-3], down[2m-3]` as local arrays -- ncu showed 55 GB of DRAM writes per launch for an
+// algorithm that needs 5 MB, because the local-memory footprint of the resident threads exceeds L2; moving only the
+// internal sets to shared memory removed the traffic but left 3,300 instructions per (tree, column) in branches and
+// 64-bit address arithmetic around 1,300 of Fitch arithmetic.
 // ---------------------------------------------------------------------------------------------
-template <int MAXE>
-__global__ void __launch_bounds__(256)
+// Shared memory by 32-bit address: the walk computes every address as (this thread's base) + (a byte offset from the step
+// table), one add per access, instead of letting the compiler rebuild generic pointers inside the loop.
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// Step tables (shared memory, read back as 16-byte broadcasts); all fields are BYTE offsets of slots, i.e. slot * 16 * blockDim.x.
+//   down step of pre-order position i:  DOWN(e) = F(src, sib);  MIDPOINT = F(upe, DOWN);  DOWN is kept at dst
+//   up step (internal edges only, children before parents):  slot dst = F(a, b)
+__global__ void __launch_bounds__(128)
 k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp, const uint8_t *__restrict__ topo,
-                   unsigned topo_stride, unsigned m, unsigned taxon, unsigned *__restrict__ cost) {
-	__shared__ unsigned acc[MAXE];
-	__shared__ uint8_t s_par[MAXE], s_k0[MAXE], s_k1[MAXE], s_pre[MAXE];
-	const unsigned tree = blockIdx.y, E = 2 * m - 3;
-	const unsigned col = blockIdx.x * 256u + threadIdx.x;
+                   unsigned topo_stride, unsigned n_trees, unsigned trees_per_cta, unsigned m, unsigned taxon,
+                   unsigned *__restrict__ cost) {
+	extern __shared__ uint4 sm[];                              // [3m - 1 slots][blockDim.x], then the step tables
+	const unsigned T = blockDim.x, E = 2 * m - 3, I = m - 2, tid = threadIdx.x, n_warps = T >> 5;
+	const unsigned n_steps = trees_per_cta * E;
+	uint4 *t_dn = sm + (size_t) (3 * m - 1) * T;               // [trees_per_cta][E]
+	uint4 *t_up = t_dn + n_steps;                              // [trees_per_cta][I]
+	unsigned *accw = (unsigned *) (t_up + trees_per_cta * I);  // [n_warps][n_steps]: per warp, written exactly once each
+	uint8_t *s_edge = (uint8_t *) (accw + n_warps * n_steps);
+	const unsigned col = blockIdx.x * T + tid;
 	const bool ok = col < n_blocks;
-	const uint8_t *t = topo + (size_t) tree * 4 * topo_stride;
-	for (unsigned i = threadIdx.x; i < E; i += 256) {
-		s_par[i] = t[i];
-		s_k0[i] = t[topo_stride + i];
-		s_k1[i] = t[2 * topo_stride + i];
-		s_pre[i] = t[3 * topo_stride + i];
-		acc[i] = 0;
-	}
-	__syncthreads();
+	const unsigned ONES = m + 1, UP0 = m + 2, DN0 = UP0 + I, DUMMY = DN0 + I, SB = 16u * T;   // SB: bytes per slot
 	const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-	uint4 up[MAXE], down[MAXE];
-	for (int i = (int) E - 1; i >= 0; --i) {
-		const unsigned e = s_pre[i];
-		if (edge_is_leaf(e)) up[e] = ok ? __ldg(rows + (size_t) edge_taxon(e) * n_blocks + col) : ones;
-		else up[e] = fitch_block(up[s_k0[e]], up[s_k1[e]]);
-	}
-	const uint4 r0 = ok ? __ldg(rows + col) : ones;
-	const uint4 rx = ok ? __ldg(rows + (size_t) taxon * n_blocks + col) : ones;
-	for (unsigned i = 0; i < E; ++i) {
-		const unsigned e = s_pre[i], p = s_par[e];
+	const unsigned t_begin = blockIdx.y * trees_per_cta, t_count = min(n_trees, t_begin + trees_per_cta) - t_begin;
+	auto up_slot = [&](unsigned y) -> unsigned { return edge_is_leaf(y) ? edge_taxon(y) : UP0 + (y / 2 - 1); };
+	// Down steps of all this CTA's trees, one thread per (tree, pre-order position): topology bytes -> byte offsets.
+	for (unsigned x = tid; x < t_count * E; x += T) {
+		const unsigned lt = x / E, i = x - lt * E;
+		const uint8_t *tp = topo + (size_t) (t_begin + lt) * 4 * topo_stride;
+		const unsigned e = tp[3 * topo_stride + i], p = tp[e];
 		uint4 d;
 		if (p == 0xFFu) {
-			d = r0;
+			d.x = 0;                                         // the root is taxon 0: DOWN of its only child is that row ...
+			d.y = ONES * SB;                                 // ... merged with the neutral element
 		} else {
-			const unsigned sib = (s_k0[p] == e) ? s_k1[p] : s_k0[p];
-			d = fitch_block(down[p], up[sib]);
+			const unsigned pk0 = tp[topo_stride + p], pk1 = tp[2 * topo_stride + p];
+			d.x = (DN0 + (p / 2 - 1)) * SB;
+			d.y = up_slot(pk0 == e ? pk1 : pk0) * SB;
 		}
-		down[e] = d;
-		unsigned c = cost_block(fitch_block(up[e], d), rx, ok ? col : 0u, wp);
-		c = warp_sum(ok ? c : 0u);
-		if ((threadIdx.x & 31u) == 0 && c) atomicAdd(&acc[e], c);
+		d.z = up_slot(e) * SB;
+		d.w = (edge_is_leaf(e) ? DUMMY : DN0 + (e / 2 - 1)) * SB;
+		t_dn[x] = d;
+		s_edge[x] = (uint8_t) e;
+	}
+	// Up steps: one thread per tree lists its internal edges in reverse pre-order.
+	if (tid < t_count) {
+		const uint8_t *tp = topo + (size_t) (t_begin + tid) * 4 * topo_stride;
+		unsigned k = 0;
+		for (int i = (int) E - 1; i >= 0; --i) {
+			const unsigned e = tp[3 * topo_stride + i];
+			if (edge_is_leaf(e)) continue;
+			t_up[tid * I + k++] = make_uint4((UP0 + (e / 2 - 1)) * SB, up_slot(tp[topo_stride + e]) * SB, up_slot(tp[2 * topo_stride + e]) * SB, 0u);
+		}
+	}
+	// Rows of this column tile: the scored taxon is row `taxon` (= m for the search's use), rows 0 .. m-1 are the leaves.
+	// Columns past the end hold all ones in every row: they merge to all ones and cost nothing.
+	for (unsigned t = 0; t <= m; ++t) sm[t * T + tid] = ok ? __ldg(rows + (size_t) (t == m ? taxon : t) * n_blocks + col) : ones;
+	sm[ONES * T + tid] = ones;
+	const uint4 rx = sm[m * T + tid];
+	const bool w1 = 4u * (ok ? col : 0u) >= wp.heavy_words;     // this column holds weight-1 sites only
+	const unsigned me = (unsigned) __cvta_generic_to_shared(sm) + 16u * tid;           // this thread's column of slot 0
+	const unsigned dn0 = (unsigned) __cvta_generic_to_shared(t_dn), up0 = (unsigned) __cvta_generic_to_shared(t_up);
+	unsigned acc_at = (unsigned) __cvta_generic_to_shared(accw) + 4u * (tid >> 5) * n_steps;
+	const bool lane0 = (tid & 31u) == 0;
+	__syncthreads();
+	for (unsigned lt = 0; lt < t_count; ++lt) {
+		unsigned at = up0 + 16u * lt * I;
+		for (unsigned k = 0; k < I; ++k, at += 16u) {           // UP sets of the internal edges, children before parents
+			const uint4 u = lds128(at);
+			sts128(me + u.x, fitch_block(lds128(me + u.y), lds128(me + u.z)));
+		}
+		at = dn0 + 16u * lt * E;
+		for (unsigned i = 0; i < E; ++i, at += 16u, acc_at += 4u) {   // DOWN and MIDPOINT in pre-order, scored on the spot
+			const uint4 w = lds128(at);
+			const uint4 d = fitch_block(lds128(me + w.x), lds128(me + w.y));
+			sts128(me + w.w, d);
+			const uint4 mid = fitch_block(lds128(me + w.z), d);
+			unsigned c;
+			if (w1) c = cost_word_w1(mid.x, rx.x) + cost_word_w1(mid.y, rx.y) + cost_word_w1(mid.z, rx.z) + cost_word_w1(mid.w, rx.w);
+			else c = cost_block(mid, rx, col, wp);
+			c = __reduce_add_sync(0xffffffffu, c);
+			if (lane0) sts32(acc_at, c);
+		}
 	}
 	__syncthreads();
-	for (unsigned e = threadIdx.x; e < E; e += 256) {
-		if (acc[e]) atomicAdd(cost + (size_t) tree * E + e, acc[e]);
+	for (unsigned x = tid; x < t_count * E; x += T) {
+		unsigned c = 0;
+		for (unsigned w = 0; w < n_warps; ++w) c += accw[w * n_steps + x];
+		if (c) atomicAdd(cost + (size_t) (t_begin + x / E) * E + s_edge[x], c);
 	}
 }
 
 // cost[tree][edge] of inserting `taxon` on every edge of trees whose topologies are in d_topo.
 int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
                             unsigned taxon, unsigned *d_cost) {
-	const unsigned E = 2 * m - 3;
+	const unsigned E = 2 * m - 3, slots = 3 * m - 1;
+	// threads per CTA: as many as keep two CTAs per SM (3m - 1 slots of 16 bytes per thread)
+	unsigned threads = 128;
+	while (threads > 32 && (size_t) slots * 16 * threads > ((size_t) 100 << 10)) threads >>= 1;
+	// trees per CTA: enough to amortise loading the rows and building the tables, few enough to fill the GPU several times over
+	const unsigned col_tiles = (ctx->n_blocks + threads - 1) / threads;
+	unsigned per_cta = 16;
+	while (per_cta > 1 && (unsigned long long) col_tiles * ((n_trees + per_cta - 1) / per_cta) < 16ull * ctx->sm_count) per_cta >>= 1;
+	// shared memory: the slots, then per tree E down steps + (m - 2) up steps of 16 bytes, one cost word per warp and step, E edge ids
+	auto bytes = [&](unsigned trees) { return (size_t) slots * 16 * threads + (size_t) trees * ((size_t) E * (16 + 4 * (threads / 32) + 1) + (size_t) (m - 2) * 16) + 16; };
+	while (per_cta > 1 && bytes(per_cta) > bytes(1) + ((size_t) 9 << 10)) per_cta >>= 1;      // tables: at most 9 KiB on top of the slots
+	const size_t smem = bytes(per_cta);
+	if (smem > ((size_t) 220 << 10)) return set_error(XMP_ERR_ARG, "trees on %u taxa need %zu bytes of shared memory per CTA", m, smem);
+	XMP_CUDA(cudaFuncSetAttribute(k_score_trees_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	XMP_CUDA(cudaMemsetAsync(d_cost, 0, (size_t) n_trees * E * sizeof(unsigned), ctx->stream));
-	for (unsigned t0 = 0; t0 < n_trees; t0 += 65535u) {
-		const unsigned nt = n_trees - t0 < 65535u ? n_trees - t0 : 65535u;
-		dim3 grid((ctx->n_blocks + 255) / 256, nt);
-		const uint8_t *topo = d_topo + (size_t) t0 * 4 * topo_stride;
-		unsigned *cost = d_cost + (size_t) t0 * E;
-		if (E <= 16) k_score_trees_wide<16><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
-		else if (E <= 32) k_score_trees_wide<32><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
-		else if (E <= 72) k_score_trees_wide<72><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
-		else k_score_trees_wide<200><<<grid, 256, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, topo, topo_stride, m, taxon, cost);
+	for (unsigned t0 = 0; t0 < n_trees; t0 += 65535u * per_cta) {
+		const unsigned nt = std::min(n_trees - t0, 65535u * per_cta);
+		dim3 grid(col_tiles, (nt + per_cta - 1) / per_cta);
+		k_score_trees_wide<<<grid, threads, smem, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo + (size_t) t0 * 4 * topo_stride, topo_stride, nt,
+		                                                        per_cta, m, taxon, d_cost + (size_t) t0 * E);
 	}
 	XMP_CUDA(cudaGetLastError());
 	return XMP_OK;

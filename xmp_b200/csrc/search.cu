@@ -1554,16 +1554,18 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	rc = begin_bound(ctx, S);
 	if (rc) return fail(rc);
 
-	// Where the frontier is dealt out to shards: the first tree size with >= 4096 subtrees per shard.  The deal is the
-	// load balance: subtree sizes are heavy-tailed, and only thousands of them per shard even out (measured on 8 GPUs
-	// with 64 per shard: its36 under -Bd left one GPU with twice the work of the others, and stealing cannot repair that
-	// cheaply -- a thief only ever gets what is open between two sweeps).  The shallow prefix that every shard expands
-	// redundantly stays a few thousand trees (XMP_SPLIT_PER_SHARD overrides the 4096).
+	// Where the frontier is dealt out to shards: the first tree size with >= 65536 subtrees per shard.  The deal is the
+	// load balance: subtree sizes are heavy-tailed, and only tens of thousands of them per shard even out.  Measured on
+	// 8 GPUs (profiles/r02_scaling.md): with 64 per shard its36 under -Bd left one GPU with twice the work of the others,
+	// and stealing cannot repair that cheaply -- a thief only ever gets what is open between two sweeps; with 4096 the
+	// slowest GPU still ran 40 % longer than the fastest; with 65536 (tree size 10 on 8 GPUs) all finish within 15 %.
+	// The shallow prefix that every shard expands redundantly is then ~150 K trees, a fraction of a millisecond; with
+	// 2^20 per shard it starts to show (h4 +7 % nodes).  XMP_SPLIT_PER_SHARD overrides.
 	S->split_level = 0;
 	if (S->prm.shard_count > 1) {
 		unsigned s = S->prm.split_level;
 		if (s == 0) {
-			const double per_shard = (double) std::max(env_unsigned("XMP_SPLIT_PER_SHARD", 4096), 1u);
+			const double per_shard = (double) std::max(env_unsigned("XMP_SPLIT_PER_SHARD", 65536), 1u);
 			s = 4;
 			while (s + 2 < S->n && odd_factorial(s) < per_shard * S->prm.shard_count) ++s;
 		}
