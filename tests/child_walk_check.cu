@@ -213,6 +213,27 @@ int main(int argc, char **argv) {
 						wj = wn; ux = uxn; us = usn;
 					}
 					if (overflow) { printf("rep %u m %u P %u: stack overflow flagged with the worst-case depth\n", rep, m, P); return 1; }
+					// --- the lean step of k_expand_last_fused (depth, internal flag and the two UP sets only; upath[] variant) ---
+					if (!eager) {
+						std::vector<uint4> upath2(D), dstack2(D);
+						ChildWalk lw;
+						bool of2 = false;
+						lw.init(ph, L, m, P, PU, rt, upath2.data(), T, D, of2);
+						for (unsigned j = 0; j < Ec; ++j) {
+							unsigned depth = 0;
+							bool internal = false;
+							uint4 lux, lus;
+							lw.step_lean(j, lw.word_for(j), depth, internal, lux, lus, upath2.data(), T, r0);
+							const unsigned e = cpre[j];
+							const uint4 dn = depth == 0 ? r0 : fitch_block(dstack2[depth - 1], lus);
+							if (internal) dstack2[depth] = dn;
+							if (depth != prog_depth(want[j]) || internal != (prog_size(want[j]) > 1u) || lw.edge_at(j) != prog_edge(want[j])) {
+								printf("rep %u m %u P %u step %u: lean step gives depth %u internal %d edge %u, from scratch %08x\n", rep, m, P, j, depth, (int) internal, lw.edge_at(j), want[j]);
+								return 1;
+							}
+							if (!same(lux, cup[e]) || !same(dn, cdown[e])) { printf("rep %u m %u P %u step %u col %u: lean step: UP or DOWN set differs\n", rep, m, P, j, col); return 1; }
+						}
+					}
 				}
 				for (unsigned j = 0; j < Ec; ++j) {
 					if (cost[j] != want_cost[j]) { printf("rep %u m %u P %u step %u: cost %u, site by site %u\n", rep, m, P, j, cost[j], want_cost[j]); return 1; }

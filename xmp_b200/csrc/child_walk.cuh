@@ -92,22 +92,22 @@ struct ChildWalk {
 		rt = row_new;
 		sp = make_splice(P, prog[P * 32u], E);
 		lim = 0;
-		uint4 u = fitch_block(rt, XMP_LDG(PU + (size_t) P * rs));
+		uint4 u = fitch_block(rt, XMP_LDG(PU + P * rs));
 		gup = child_rows;
-		if (gup) gup[(size_t) P * rs] = u;
+		if (gup) gup[P * rs] = u;
 		else upath[0] = u;
 		// Up the root path.  The set hanging off the path at each level is requested one level ahead: the chain
 		// of dependent loads is then the program words alone (mostly L1 hits: a warp shares a few parents), not
 		// program word -> row -> program word -> row.
 		unsigned k = 1, cur = P, other = sp.sv;
-		uint4 off = sp.dv > 0 ? XMP_LDG(PU + (size_t) other * rs) : rt;       // `other` hangs off the path: unchanged
+		uint4 off = sp.dv > 0 ? XMP_LDG(PU + other * rs) : rt;       // `other` hangs off the path: unchanged
 		for (unsigned depth = sp.dv; depth > 0; --depth) {
 			cur = parent_pos(cur, other);
 			other = prog_sib(prog[cur * 32u]);
-			const uint4 off_next = depth > 1 ? XMP_LDG(PU + (size_t) other * rs) : rt;
+			const uint4 off_next = depth > 1 ? XMP_LDG(PU + other * rs) : rt;
 			u = fitch_block(u, off);
-			if (gup) gup[(size_t) cur * rs] = u;
-			else if (k < D) upath[(size_t) k * T] = u;
+			if (gup) gup[cur * rs] = u;
+			else if (k < D) upath[k * T] = u;
 			else overflow = true;
 			off = off_next;
 			++k;
@@ -148,20 +148,53 @@ struct ChildWalk {
 #ifdef XMP_WALK_UL
 			// A/B variant (scripts/build_variant.sh): both rows come from global memory, so pick the ADDRESS and load
 			// unconditionally (any valid row when the value is not used) -- selects instead of branch regions.
-			const uint4 *pu = src_u == 1u ? gup + (size_t) j * rs : PU + (size_t) row_u * rs;
-			const uint4 *ps = src_s == 1u ? gup + (size_t) s * rs : PU + (size_t) (src_s == 0u ? row_s : 0u) * rs;
+			const uint4 *pu = src_u == 1u ? gup + j * rs : PU + row_u * rs;
+			const uint4 *ps = src_s == 1u ? gup + s * rs : PU + (src_s == 0u ? row_s : 0u) * rs;
 			const uint4 a = *pu, b = *ps;
 			ux = src_u == 2u ? rt : a;
 			us = src_s < 2u ? b : (src_s == 2u ? rt : r0);
 			return;
 #else
-			ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? gup[(size_t) j * rs] : rt);
-			us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? gup[(size_t) s * rs] : (src_s == 2u ? rt : r0));
+			ux = src_u == 0u ? XMP_LDG(PU + row_u * rs) : (src_u == 1u ? gup[j * rs] : rt);
+			us = src_s == 0u ? XMP_LDG(PU + row_s * rs) : (src_s == 1u ? gup[s * rs] : (src_s == 2u ? rt : r0));
 			return;
 #endif
 		}
-		ux = src_u == 0u ? XMP_LDG(PU + (size_t) row_u * rs) : (src_u == 1u ? upath[(size_t) k_u * T] : rt);
-		us = src_s == 0u ? XMP_LDG(PU + (size_t) row_s * rs) : (src_s == 1u ? upath[(size_t) k_s * T] : (src_s == 2u ? rt : r0));
+		ux = src_u == 0u ? XMP_LDG(PU + row_u * rs) : (src_u == 1u ? upath[k_u * T] : rt);
+		us = src_s == 0u ? XMP_LDG(PU + row_s * rs) : (src_s == 1u ? upath[k_s * T] : (src_s == 2u ? rt : r0));
+	}
+
+	// The same step for a kernel that does not keep the child (k_expand_last_fused): instead of the child's whole
+	// program word only what the walk itself consumes -- the depth of position j in the child and whether it is an
+	// internal node -- and the two UP sets.  (The word costs ~50 instructions per step in selects; the fused kernel needs
+	// the edge id of a position only for the few trees it emits, and takes it from edge_at().)  upath[] variant only.
+	XMP_HD void step_lean(unsigned j, unsigned w, unsigned &depth, bool &internal, uint4 &ux, uint4 &us, const uint4 *upath, unsigned T,
+	                      const uint4 &r0) {
+		const unsigned P = sp.P, q = j - P;                      // q = 0, 1, 2: the spliced steps b, a, v
+		const bool after = j > P + 2u;
+		const unsigned i = after ? j - 2u : (j < E ? j : E - 1u); // parent position this step starts from (w = prog[parent_index(j)])
+		const unsigned d = prog_depth(w), s = prog_sib(w), sz = prog_size(w);
+		const bool anc = j < P && j + sz > P;                    // proper ancestor of P
+		const bool on_path = !anc && d <= lim && s != XMP_NO_POS; // my sibling is P or an ancestor of P
+		if (q >= 3u) lim = anc ? d + 1u : (lim < d ? lim : d);    // the spliced steps re-read positions P - 1 and P: no change
+		// defaults: an ordinary node
+		depth = d + ((after && i < P + sp.szv) ? 1u : 0u);
+		internal = sz > 1u;
+		unsigned src_u = anc ? 1u : 0u, row_u = i, src_s = s == XMP_NO_POS ? 3u : (on_path ? 1u : 0u), row_s = s, k = sp.dv - d;
+		unsigned k_u = k;
+		if (q == 0u) { src_u = 1u; k_u = 0u; row_s = sp.sv; src_s = sp.sv == XMP_NO_POS ? 3u : 0u; depth = sp.dv; internal = true; }
+		if (q == 1u) { src_u = 2u; src_s = 0u; row_s = P; depth = sp.dv + 1u; internal = false; }
+		if (q == 2u) { src_u = 0u; row_u = P; src_s = 2u; depth = sp.dv + 1u; internal = sp.szv > 1u; }
+		ux = src_u == 0u ? XMP_LDG(PU + row_u * rs) : (src_u == 1u ? upath[k_u * T] : rt);
+		us = src_s == 0u ? XMP_LDG(PU + row_s * rs) : (src_s == 1u ? upath[k * T] : (src_s == 2u ? rt : r0));
+	}
+	// Edge id of the child's position j (for the trees the fused kernel emits).
+	XMP_HD unsigned edge_at(unsigned j) const {
+		const unsigned P = sp.P;
+		if (j == P) return sp.b;
+		if (j == P + 1u) return sp.a;
+		if (j == P + 2u) return sp.xv;
+		return prog_edge(prog[parent_index(j, P) * 32u]);
 	}
 };
 

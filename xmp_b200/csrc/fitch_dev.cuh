@@ -78,6 +78,18 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
 	return r;
 }
 
+// Shared memory by 32-bit address (__cvta_generic_to_shared): a walk computes every address as (this thread's base) + (a byte
+// offset), one add per access, instead of letting the compiler rebuild generic pointers to dynamic shared memory inside its loop.
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 	v += __shfl_xor_sync(0xffffffffu, v, 16);
 	v += __shfl_xor_sync(0xffffffffu, v, 8);

@@ -379,18 +379,6 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 // internal sets to shared memory removed the traffic but left 3,300 instructions per (tree, column) in branches and
 // 64-bit address arithmetic around 1,300 of Fitch arithmetic.
 // ---------------------------------------------------------------------------------------------
-// Shared memory by 32-bit address: the walk computes every address as (this thread's base) + (a byte offset from the step
-// table), one add per access, instead of letting the compiler rebuild generic pointers inside the loop.
-__device__ __forceinline__ uint4 lds128(unsigned addr) {
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ void sts128(unsigned addr, const uint4 &v) {
-	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-
 // Step tables (shared memory, read back as 16-byte broadcasts); all fields are BYTE offsets of slots, i.e. slot * 16 * blockDim.x.
 //   down step of pre-order position i:  DOWN(e) = F(src, sib);  MIDPOINT = F(upe, DOWN);  DOWN is kept at dst
 //   up step (internal edges only, children before parents):  slot dst = F(a, b)

@@ -319,7 +319,8 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = nullptr;                                           // the root-path UP sets go through the child's record
-	uint4 *dstack = smem + threadIdx.x;
+	// the DOWN stack by 32-bit shared address: entry d of this thread at ds0 + d * SB
+	const unsigned ds0 = (unsigned) __cvta_generic_to_shared(smem + threadIdx.x), SB = 16u * T;
 	unsigned *acc = (unsigned *) (smem + (size_t) D * T);            // [cpc][Ec], used when W > 1
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned cpc = T / W;                                        // whole children per CTA (W <= 32 <= T)
@@ -329,6 +330,7 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 	const uint4 r0 = __ldg(rows + col);
 	const uint4 rt = __ldg(rows + (size_t) m * W + col);
 	const uint4 rn = __ldg(rows + (size_t) (m + 1) * W + col);         // the taxon the child is scored against
+	const bool w1 = 4u * col >= wp.heavy_words;                        // this column holds weight-1 sites only
 	unsigned my_merges = 0, my_depth = 0;
 	bool overflow = false;
 	for (unsigned base = blockIdx.x * cpc; base < n_children; base += gridDim.x * cpc) {
@@ -355,24 +357,30 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 			uint4 ux, us;
 			unsigned pw1 = cw.word_for(1);                  // Ec >= 5
 			cw.step(0, cw.word_for(0), wj, ux, us, upath, T, r0);
-			for (unsigned j = 0; j < Ec; ++j) {
+			uint4 *cu_at = CU;                              // row j of the child, its program and cost words: running pointers
+			unsigned *prog_at = cprog, *cost_at = ccost;
+			for (unsigned j = 0; j < Ec; ++j, cu_at += rs, prog_at += 32, cost_at += 32) {
 				const unsigned pw2 = cw.word_for(j + 2);    // clamped past the end
 				unsigned wn = wj;
 				uint4 uxn = ux, usn = us;
 				if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
 				pw1 = pw2;
 				const unsigned d = prog_depth(wj);
-				const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
+				uint4 dn = r0;
+				if (d) dn = fitch_block(lds128(ds0 + (d - 1 < D ? d - 1 : 0u) * SB), us);   // d - 1 >= D: overflow is already flagged
 				if (prog_size(wj) > 1u) {
-					if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
+					if (d < D) sts128(ds0 + d * SB, dn); else overflow = true;
 				}
 				my_depth = max(my_depth, d);
-				CU[(size_t) j * rs] = ux;
-				const unsigned c = cost_block(fitch_block(ux, dn), rn, col, wp);
-				if (W == 1) ccost[j * 32u] = c;
+				*cu_at = ux;
+				const uint4 mid = fitch_block(ux, dn);
+				unsigned c;
+				if (w1) c = cost_word_w1(mid.x, rn.x) + cost_word_w1(mid.y, rn.y) + cost_word_w1(mid.z, rn.z) + cost_word_w1(mid.w, rn.w);
+				else c = cost_block(mid, rn, col, wp);
+				if (W == 1) *cost_at = c;
 				else if (c) atomicAdd(&acc[lc * Ec + j], c);
 				if (col == 0) {
-					cprog[j * 32u] = wj;
+					*prog_at = wj;
 					if (j == 0) first_edge = prog_edge(wj);
 				}
 				wj = wn; ux = uxn; us = usn;
@@ -424,22 +432,29 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 	extern __shared__ uint4 smem[];
 	const unsigned T = blockDim.x;
 	uint4 *upath = smem + threadIdx.x;
-	uint4 *dstack = smem + (size_t) D * T + threadIdx.x;
+	// the DOWN stack by 32-bit shared address: entry d of this thread at ds0 + d * SB
+	const unsigned ds0 = (unsigned) __cvta_generic_to_shared(smem + (size_t) D * T + threadIdx.x), SB = 16u * T;
 	const unsigned W = L.W, E = 2 * m - 3, Ec = E + 2, rs = W << L.ts_shift;
 	const unsigned n_surv = min(*n_surv_ptr, s_end);
+	if (n_surv <= s_begin) return;
 	const unsigned lane = threadIdx.x & 31u, sub = lane % G;
-	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - sub));
 	const unsigned groups_per_block = T / G;
 	const bool col_ok = sub < W;
 	const unsigned col = col_ok ? sub : 0;
 	const uint4 r0 = __ldg(rows + col);
 	const uint4 rt = __ldg(rows + (size_t) m * W + col);
 	const uint4 rl = __ldg(rows + (size_t) (m + 1) * W + col);
+	const bool w1 = 4u * col >= wp.heavy_words;                 // this column holds weight-1 sites only
 	unsigned my_merges = 0;
 	bool overflow = false;
-	for (unsigned long long s = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + threadIdx.x / G; s < n_surv;
-	     s += (unsigned long long) gridDim.x * groups_per_block) {
-		const uint4 sv = surv[s];
+	// Every lane of a warp makes the same number of trips (the cost of a child is summed over its G lanes with
+	// full-mask shuffles); lanes past the end of the list walk the last survivor again and emit nothing.
+	const unsigned long long stride = (unsigned long long) gridDim.x * groups_per_block;
+	for (unsigned long long s0 = (unsigned long long) s_begin + (unsigned long long) blockIdx.x * groups_per_block + (threadIdx.x & ~31u) / G;
+	     s0 < n_surv; s0 += stride) {
+		const unsigned long long s = s0 + lane / G;
+		const bool live = s < n_surv;
+		const uint4 sv = surv[live ? s : (unsigned long long) n_surv - 1ull];
 		const unsigned pnode = sv.x, P = sv.y, score = sv.z;
 		const unsigned *ph = hdr_of(parent, L, pnode);
 		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) up_row0(L, E) * rs + col;
@@ -447,41 +462,40 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
 		unsigned bound = 0;
-		{
-			const unsigned active = __activemask();
-			const int leader = __ffs(active) - 1;
-			if ((int) lane == leader) bound = *(volatile unsigned *) bound_ptr;
-			bound = __shfl_sync(active, bound, leader);
-		}
+		if (lane == 0) bound = *(volatile unsigned *) bound_ptr;
+		bound = __shfl_sync(0xffffffffu, bound, 0);
 		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
-		unsigned wj;
-		uint4 ux, us;
+		unsigned depth, depth_n = 0;
+		bool internal, internal_n = false;
+		uint4 ux, us, uxn, usn;
 		unsigned pw1 = cw.word_for(1);                      // Ec >= 5
-		cw.step(0, cw.word_for(0), wj, ux, us, upath, T, r0);
+		cw.step_lean(0, cw.word_for(0), depth, internal, ux, us, upath, T, r0);
 		for (unsigned j = 0; j < Ec; ++j) {
 			const unsigned pw2 = cw.word_for(j + 2);        // clamped past the end
-			unsigned wn = wj;
-			uint4 uxn = ux, usn = us;
-			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
+			if (j + 1 < Ec) cw.step_lean(j + 1, pw1, depth_n, internal_n, uxn, usn, upath, T, r0);
 			pw1 = pw2;
-			const unsigned d = prog_depth(wj);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
-			if (prog_size(wj) > 1u) {
-				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
+			uint4 dn = r0;
+			if (depth) dn = fitch_block(lds128(ds0 + (depth - 1 < D ? depth - 1 : 0u) * SB), us);   // depth - 1 >= D: overflow is already flagged
+			if (internal) {
+				if (depth < D) sts128(ds0 + depth * SB, dn); else overflow = true;
 			}
-			unsigned c = col_ok ? cost_block(fitch_block(ux, dn), rl, col, wp) : 0u;
+			const uint4 mid = fitch_block(ux, dn);
+			unsigned c;
+			if (w1) c = cost_word_w1(mid.x, rl.x) + cost_word_w1(mid.y, rl.y) + cost_word_w1(mid.z, rl.z) + cost_word_w1(mid.w, rl.w);
+			else c = cost_block(mid, rl, col, wp);
+			if (!col_ok) c = 0;
 #pragma unroll
-			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
-			if (sub == 0 && accept_insertion(c, bound, score, rest_last)) {
+			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+			if (live && sub == 0 && accept_insertion(c, bound, score, rest_last)) {
 				if (score + c < bound) lower_bound(bound_ptr, score + c, peers);
 				const unsigned slot = atomicAdd(n_trees, 1u);
 				if (slot < trees_cap) {
-					emit_tree(trees + (size_t) slot * L.trec, L, ph, score + c, m, cw.sp.xv, prog_edge(wj), true);
+					emit_tree(trees + (size_t) slot * L.trec, L, ph, score + c, m, cw.sp.xv, cw.edge_at(j), true);
 				}
 			}
-			wj = wn; ux = uxn; us = usn;
+			depth = depth_n; internal = internal_n; ux = uxn; us = usn;
 		}
-		if (sub == 0) my_merges += n_up + 2 * Ec;
+		if (live && sub == 0) my_merges += n_up + 2 * Ec;
 	}
 	my_merges = warp_sum(my_merges);
 	if (lane == 0 && my_merges) atomicAdd(merges, (unsigned long long) my_merges);
