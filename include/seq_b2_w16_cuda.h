@@ -8,8 +8,9 @@
  * reference (src/yanbader.c:160-166,336-342,364-369,420-425, src/common.c:569-610, src/greedytree.c:28-34, ...) then
  * lands in libxmp_b200.so.
  *
- * What a maintainer adds to the reference (INTEGRATION.md shows it; oracle/Makefile's `ref_cuda` target does exactly
- * this at build time, on a generated copy of seq.h, to prove that the reference links and runs against the library):
+ * What a maintainer adds to the reference (INTEGRATION.md shows it; this repository's test build does exactly this at
+ * build time, on a generated copy of seq.h, to prove that the reference links and runs against the library -- the
+ * `ref_cuda` target described there):
  *     switches.h.in   #cmakedefine CUDAFITCH                                  (one line)
  *     seq.h:5         ... + defined(SSE2ASMFITCH) + defined(CUDAFITCH) != 1   (the one-family check)
  *     seq.h:20        #include "seq_b2_w16_cuda.h"                            (after seq_b2_sse2asm.h)
