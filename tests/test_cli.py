@@ -299,10 +299,10 @@ def _run_over_stub(stub_dir, exe, args, cwd, devices=1, skew=False):
 
 
 @pytest.mark.parametrize("name", ["its10", "quick2", "primate", "53humans.12", "its14"])
-@pytest.mark.parametrize("devices, skew", [(1, False), (3, False), (4, True)])
+@pytest.mark.parametrize("devices, skew", [(1, False), (3, False), (4, True), (8, True), (8, False)])
 def test_whole_program_over_the_test_double(stub_dir, alignment_dir, goldens, tmp_path, name, devices, skew):
-    """The reference's result file, byte for byte, from fastdnamp_b200's host side with 1, 3 and 4 scheduler threads --
-    in the last case every subtree starts on shard 0 and the other three live on work stolen through the mailbox."""
+    """The reference's result file, byte for byte, from fastdnamp_b200's host side with 1, 3, 4 and 8 scheduler threads over
+    the exchange protocol -- with `skew` every subtree starts on shard 0 and the others live on stolen work."""
     from tests.conftest import golden_output
     g = goldens[name]
     out = tmp_path / "out.nex"

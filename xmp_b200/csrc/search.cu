@@ -1556,6 +1556,11 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	if (ctx->num_taxa < 4) return set_error(XMP_ERR_ARG, "the search needs at least four taxa");
 	const unsigned shard_count = params->shard_count ? params->shard_count : 1u;
 	if (params->shard_index >= shard_count) return set_error(XMP_ERR_ARG, "shard_index %u >= shard_count %u", params->shard_index, shard_count);
+	if (ctx->xch_connected && (shard_count != ctx->xch_world || params->shard_index != ctx->xch_rank)) {
+		return set_error(XMP_ERR_ARG, "this context is connected as rank %u of %u: its searches are shard %u of %u (got %u of %u); "
+		                              "xmp_cuda_exchange_disconnect first for a search of its own",
+		                 ctx->xch_rank, ctx->xch_world, ctx->xch_rank, ctx->xch_world, params->shard_index, shard_count);
+	}
 	XMP_CUDA(cudaSetDevice(ctx->device));
 	search_destroy(ctx);
 	Search *S = new Search();
