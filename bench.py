@@ -21,6 +21,13 @@ weight-1 scorer (reference FitchScoreWeight1, src/fitchtemplate_b2_w8_fastc64.in
 
 N > 1 (torchrun, one rank per GPU): trees are independent, so every rank scores its own 4096 trees
 (weak scaling, no data-path collective); time is the max over ranks.
+
+  bandb     the second half of BASELINE's metric: exact branch and bound on the reference's measure/ datasets (bundled
+            under tests/golden), time from search_begin to the proven optimum with the full MP set, nodes/s, and -- at
+            N > 1, over the peer exchange of include/xmp_cuda.h (2d) -- speed-up, efficiency and node inflation against
+            rank 0's own one-GPU search of the same dataset in the same run.  Every search is checked against the
+            reference's score, tree count and canonical tree-set hash.  At N = 1 the reference's serial program
+            (oracle/_ref/fastdnamp_ref) is timed on the same box for the datasets it finishes within ~35 s.
 """
 import argparse
 import json
