@@ -96,3 +96,23 @@ def test_sharded_search_over_gloo(tmp_path, alignment_dir, goldens, stub_dir, wo
     if skew and name != "quick2":
         # the ranks that started empty did real work, i.e. jobs moved (quick2 is over before anybody can ask)
         assert all(int(s[4]) > 0 for s in stats[1:]), [int(s[4]) for s in stats]
+
+
+def test_exchange_protocol_invariants_under_random_timing(tmp_path):
+    """tests/proto_check.cpp: the product's protocol source (xmp_b200/csrc/exchange_proto.h) with 2 to 8 ranks as threads over
+    host atomics, synthetic job trees and random pauses -- every job executed exactly once, idle ranks never give work away, the
+    busy counter ends at zero, every rank stops with the finished flag and without work, all bound words agree at the end; once
+    more under ThreadSanitizer where its runtime is available."""
+    import subprocess
+    exe = str(tmp_path / "proto_check")
+    src = os.path.join(ROOT, "tests", "proto_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, src], check=True)
+    for ranks, rounds in ((2, 20), (3, 20), (5, 12), (8, 12)):
+        r = subprocess.run([exe, str(ranks), str(rounds), str(ranks * 7)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+    tsan = str(tmp_path / "proto_check_tsan")
+    c = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-o", tsan, src], capture_output=True, text=True)
+    if c.returncode == 0:
+        r = subprocess.run([tsan, "4", "4", "11"], capture_output=True, text=True, timeout=600)
+        if "unexpected memory mapping" not in r.stderr:
+            assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr and r.stdout.startswith("OK "), r.stdout + r.stderr[-2000:]
