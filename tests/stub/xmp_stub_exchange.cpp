@@ -110,6 +110,9 @@ int xmp_cuda_exchange_handle(xmp_ctx *c, unsigned char *handle) {
 
 static int connect_common(xmp_ctx *c, unsigned rank, unsigned world) {
 	if (!c || rank >= world || world > XCH_MAX_RANKS || !region()) return stub_fail(XMP_ERR_ARG, "bad exchange arguments");
+	// XMP_STUB_FAIL_CONNECT=<rank>: that rank cannot map its peers (what a node without peer access looks like to the driver)
+	const char *bad = getenv("XMP_STUB_FAIL_CONNECT");
+	if (bad && *bad && (unsigned) atoi(bad) == rank) return stub_fail(XMP_ERR_NODEVICE, "stub: peers cannot be mapped");
 	c->xch_rank = rank;
 	c->xch_world = world;
 	c->xch_connected = world > 1;

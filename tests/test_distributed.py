@@ -21,7 +21,7 @@ from tests.conftest import GOLDEN, ROOT, golden_trees
 from tests.newick import canonical_newick
 
 
-def _worker(rank, world, port, name, alignment_path, out_dir, skew, stub):
+def _worker(rank, world, port, name, alignment_path, out_dir, skew, stub, fail_connect=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -41,12 +41,14 @@ def _worker(rank, world, port, name, alignment_path, out_dir, skew, stub):
         os.environ["XMP_STUB_DEVICES"] = str(world)
         if skew:
             os.environ["XMP_STUB_SKEW"] = "1"
+        if fail_connect is not None:
+            os.environ["XMP_STUB_FAIL_CONNECT"] = str(fail_connect)
         xc._LIB = xc.bind(ctypes.CDLL(os.path.join(stub, "libxmp_b200.so")), partial=True)
         eng = xc.Context(rank)
         eng.load_problem(p)
         score, total, paths, info = xd.sharded_search(eng, p.num_taxa, "cpu", begin={"bound": p.bound})
         nodes = eng.search_stats()["nodes"]
-        assert info["transport"] == "peer"
+        assert info["transport"] == ("peer" if fail_connect is None else "collective")
     else:
         from tests.oracle_engine import OracleEngine
         eng = OracleEngine(p)
@@ -116,3 +118,17 @@ def test_exchange_protocol_invariants_under_random_timing(tmp_path):
         r = subprocess.run([tsan, "4", "4", "11"], capture_output=True, text=True, timeout=600)
         if "unexpected memory mapping" not in r.stderr:
             assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr and r.stdout.startswith("OK "), r.stdout + r.stderr[-2000:]
+
+
+def test_driver_falls_back_together_when_one_rank_cannot_map_its_peers(tmp_path, alignment_dir, goldens, stub_dir):
+    """One rank's xmp_cuda_exchange_connect fails (a node whose GPUs are not peers): every rank must end up disconnected and
+    on the lock-step transport -- agreed through one all-reduce -- and the search still returns the reference's set."""
+    name, world = "53humans.16", 3
+    g = goldens[name]
+    port = 29500 + (os.getpid() * 7 + 977) % 2000
+    mp.spawn(_worker, args=(world, port, name, str(alignment_dir / g["alignment"]), str(tmp_path), False, stub_dir, 1), nprocs=world, join=True)
+    stats = [np.load(tmp_path / ("r%d.npy" % r)) for r in range(world)]
+    assert all(int(s[0]) == g["score"] and int(s[1]) == g["num_trees"] for s in stats)
+    assert sum(int(s[2]) for s in stats) == g["num_trees"]
+    trees = open(tmp_path / "trees.txt").read().split()
+    assert sorted(canonical_newick(t) for t in trees) == golden_trees(name)
