@@ -139,3 +139,11 @@ def test_tree_bookkeeping_with_and_without_the_cap(tmp_path):
     assert (total, stored) == (10, 10) and (dfs_sorted(got) == dfs_sorted(c[:10])).all()
     total, stored, _ = replay(batches[:1] + [(b, np.full(len(b), 101), 101)], 1000, 10)
     assert total == len(a) + len(b) and stored == 1000
+    # after a cut, trees that do not come before the last kept one are counted without being stored (the threshold
+    # pre-filter): the same 3.2 M trees, all of one length, arriving in 80 drains -- several cuts, each with a lower
+    # threshold -- must still leave exactly the first 500 of the depth-first order and the complete count
+    everything = all_paths[:3_200_000]
+    pieces = np.array_split(everything, 80)
+    total, stored, got = replay([(p, np.full(len(p), 77), 77) for p in pieces], 500, 3_000_000)
+    assert total == len(everything) and 500 <= stored < 1_100_000
+    assert (dfs_sorted(got)[:500] == dfs_sorted(everything)[:500]).all()

@@ -36,6 +36,24 @@ inline void dfs_key(const uint8_t *path, unsigned n, uint8_t *key) {
 	}
 }
 
+// key(path) < thr in that order?  Stops at the first tree size where the two differ: a tree that does not come before
+// the threshold is usually told apart within the first few insertions, long before its whole key is known.
+inline bool dfs_key_before(const uint8_t *path, unsigned n, const uint8_t *thr) {
+	uint8_t pos[2 * XMP_MAX_TAXA];
+	pos[2] = 0;
+	pos[0] = 1;
+	pos[1] = 2;
+	for (unsigned t = 3; t < n; ++t) {
+		const unsigned E = 2 * t - 3, P = pos[path[t]];
+		if (P != thr[t]) return P < thr[t];
+		for (unsigned e = 0; e < E; ++e)
+			if (pos[e] >= P) pos[e] = (uint8_t) (pos[e] + 2);
+		pos[2 * t - 3] = (uint8_t) (P + 1);
+		pos[2 * t - 2] = (uint8_t) P;
+	}
+	return false;
+}
+
 // Moves the `keep` records that come first in the reference's depth-first order to the front of recs (in that
 // order); the others follow in no particular order.  path_off = offset of the path inside a record.
 inline void keep_first_dfs(uint8_t *recs, size_t n_rec, size_t stride, size_t path_off, unsigned n, size_t keep) {
@@ -74,12 +92,18 @@ struct TreeBook {
 	unsigned host_bound = 0xffffffffu;    // the bound recs was last filtered against
 	unsigned long long dropped = 0;       // optimal trees counted but no longer held (the -m cut)
 	unsigned dropped_score = 0;           //   ... and the length they had: they only count while that is still the bound
+	// After a cut the held records are the first max_trees seen so far; a later tree whose key does not come before the
+	// last of them can never be among the first max_trees overall: it is counted and not even stored.  (53humans.29 under
+	// -Bp -m 1000 has 88 M optimal trees: without this every one of them was stored, keyed in full and selected against.)
+	bool have_thr = false;
+	uint8_t thr[XMP_MAX_TAXA + 4];        // key of the last record kept by the latest cut (valid while dropped_score is the bound)
 
 	void reset() {
 		recs.clear();
 		dropped = 0;
 		dropped_score = 0;
 		host_bound = 0xffffffffu;
+		have_thr = false;
 	}
 	unsigned length_of(size_t r) const {
 		unsigned sc;
@@ -101,19 +125,48 @@ struct TreeBook {
 		recs.resize(keep * trec);
 		dropped += n_rec - keep;
 		dropped_score = bound;
+		dfs_key(recs.data() + (keep - 1) * trec + 4, n, thr);     // the kept records are in order: the last one is the threshold
+		have_thr = true;
 	}
 	// Records [old, end) have just arrived.  Drop what the current bound already rules out -- only the new records,
-	// unless the bound has moved since the older ones were checked -- then apply the -m cut.
+	// unless the bound has moved since the older ones were checked -- and, after a cut, what cannot be among the first
+	// max_trees any more (counted, not stored); then apply the -m cut.
 	void absorb(size_t old, unsigned bound) {
-		size_t w = bound < host_bound ? 0 : old;
+		const size_t first = bound < host_bound ? 0 : old;
 		host_bound = bound;
-		for (size_t r = w; r < recs.size(); r += trec) {
-			if (length_of(r) <= bound) {
-				if (w != r) memmove(recs.data() + w, recs.data() + r, trec);
-				w += trec;
+		const bool use_thr = have_thr && dropped_score == bound && dropped > 0;
+		const size_t n_new = (recs.size() - first) / trec;
+		std::vector<uint8_t> keepf(n_new);
+		unsigned n_thr = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+		if (n_new < 65536) n_thr = 1;
+		std::vector<unsigned long long> counted(n_thr, 0);
+		auto work = [&](unsigned k, size_t lo, size_t hi) {
+			for (size_t i = lo; i < hi; ++i) {
+				const size_t r = first + i * trec;
+				const unsigned len = length_of(r);
+				bool keep = len <= bound;
+				if (keep && use_thr && len == bound && !dfs_key_before(recs.data() + r + 4, n, thr)) {
+					keep = false;
+					++counted[k];
+				}
+				keepf[i] = keep;
 			}
+		};
+		if (n_thr == 1) work(0, 0, n_new);
+		else {
+			std::vector<std::thread> th;
+			for (unsigned k = 0; k < n_thr; ++k) th.emplace_back(work, k, n_new * k / n_thr, n_new * (k + 1) / n_thr);
+			for (auto &x : th) x.join();
+		}
+		size_t w = first;
+		for (size_t i = 0; i < n_new; ++i) {
+			if (!keepf[i]) continue;
+			const size_t r = first + i * trec;
+			if (w != r) memmove(recs.data() + w, recs.data() + r, trec);
+			w += trec;
 		}
 		recs.resize(w);
+		for (unsigned k = 0; k < n_thr; ++k) dropped += counted[k];
 		cap(bound);
 	}
 	// Optimal trees known: how many there are, and for how many of them the path is still held.
