@@ -419,6 +419,60 @@ def run_reference_bandb(names, budget_s=120.0):
     return out
 
 
+# The reference's PARALLEL program on this box: its own boss / worker sources (src/mpiboss.c, src/mpiworker.c) compiled with
+# TARGETMULTI against the one-node MPI of oracle/shim/mpi (there is no MPI installation in the image), one boss plus one worker
+# per host core.  Ordered by weight in the review: the hard h / mh sets and its36 first.
+REF_MPI_SAME_BOX = ["h4", "mh3", "its36", "h5", "Metazoan", "rbc14x759", "h1", "mh1", "mt-10"]
+
+
+def run_reference_bandb_mpi(names, workers, budget_s=150.0):
+    """`xmpirun -n workers + 1 fastdnamp_ref_mpi <the golden's flags>` per dataset, one after the other (each run uses every
+    core), until the time budget is spent.  Returns {name: {"s": its "Time to perform branch and bound search", "workers": W}}
+    for the runs that reproduced the golden score and tree count.  Test infrastructure used as a reported CPU baseline only."""
+    import gzip
+    import re
+    import signal
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "fastdnamp_ref_mpi")
+    launcher = os.path.join(ROOT, "oracle", "_ref", "xmpirun")
+    if not (os.path.exists(exe) and os.path.exists(launcher)):
+        return {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    goldens = json.load(open(os.path.join(gold, "datasets.json")))
+    bundle = json.loads(gzip.open(os.path.join(gold, "alignments.json.gz")).read())
+    out, deadline = {}, time.time() + budget_s
+    with tempfile.TemporaryDirectory(prefix="xmprefmpi_") as top:
+        for name in names:
+            left = deadline - time.time()
+            if left < 2.0:
+                break
+            g = goldens[name]
+            d = os.path.join(top, name)
+            os.makedirs(d)
+            open(os.path.join(d, "in.phy"), "wb").write(bundle[g["alignment"]].encode("latin-1"))
+            cmd = [launcher, "-n", str(workers + 1), exe, "--tbr=N", "--seed=1", "--displaynewbounds=n", "--displaynewtrees=n",
+                   "--updatesecs=0"] + list(g["flags"]) + ["-o", "out.nex", "in.phy"]
+            pr = subprocess.Popen(cmd, cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, start_new_session=True)
+            try:
+                _, err = pr.communicate(timeout=left)
+            except subprocess.TimeoutExpired:
+                try:
+                    os.killpg(pr.pid, signal.SIGKILL)          # the launcher and its ranks: our own process group, nothing else
+                except ProcessLookupError:
+                    pass
+                pr.wait()
+                continue
+            m = re.search(r"Time to perform branch and bound search:\s+([\d.]+)s", err or "")
+            try:
+                text = open(os.path.join(d, "out.nex")).read()
+            except OSError:
+                continue
+            ok = re.search(r"Each tree has score %d\b" % g["score"], text) and text.count("TREE FASTDNAMP_") == g["num_trees"]
+            if pr.returncode == 0 and m and ok:
+                out[name] = {"s": float(m.group(1)), "workers": workers}
+    return out
+
+
 # ------------------------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -621,6 +675,21 @@ def run_ours(args):
                     by_name[name]["reference_cpu_bandb_s"] = secs_ref
                     by_name[name]["reference_cpu_source"] = "same box, same run (oracle/_ref/fastdnamp_ref, 1 core)"
             out["bandb"]["reference_cpu_same_box_s"] = ref_s
+            # ... and its parallel (boss / worker) program on all the cores of this box, same run
+            try:
+                workers = max(1, (os.cpu_count() or 2))
+                mpi_s = run_reference_bandb_mpi([n for n in REF_MPI_SAME_BOX if n in by_name], workers)
+            except Exception as e:  # noqa: BLE001  (a reported baseline must not cost the headline line)
+                print("bench.py: the reference's parallel program failed: %r" % (e,), file=sys.stderr)
+                mpi_s = {}
+            for name, r in mpi_s.items():
+                by_name[name]["reference_cpu_parallel_s"] = r["s"]
+                by_name[name]["reference_cpu_parallel_workers"] = r["workers"]
+            out["bandb"]["reference_cpu_parallel_same_box"] = {
+                "what": "the reference's own MPI boss / worker program (src/mpiboss.c, src/mpiworker.c, unmodified, TARGETMULTI) on this "
+                        "box's host cores in this run: one boss and one worker per core over the one-node MPI of oracle/shim/mpi; its "
+                        "'Time to perform branch and bound search'; score and tree count checked against the goldens",
+                "workers": workers if mpi_s else 0, "seconds": {k: v["s"] for k, v in mpi_s.items()}}
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()

@@ -134,7 +134,11 @@ struct TreeBook {
 	void absorb(size_t old, unsigned bound) {
 		const size_t first = bound < host_bound ? 0 : old;
 		host_bound = bound;
+#ifdef XMP_TREEBOOK_NO_PREFILTER                 // A/B switch of scripts/cpu_tree_book_bench.py only: the round-2 code before the pre-filter
+		const bool use_thr = false;
+#else
 		const bool use_thr = have_thr && dropped_score == bound && dropped > 0;
+#endif
 		const size_t n_new = (recs.size() - first) / trec;
 		std::vector<uint8_t> keepf(n_new);
 		unsigned n_thr = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
