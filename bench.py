@@ -425,7 +425,7 @@ def run_reference_bandb(names, budget_s=120.0):
 REF_MPI_SAME_BOX = ["h4", "mh3", "its36", "h5", "Metazoan", "rbc14x759", "h1", "mh1", "mt-10"]
 
 
-def run_reference_bandb_mpi(names, workers, budget_s=150.0):
+def run_reference_bandb_mpi(names, workers, budget_s=120.0):
     """`xmpirun -n workers + 1 fastdnamp_ref_mpi <the golden's flags>` per dataset, one after the other (each run uses every
     core), until the time budget is spent.  Returns {name: {"s": its "Time to perform branch and bound search", "workers": W}}
     for the runs that reproduced the golden score and tree count.  Test infrastructure used as a reported CPU baseline only."""
@@ -676,8 +676,9 @@ def run_ours(args):
                     by_name[name]["reference_cpu_source"] = "same box, same run (oracle/_ref/fastdnamp_ref, 1 core)"
             out["bandb"]["reference_cpu_same_box_s"] = ref_s
             # ... and its parallel (boss / worker) program on all the cores of this box, same run
+            workers = 0
             try:
-                workers = max(1, (os.cpu_count() or 2))
+                workers = max(1, min(len(os.sched_getaffinity(0)) or (os.cpu_count() or 2), 32))     # one worker per core (at most 32), plus the boss
                 mpi_s = run_reference_bandb_mpi([n for n in REF_MPI_SAME_BOX if n in by_name], workers)
             except Exception as e:  # noqa: BLE001  (a reported baseline must not cost the headline line)
                 print("bench.py: the reference's parallel program failed: %r" % (e,), file=sys.stderr)
