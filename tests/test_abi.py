@@ -147,3 +147,25 @@ def test_tree_bookkeeping_with_and_without_the_cap(tmp_path):
     total, stored, got = replay([(p, np.full(len(p), 77), 77) for p in pieces], 500, 3_000_000)
     assert total == len(everything) and 500 <= stored < 1_100_000
     assert (dfs_sorted(got)[:500] == dfs_sorted(everything)[:500]).all()
+
+
+def test_bench_reference_arm_contract_under_torchrun(tmp_path):
+    """`bench.py --impl reference` is the driver's CPU arm: the reference's own Fitch code (oracle/_ref) on the host cores, no
+    GPU involved, so it runs here.  Launched the way the driver launches N > 1 (torchrun, one process per rank): rank 0
+    alone works and prints ONE JSON line with the contract's keys, the other rank exits 0 without output."""
+    import json
+    import sys
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libxmpref_fitch.so")):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["steps"] == 1 and out["higher_is_better"] is True
+    assert out["metric"] == "fitch_insertion_scoring_site_merges_per_s" and out["unit"] == "Gsite-merges/s" and out["value"] > 0
+    assert out["cpu_baseline"]["kind"] == "reference" and out["cpu_baseline"]["cores"] >= 1 and out["cpu_baseline"]["value"] == out["value"]
+    assert out["e2e"] == {"value": out["value"], "unit": out["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert out["config"]["taxa"] == 64 and out["config"]["sites"] == 1 << 20 and out["config"]["m"] == 8
