@@ -54,6 +54,9 @@ DATASETS = {
     "Metazoan": ("measure/Metazoan.phy", []),
     # the author's own setting for its36 (tools/FastdnampPerfTesting.pm:31-34)
     "its36": ("measure/its36.phy", ["-Bp", "-b", "233", "-m", "100000"]),
+    # the five simulated 24-taxon alignments of measure/ (0.1-4 M nodes each): CPU-side parity cases
+    "e1": ("measure/e1.phy", []), "e3": ("measure/e3.phy", []), "e4": ("measure/e4.phy", []),
+    "e5": ("measure/e5.phy", []), "e6": ("measure/e6.phy", []),
     # small extra cases: quick parity runs and ambiguity codes
     "mt-10.Bm": ("measure/mt-10.phy", ["-Bm"]),
     "h3.Bm": ("measure/h3.phy", ["-Bm"]),

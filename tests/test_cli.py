@@ -298,7 +298,7 @@ def _run_over_stub(stub_dir, exe, args, cwd, devices=1, skew=False):
     return subprocess.run([exe, "--gpus=%d" % devices] + args, cwd=cwd, capture_output=True, text=True, env=env, timeout=300)
 
 
-@pytest.mark.parametrize("name", ["its10", "quick2", "primate", "53humans.12", "its14"])
+@pytest.mark.parametrize("name", ["its10", "quick2", "primate", "53humans.12", "its14", "e4"])
 @pytest.mark.parametrize("devices, skew", [(1, False), (3, False), (4, True), (8, True), (8, False)])
 def test_whole_program_over_the_test_double(stub_dir, alignment_dir, goldens, tmp_path, name, devices, skew):
     """The reference's result file, byte for byte, from fastdnamp_b200's host side with 1, 3, 4 and 8 scheduler threads over

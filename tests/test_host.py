@@ -11,7 +11,7 @@ from tests.newick import canonical_newick
 from xmp_b200 import hostlib as xh
 
 FAST = ["mt-10", "rbc14x759", "h1", "h2", "h3", "h4", "h5", "mh1", "mh2", "mh3", "mh4", "mh6", "EukaryotesrDNA",
-        "Metazoan", "its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16"]
+        "Metazoan", "its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16", "e1", "e3", "e4", "e5", "e6"]
 
 
 def prepare(alignment_dir, goldens, name, **kw):

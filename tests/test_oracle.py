@@ -72,7 +72,7 @@ def test_oracle_equals_compiled_reference_on_random_inputs():
             int(O.xo_fitch_bases_and_compare(ol.p(s1), ol.p(s2), ol.p(got), ol.p(prev), nbytes) != 0)
 
 
-SEARCH_CASES = ["its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16", "mt-10", "EukaryotesrDNA"]
+SEARCH_CASES = ["its10", "its12", "its14", "primate", "quick2", "53humans.12", "53humans.16", "mt-10", "EukaryotesrDNA", "e1", "e4", "e6"]
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES)

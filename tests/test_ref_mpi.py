@@ -59,7 +59,7 @@ def test_program_needs_the_launcher(tmp_path):
     assert r.returncode != 0 and "xmpirun" in r.stderr
 
 
-@pytest.mark.parametrize("name,ranks", [("quick2", 2), ("its12", 4), ("mt-10", 5), ("h3", 9), ("mh6", 7), ("h3.b358", 4)])
+@pytest.mark.parametrize("name,ranks", [("quick2", 2), ("its12", 4), ("mt-10", 5), ("h3", 9), ("mh6", 7), ("h3.b358", 4), ("e3", 5), ("e5", 9)])
 def test_parallel_reference_finds_the_serial_reference_set(tmp_path, alignment_dir, goldens, name, ranks):
     """One boss and ranks - 1 workers: score, number of trees and canonical tree set of the serial program's golden."""
     _build()
