@@ -87,7 +87,41 @@ static void sets_from_scratch(const Topo &t, const std::vector<uint4> &rows, uns
 	}
 }
 
+// The SWAR primitives themselves (fitch_dev.cuh), against the definition nibble by nibble (src/seq_b2_w1_basic.c:155-244: the
+// intersection if it is not empty, else the union and one unit of cost): every pair of state sets -- the empty set included,
+// which only padding can produce -- at every nibble position, with random neighbours so that a carry or a borrow crossing a
+// nibble boundary would show.
+static unsigned check_primitives() {
+	unsigned checked = 0;
+	for (unsigned pos = 0; pos < 8; ++pos)
+		for (unsigned sa = 0; sa < 16; ++sa)
+			for (unsigned sb = 0; sb < 16; ++sb)
+				for (unsigned rep = 0; rep < 64; ++rep) {
+					unsigned a = 0, b = 0;
+					for (unsigned s = 0; s < 8; ++s) {
+						a |= (s == pos ? sa : rnd(16)) << (4 * s);
+						b |= (s == pos ? sb : rnd(16)) << (4 * s);
+					}
+					unsigned want = 0, want_cost = 0, want_empty = 0;
+					for (unsigned s = 0; s < 8; ++s) {
+						const unsigned x = (a >> (4 * s)) & 15u, y = (b >> (4 * s)) & 15u;
+						want |= ((x & y) ? (x & y) : (x | y)) << (4 * s);
+						if (!(x & y)) {
+							++want_cost;
+							want_empty |= 8u << (4 * s);
+						}
+					}
+					if (fitch_word(a, b) != want || cost_word_w1(a, b) != want_cost || empty_mask(a, b) != want_empty) {
+						printf("primitive mismatch: a=%08x b=%08x merge %08x (want %08x) cost %u (want %u)\n", a, b, fitch_word(a, b), want, cost_word_w1(a, b), want_cost);
+						exit(1);
+					}
+					++checked;
+				}
+	return checked;
+}
+
 int main(int argc, char **argv) {
+	check_primitives();
 	const unsigned max_taxa = argc > 1 ? (unsigned) atoi(argv[1]) : 24;
 	const unsigned reps = argc > 2 ? (unsigned) atoi(argv[2]) : 40;
 	unsigned long checked = 0;

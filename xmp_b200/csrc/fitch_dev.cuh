@@ -42,8 +42,8 @@ XMP_FHD unsigned empty_mask(unsigned a, unsigned b) {
 // Preliminary Fitch set of a node from its two neighbours.
 XMP_FHD unsigned fitch_word(unsigned a, unsigned b) {
 	unsigned e = empty_mask(a, b);
-	unsigned m = (e - (e >> 3)) | e;          // 0xF where the intersection is empty
-	return (a & b) | ((a | b) & m);
+	unsigned m = (e >> 3) * 15u;              // 0xF where the intersection is empty; a multiply so that it runs on the FMA pipe
+	return (a & b) | ((a | b) & m);           //   (IMAD) beside the ALU pipe that LOP3 / SHF / IADD share: 6 + 1 instead of 7 + 1
 }
 
 XMP_FHD uint4 fitch_block(const uint4 &a, const uint4 &b) {
