@@ -120,8 +120,69 @@ static unsigned check_primitives() {
 	return checked;
 }
 
+// The planar form of a block (fitch_dev.cuh): the transposition bit by bit, then the two facts a kernel that keeps its sets
+// planar relies on -- merging commutes with the transposition, costs do not change -- on random blocks (single states,
+// ambiguity sets, padding nibbles 0xF, and empty sets for good measure), weight-1 and weighted, heavy and light blocks.
+static unsigned check_planar() {
+	unsigned checked = 0;
+	for (unsigned rep = 0; rep < 60000; ++rep) {
+		unsigned aw[4], bw[4];
+		for (unsigned i = 0; i < 4; ++i) {
+			aw[i] = bw[i] = 0;
+			for (unsigned j = 0; j < 8; ++j) {
+				const unsigned kind = rnd(10);
+				aw[i] |= (kind < 6 ? 1u << rnd(4) : (kind < 9 ? rnd(16) : 15u)) << (4 * j);
+				bw[i] |= (rnd(10) < 6 ? 1u << rnd(4) : rnd(16)) << (4 * j);
+			}
+		}
+		const uint4 a = make_uint4(aw[0], aw[1], aw[2], aw[3]), b = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+		const uint4 pa = to_planar(a), pb = to_planar(b);
+		const unsigned pw[4] = {pa.x, pa.y, pa.z, pa.w};
+		for (unsigned i = 0; i < 4; ++i)
+			for (unsigned j = 0; j < 8; ++j)
+				for (unsigned k = 0; k < 4; ++k)
+					if (((pw[k] >> (4 * j + i)) & 1u) != ((aw[i] >> (4 * j + k)) & 1u)) {
+						printf("to_planar: word %u nibble %u base %u\n", i, j, k);
+						exit(1);
+					}
+		if (!same(to_planar(fitch_block(a, b)), fitch_block_planar(pa, pb))) {
+			printf("planar merge differs\n");
+			exit(1);
+		}
+		const unsigned w1 = cost_word_w1(a.x, b.x) + cost_word_w1(a.y, b.y) + cost_word_w1(a.z, b.z) + cost_word_w1(a.w, b.w);
+		if (cost_block_planar_w1(pa, pb) != w1) {
+			printf("planar weight-1 cost differs\n");
+			exit(1);
+		}
+		// weighted: 3 blocks of planes built the way the library builds them, the heavy part ending anywhere (also inside a block)
+		const unsigned n_words = 12, n_planes = 3, heavy_words = rnd(n_words + 1), block = rnd(3);
+		unsigned planes[3 * 12];
+		for (unsigned x = 0; x < n_planes * n_words; ++x) planes[x] = 0;
+		for (unsigned w = 0; w < heavy_words; ++w)
+			for (unsigned nib = 0; nib < 8; ++nib) {
+				const unsigned wt = 1 + rnd(7);
+				for (unsigned k = 0; k < n_planes; ++k)
+					if ((wt >> k) & 1u) planes[k * n_words + w] |= 8u << (4 * nib);
+			}
+		WeightPlanes wp{planes, n_words, heavy_words, n_planes};
+		if (cost_block_planar(pa, pb, block, wp) != cost_block(a, b, block, wp)) {
+			printf("planar weighted cost differs (block %u, heavy words %u)\n", block, heavy_words);
+			exit(1);
+		}
+		++checked;
+	}
+	// the neutral element of the merge is all ones in both forms
+	const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+	if (!same(to_planar(ones), ones)) {
+		printf("to_planar(ones)\n");
+		exit(1);
+	}
+	return checked;
+}
+
 int main(int argc, char **argv) {
 	check_primitives();
+	check_planar();
 	const unsigned max_taxa = argc > 1 ? (unsigned) atoi(argv[1]) : 24;
 	const unsigned reps = argc > 2 ? (unsigned) atoi(argv[2]) : 40;
 	unsigned long checked = 0;
@@ -183,6 +244,29 @@ int main(int argc, char **argv) {
 			std::vector<uint4> up(MAXE), down(MAXE), mid(MAXE);
 			for (unsigned col = 0; col < W; ++col) {
 				sets_from_scratch(t, rows, W, col, up.data(), down.data(), mid.data());
+				// the same tree with every set in planar form, as k_score_trees_wide keeps them: rows transposed once, planar
+				// merges throughout -- every set must be the transposed packed set, every insertion cost the same
+				{
+					std::vector<uint4> pup(MAXE), pdown(MAXE);
+					for (int i = (int) E - 1; i >= 0; --i) {
+						const unsigned e = pre[i];
+						pup[e] = t.k0[e] == 0xFF ? to_planar(rows[(size_t) edge_taxon(e) * W + col]) : fitch_block_planar(pup[t.k0[e]], pup[t.k1[e]]);
+					}
+					const uint4 pnext = to_planar(rows[(size_t) m * W + col]);
+					for (unsigned i = 0; i < E; ++i) {
+						const unsigned e = pre[i], p = t.par[e];
+						pdown[e] = p == 0xFF ? fitch_block_planar(to_planar(rows[col]), make_uint4(~0u, ~0u, ~0u, ~0u))
+						                     : fitch_block_planar(pdown[p], pup[t.k0[p] == e ? t.k1[p] : t.k0[p]]);
+						const uint4 pmid = fitch_block_planar(pup[e], pdown[e]);
+						const bool w1 = 4u * col >= wp.heavy_words;
+						const unsigned c = w1 ? cost_block_planar_w1(pmid, pnext) : cost_block_planar(pmid, pnext, col, wp);
+						if (!same(pup[e], to_planar(up[e])) || !same(pdown[e], to_planar(down[e])) || !same(pmid, to_planar(mid[e])) ||
+						    c != cost_block(mid[e], rows[(size_t) m * W + col], col, wp)) {
+							printf("planar tree: m=%u edge %u column %u\n", m, e, col);
+							return 1;
+						}
+					}
+				}
 				uint4 *base = sets_of(pool, L, slot) + col;
 				const size_t rs = (size_t) W << L.ts_shift;
 				for (unsigned i = 0; i < E; ++i) {

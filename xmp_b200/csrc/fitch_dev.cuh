@@ -71,6 +71,48 @@ XMP_FHD unsigned cost_block(const uint4 &a, const uint4 &b, unsigned block, cons
 	return cost_word(a.x, b.x, w, wp) + cost_word(a.y, b.y, w + 1, wp) + cost_word(a.z, b.z, w + 2, wp) + cost_word(a.w, b.w, w + 3, wp);
 }
 
+// ---- planar blocks -------------------------------------------------------------------------------------------
+// The same 128 bits per 32 sites, transposed inside the block: word k holds bit k (base k) of every site, the site in
+// nibble j of word i sitting at bit 4j + i.  In this form the Fitch merge is pure three-input logic -- the sites whose
+// sets intersect are the OR over the four planes of (a AND b), and every plane of the result is one LOP3 of its two
+// inputs and that word -- 8 LOP3 per 32 sites where the packed form takes 4 x (4 LOP3 + SHF + add + IMAD), and a
+// weight-1 cost is 4 LOP3 and one POPC where the packed form takes 4 x (3 LOP3 + add + POPC).  Used by kernels that
+// keep their state sets to themselves (k_score_trees_wide: rows are transposed when a CTA loads them, costs come out
+// the same); everything that crosses the C ABI stays in the reference's packed form (src/common.h:75-78).
+// The transposition is a homomorphism: to_planar(fitch_block(a, b)) == fitch_block_planar(to_planar(a), to_planar(b)),
+// and the costs agree; tests/child_walk_check.cu checks both on the host.
+XMP_FHD unsigned planar_pick(unsigned c0, unsigned c1, unsigned c2, unsigned c3) {
+	return (c0 & 0x11111111u) | (c1 & 0x22222222u) | (c2 & 0x44444444u) | (c3 & 0x88888888u);
+}
+XMP_FHD uint4 to_planar(const uint4 &v) {          // plane k, bit 4j + i  <-  bit 4j + k of word i: word i shifted by i - k
+	return make_uint4(planar_pick(v.x, v.y << 1, v.z << 2, v.w << 3),
+	                  planar_pick(v.x >> 1, v.y, v.z << 1, v.w << 2),
+	                  planar_pick(v.x >> 2, v.y >> 1, v.z, v.w << 1),
+	                  planar_pick(v.x >> 3, v.y >> 2, v.z >> 1, v.w));
+}
+// Bit s set iff the sets of site s intersect.
+XMP_FHD unsigned planar_meet(const uint4 &a, const uint4 &b) { return (a.x & b.x) | (a.y & b.y) | (a.z & b.z) | (a.w & b.w); }
+XMP_FHD uint4 fitch_block_planar(const uint4 &a, const uint4 &b) {
+	const unsigned ne = planar_meet(a, b);         // where it is set the result is a AND b, elsewhere a OR b
+	return make_uint4((a.x & b.x) | ((a.x | b.x) & ~ne), (a.y & b.y) | ((a.y | b.y) & ~ne),
+	                  (a.z & b.z) | ((a.z | b.z) & ~ne), (a.w & b.w) | ((a.w | b.w) & ~ne));
+}
+XMP_FHD unsigned cost_block_planar_w1(const uint4 &a, const uint4 &b) { return XMP_POPC(~planar_meet(a, b)); }
+// Weighted: the flags of word i of the packed block are bits i, 4 + i, 8 + i, ... of the planar flag word; put back on
+// bit 3 of their nibbles they meet the bit-sliced weight planes as in cost_word().
+XMP_FHD unsigned cost_block_planar(const uint4 &a, const uint4 &b, unsigned block, const WeightPlanes &wp) {
+	const unsigned n = ~planar_meet(a, b), w = 4 * block;
+	if (w >= wp.heavy_words) return XMP_POPC(n);
+	unsigned s = 0;
+	for (unsigned i = 0; i < 4; ++i) {
+		const unsigned e = ((n >> i) & 0x11111111u) << 3;
+		if (w + i >= wp.heavy_words) s += XMP_POPC(e);
+		else
+			for (unsigned k = 0; k < wp.n_planes; ++k) s += XMP_POPC(e & XMP_LDG(wp.planes + (size_t) k * wp.n_words + w + i)) << k;
+	}
+	return s;
+}
+
 // Streaming 128-bit load: read once, do not keep in L1.
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
 	uint4 r;

@@ -430,7 +430,9 @@ k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlan
 	}
 	// Rows of this column tile: the scored taxon is row `taxon` (= m for the search's use), rows 0 .. m-1 are the leaves.
 	// Columns past the end hold all ones in every row: they merge to all ones and cost nothing.
-	for (unsigned t = 0; t <= m; ++t) sm[t * T + tid] = ok ? __ldg(rows + (size_t) (t == m ? taxon : t) * n_blocks + col) : ones;
+	// Every slot holds its block in PLANAR form (fitch_dev.cuh): the rows are transposed here, once per CTA, and from then on a merge
+	// is 8 LOP3 instead of 28 instructions and a weight-1 cost 4 LOP3 + POPC instead of 20; only the costs leave the kernel.
+	for (unsigned t = 0; t <= m; ++t) sm[t * T + tid] = ok ? to_planar(__ldg(rows + (size_t) (t == m ? taxon : t) * n_blocks + col)) : ones;
 	sm[ONES * T + tid] = ones;
 	const uint4 rx = sm[m * T + tid];
 	const bool w1 = 4u * (ok ? col : 0u) >= wp.heavy_words;     // this column holds weight-1 sites only
@@ -443,17 +445,17 @@ k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlan
 		unsigned at = up0 + 16u * lt * I;
 		for (unsigned k = 0; k < I; ++k, at += 16u) {           // UP sets of the internal edges, children before parents
 			const uint4 u = lds128(at);
-			sts128(me + u.x, fitch_block(lds128(me + u.y), lds128(me + u.z)));
+			sts128(me + u.x, fitch_block_planar(lds128(me + u.y), lds128(me + u.z)));
 		}
 		at = dn0 + 16u * lt * E;
 		for (unsigned i = 0; i < E; ++i, at += 16u, acc_at += 4u) {   // DOWN and MIDPOINT in pre-order, scored on the spot
 			const uint4 w = lds128(at);
-			const uint4 d = fitch_block(lds128(me + w.x), lds128(me + w.y));
+			const uint4 d = fitch_block_planar(lds128(me + w.x), lds128(me + w.y));
 			sts128(me + w.w, d);
-			const uint4 mid = fitch_block(lds128(me + w.z), d);
+			const uint4 mid = fitch_block_planar(lds128(me + w.z), d);
 			unsigned c;
-			if (w1) c = cost_word_w1(mid.x, rx.x) + cost_word_w1(mid.y, rx.y) + cost_word_w1(mid.z, rx.z) + cost_word_w1(mid.w, rx.w);
-			else c = cost_block(mid, rx, col, wp);
+			if (w1) c = cost_block_planar_w1(mid, rx);
+			else c = cost_block_planar(mid, rx, col, wp);
 			c = __reduce_add_sync(0xffffffffu, c);
 			if (lane0) sts32(acc_at, c);
 		}
