@@ -572,6 +572,27 @@ def run_ours(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_reps
     assert int(cost_host.astype(np.int64).sum()) == checksum, "end-to-end costs differ from the resident-input costs"
+    # The same call with the end-to-end kernel in its PACKED form (XMP_E2E_PACKED=1: the kernel every measurement up to the end of
+    # round 2 was taken with; the shipped one keeps its sets in planar form): an A/B inside one run.  A reported
+    # extra, so a failure here is recorded and does not cost the line.
+    e2e_packed = None
+    try:
+        cost_packed = np.zeros_like(cost_host)
+        os.environ["XMP_E2E_PACKED"] = "1"
+        ctx2.load(rows_np)
+        ctx2.score_insertions_host(wl["paths"][:e2e_trees], M, cost_packed)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_reps):
+            ctx2.load(rows_np)
+            ctx2.score_insertions_host(wl["paths"][:e2e_trees], M, cost_packed)
+        torch.cuda.synchronize()
+        e2e_packed = {"ms_per_step": (time.perf_counter() - t0) / e2e_reps * 1e3, "costs_equal_planar_form": bool((cost_packed == cost_host).all()),
+                      "planar_form_ms_per_step_this_rank": e2e_s * 1e3}
+    except Exception as e:  # noqa: BLE001
+        e2e_packed = {"error": repr(e)}
+    finally:
+        os.environ.pop("XMP_E2E_PACKED", None)
     ctx2.close()
 
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -623,7 +644,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "what": "xmp_cuda_load(alignment from pinned host memory) + xmp_cuda_score_insertions_host(topologies) -> costs in host memory; "
-                        "state sets are built on the device inside the timed region; counts insertion-scoring site-merges only"},
+                        "state sets are built on the device inside the timed region; counts insertion-scoring site-merges only",
+                "packed_form": e2e_packed},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_score_wide<8>", "algorithmic_bytes_per_launch": n_pairs * NUM_SITES // 2,

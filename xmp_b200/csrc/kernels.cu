@@ -382,6 +382,9 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 // Step tables (shared memory, read back as 16-byte broadcasts); all fields are BYTE offsets of slots, i.e. slot * 16 * blockDim.x.
 //   down step of pre-order position i:  DOWN(e) = F(src, sib);  MIDPOINT = F(upe, DOWN);  DOWN is kept at dst
 //   up step (internal edges only, children before parents):  slot dst = F(a, b)
+// PLANAR = false is the packed form the kernel used until the end of round 2 (every GPU measurement of that round); kept
+// selectable (XMP_E2E_PACKED=1) so that bench.py can time both forms in one run.
+template <bool PLANAR>
 __global__ void __launch_bounds__(128)
 k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp, const uint8_t *__restrict__ topo,
                    unsigned topo_stride, unsigned n_trees, unsigned trees_per_cta, unsigned m, unsigned taxon,
@@ -432,7 +435,10 @@ k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlan
 	// Columns past the end hold all ones in every row: they merge to all ones and cost nothing.
 	// Every slot holds its block in PLANAR form (fitch_dev.cuh): the rows are transposed here, once per CTA, and from then on a merge
 	// is 8 LOP3 instead of 28 instructions and a weight-1 cost 4 LOP3 + POPC instead of 20; only the costs leave the kernel.
-	for (unsigned t = 0; t <= m; ++t) sm[t * T + tid] = ok ? to_planar(__ldg(rows + (size_t) (t == m ? taxon : t) * n_blocks + col)) : ones;
+	for (unsigned t = 0; t <= m; ++t) {
+		const uint4 r = ok ? __ldg(rows + (size_t) (t == m ? taxon : t) * n_blocks + col) : ones;
+		sm[t * T + tid] = PLANAR ? to_planar(r) : r;                 // to_planar(ones) == ones
+	}
 	sm[ONES * T + tid] = ones;
 	const uint4 rx = sm[m * T + tid];
 	const bool w1 = 4u * (ok ? col : 0u) >= wp.heavy_words;     // this column holds weight-1 sites only
@@ -445,17 +451,25 @@ k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlan
 		unsigned at = up0 + 16u * lt * I;
 		for (unsigned k = 0; k < I; ++k, at += 16u) {           // UP sets of the internal edges, children before parents
 			const uint4 u = lds128(at);
-			sts128(me + u.x, fitch_block_planar(lds128(me + u.y), lds128(me + u.z)));
+			const uint4 a = lds128(me + u.y), b = lds128(me + u.z);
+			sts128(me + u.x, PLANAR ? fitch_block_planar(a, b) : fitch_block(a, b));
 		}
 		at = dn0 + 16u * lt * E;
 		for (unsigned i = 0; i < E; ++i, at += 16u, acc_at += 4u) {   // DOWN and MIDPOINT in pre-order, scored on the spot
 			const uint4 w = lds128(at);
-			const uint4 d = fitch_block_planar(lds128(me + w.x), lds128(me + w.y));
+			const uint4 a = lds128(me + w.x), b = lds128(me + w.y);
+			const uint4 d = PLANAR ? fitch_block_planar(a, b) : fitch_block(a, b);
 			sts128(me + w.w, d);
-			const uint4 mid = fitch_block_planar(lds128(me + w.z), d);
+			const uint4 ue = lds128(me + w.z);
+			const uint4 mid = PLANAR ? fitch_block_planar(ue, d) : fitch_block(ue, d);
 			unsigned c;
-			if (w1) c = cost_block_planar_w1(mid, rx);
-			else c = cost_block_planar(mid, rx, col, wp);
+			if (PLANAR) {
+				if (w1) c = cost_block_planar_w1(mid, rx);
+				else c = cost_block_planar(mid, rx, col, wp);
+			} else {
+				if (w1) c = cost_word_w1(mid.x, rx.x) + cost_word_w1(mid.y, rx.y) + cost_word_w1(mid.z, rx.z) + cost_word_w1(mid.w, rx.w);
+				else c = cost_block(mid, rx, col, wp);
+			}
 			c = __reduce_add_sync(0xffffffffu, c);
 			if (lane0) sts32(acc_at, c);
 		}
@@ -484,13 +498,20 @@ int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_s
 	while (per_cta > 1 && bytes(per_cta) > bytes(1) + ((size_t) 9 << 10)) per_cta >>= 1;      // tables: at most 9 KiB on top of the slots
 	const size_t smem = bytes(per_cta);
 	if (smem > ((size_t) 220 << 10)) return set_error(XMP_ERR_ARG, "trees on %u taxa need %zu bytes of shared memory per CTA", m, smem);
-	XMP_CUDA(cudaFuncSetAttribute(k_score_trees_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	const char *env = getenv("XMP_E2E_PACKED");
+	const bool packed = env && env[0] == '1';                      // A/B switch for measurements: the packed-form kernel
+	XMP_CUDA(cudaFuncSetAttribute(k_score_trees_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	XMP_CUDA(cudaFuncSetAttribute(k_score_trees_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	XMP_CUDA(cudaMemsetAsync(d_cost, 0, (size_t) n_trees * E * sizeof(unsigned), ctx->stream));
 	for (unsigned t0 = 0; t0 < n_trees; t0 += 65535u * per_cta) {
 		const unsigned nt = std::min(n_trees - t0, 65535u * per_cta);
 		dim3 grid(col_tiles, (nt + per_cta - 1) / per_cta);
-		k_score_trees_wide<<<grid, threads, smem, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo + (size_t) t0 * 4 * topo_stride, topo_stride, nt,
-		                                                        per_cta, m, taxon, d_cost + (size_t) t0 * E);
+		if (packed)
+			k_score_trees_wide<false><<<grid, threads, smem, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo + (size_t) t0 * 4 * topo_stride, topo_stride,
+			                                                               nt, per_cta, m, taxon, d_cost + (size_t) t0 * E);
+		else
+			k_score_trees_wide<true><<<grid, threads, smem, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo + (size_t) t0 * 4 * topo_stride, topo_stride,
+			                                                              nt, per_cta, m, taxon, d_cost + (size_t) t0 * E);
 	}
 	XMP_CUDA(cudaGetLastError());
 	return XMP_OK;
