@@ -473,6 +473,24 @@ def run_reference_bandb_mpi(names, workers, budget_s=90.0):
     return out
 
 
+def run_planar_search_ab(names, timeout_s=150.0):
+    """A/B of the search with every state set in planar form (XMP_SEARCH_PLANAR=1: an off-by-default switch of the library, DESIGN.md
+    section 7) on a few datasets, in a SEPARATE process so that nothing it does can touch this run: `bench.py --bandb-only` with the
+    switch in its environment.  Returns the records of that run (time to optimum, matches_reference, ...) or {"error": ...}."""
+    env = dict(os.environ, XMP_SEARCH_PLANAR="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--bandb-only", ",".join(names)], env=env, capture_output=True, text=True,
+                           timeout=timeout_s)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "exit code %d: %s" % (r.returncode, (r.stderr or "")[-400:])}
+        return {"datasets": json.loads(lines[-1])["datasets"]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 # ------------------------------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -612,6 +630,10 @@ def run_ours(args):
                 bandb_error = repr(e)
         else:
             bandb = run_bandb(torch, xc, dist, rank, world, local, BANDB_DATASETS)
+    planar_ab = None
+    if world == 1 and bandb is not None and not os.environ.get("XMP_SEARCH_PLANAR") and not os.environ.get("XMP_BENCH_NO_PLANAR_AB"):
+        # the planar-form search variant on the three searches the review names, while the GPU is otherwise idle
+        planar_ab = run_planar_search_ab(["h4", "mh3", "its36"])
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -676,6 +698,19 @@ def run_ours(args):
                         "n_gpus": world, "datasets": bandb}
     if bandb_error is not None:
         out["bandb"] = {"error": bandb_error}
+    if planar_ab is not None and "bandb" in out:
+        ab = {"what": "the same searches by a second process of this run with XMP_SEARCH_PLANAR=1: every state set of the search in planar form "
+                      "(word k of a 128-bit block = base k of its 32 sites: a merge is 8 LOP3 instead of 28 instructions), an A/B switch that is "
+                      "off by default; seconds to the proven optimum and whether score, tree count and canonical tree-set hash equal the "
+                      "reference's"}
+        if "error" in planar_ab:
+            ab["error"] = planar_ab["error"]
+        else:
+            base = {b["dataset"]: b for b in (bandb or [])}
+            ab["datasets"] = [{"dataset": d["dataset"], "time_to_optimum_s": d["time_to_optimum_s"], "matches_reference": d["matches_reference"],
+                               "nodes": d["nodes"], "packed_form_time_to_optimum_s": base.get(d["dataset"], {}).get("time_to_optimum_s")}
+                              for d in planar_ab["datasets"]]
+        out["bandb"]["planar_search_variant"] = ab
     if world == 1 and not os.environ.get("XMP_BENCH_SKIP_CPU"):       # A/B runs: skip the 12-second CPU leg
         rows = rows_np
         threads = os.cpu_count() or 1

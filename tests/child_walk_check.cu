@@ -186,7 +186,13 @@ int main(int argc, char **argv) {
 	const unsigned max_taxa = argc > 1 ? (unsigned) atoi(argv[1]) : 24;
 	const unsigned reps = argc > 2 ? (unsigned) atoi(argv[2]) : 40;
 	unsigned long checked = 0;
+	// second pass: the same replay with every state set in planar form (a search run with XMP_SEARCH_PLANAR=1: planar rows in,
+	// the kernels' <PLANAR = true> instantiations) -- sets must be the transposed sets, programs and costs the same
+	for (unsigned pass = 0; pass < 2; ++pass)
 	for (unsigned rep = 0; rep < reps; ++rep) {
+		const bool planar = pass == 1;
+		auto X = [&](const uint4 &v) { return planar ? to_planar(v) : v; };
+		auto MB = [&](const uint4 &a, const uint4 &b) { return planar ? merge_block<true>(a, b) : merge_block<false>(a, b); };
 		const unsigned n = max_taxa, W = 1 + rep % 3;
 		const bool eager = rep % 4 != 3, weighted = rep % 2 == 1;
 		// alignment: mostly single states, some ambiguity sets; padding nibbles do not occur (every nibble is a set)
@@ -270,8 +276,8 @@ int main(int argc, char **argv) {
 				uint4 *base = sets_of(pool, L, slot) + col;
 				const size_t rs = (size_t) W << L.ts_shift;
 				for (unsigned i = 0; i < E; ++i) {
-					base[(size_t) (up_row0(L, E) + i) * rs] = up[pre[i]];
-					if (!eager) base[(size_t) i * rs] = mid[pre[i]];
+					base[(size_t) (up_row0(L, E) + i) * rs] = X(up[pre[i]]);
+					if (!eager) base[(size_t) i * rs] = X(mid[pre[i]]);
 				}
 			}
 			// expand at every position; continue the tree with one of them
@@ -292,14 +298,15 @@ int main(int argc, char **argv) {
 					const unsigned T = 1, D = m + 1;
 					std::vector<uint4> upath(D), dstack(D);
 					const uint4 *PU = sets_of(pool, L, slot) + (size_t) up_row0(L, E) * ((size_t) W << L.ts_shift) + col;
-					const uint4 r0 = rows[col], rt = rows[(size_t) m * W + col], rn = rows[(size_t) (m + 1) * W + col];
+					const uint4 r0 = X(rows[col]), rt = X(rows[(size_t) m * W + col]), rn = X(rows[(size_t) (m + 1) * W + col]);
 					bool overflow = false;
 					ChildWalk cw;
 					// eager layout: the root-path UP sets live in the child's own rows (tiled like a pool's), as in the kernel
 					std::vector<uint4> crows((size_t) Ec * ((size_t) W << L.ts_shift) + 64);
 					uint4 *CU = eager ? crows.data() + col : nullptr;
 					uint4 *up_arg = eager ? nullptr : upath.data();
-					cw.init(ph, L, m, P, PU, rt, up_arg, T, D, overflow, CU);
+					if (planar) cw.init<true>(ph, L, m, P, PU, rt, up_arg, T, D, overflow, CU);
+					else cw.init<false>(ph, L, m, P, PU, rt, up_arg, T, D, overflow, CU);
 					unsigned wj, pw1 = cw.word_for(1);
 					uint4 ux, us;
 					cw.step(0, cw.word_for(0), wj, ux, us, up_arg, T, r0);
@@ -310,21 +317,24 @@ int main(int argc, char **argv) {
 						if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, up_arg, T, r0);
 						pw1 = pw2;
 						const unsigned d = prog_depth(wj);
-						const uint4 dn = d == 0 ? r0 : fitch_block(dstack[d - 1], us);
+						const uint4 dn = d == 0 ? r0 : MB(dstack[d - 1], us);
 						if (prog_size(wj) > 1u) {
 							if (d < D) dstack[d] = dn; else overflow = true;
 						}
 						if (CU) CU[(size_t) j * ((size_t) W << L.ts_shift)] = ux;
-						const uint4 m_j = fitch_block(ux, dn);
-						cost[j] += cost_block(m_j, rn, col, wp);
+						const uint4 m_j = MB(ux, dn);
+						// the kernels' own selection: the weight-1 form for columns past the heavy words
+						if (4u * col >= wp.heavy_words) cost[j] += planar ? score_block_w1<true>(m_j, rn) : score_block_w1<false>(m_j, rn);
+						else cost[j] += planar ? score_block<true>(m_j, rn, col, wp) : score_block<false>(m_j, rn, col, wp);
 						// --- checks ---
 						const unsigned e = cpre[j];
 						if (wj != want[j]) { printf("rep %u m %u P %u step %u: word %08x, from scratch %08x\n", rep, m, P, j, wj, want[j]); return 1; }
-						if (!same(ux, cup[e])) { printf("rep %u m %u P %u step %u col %u: UP set differs\n", rep, m, P, j, col); return 1; }
-						if (!same(dn, cdown[e])) { printf("rep %u m %u P %u step %u col %u: DOWN set differs\n", rep, m, P, j, col); return 1; }
-						if (!same(m_j, cmid[e])) { printf("rep %u m %u P %u step %u col %u: MIDPOINT set differs\n", rep, m, P, j, col); return 1; }
+						if (!same(ux, X(cup[e]))) { printf("rep %u m %u P %u step %u col %u: UP set differs\n", rep, m, P, j, col); return 1; }
+						if (!same(dn, X(cdown[e]))) { printf("rep %u m %u P %u step %u col %u: DOWN set differs\n", rep, m, P, j, col); return 1; }
+						if (!same(m_j, X(cmid[e]))) { printf("rep %u m %u P %u step %u col %u: MIDPOINT set differs\n", rep, m, P, j, col); return 1; }
 						// the reference's definition of the cost, site by site
-						const unsigned mw[4] = {cmid[e].x, cmid[e].y, cmid[e].z, cmid[e].w}, tw[4] = {rn.x, rn.y, rn.z, rn.w};
+						const uint4 rn_packed = rows[(size_t) (m + 1) * W + col];
+						const unsigned mw[4] = {cmid[e].x, cmid[e].y, cmid[e].z, cmid[e].w}, tw[4] = {rn_packed.x, rn_packed.y, rn_packed.z, rn_packed.w};
 						for (unsigned k = 0; k < 4; ++k)
 							for (unsigned s = 0; s < 8; ++s)
 								if (!((mw[k] >> (4 * s)) & (tw[k] >> (4 * s)) & 15u)) want_cost[j] += weights[(size_t) 8 * (4 * col + k) + s];
@@ -336,20 +346,21 @@ int main(int argc, char **argv) {
 						std::vector<uint4> upath2(D), dstack2(D);
 						ChildWalk lw;
 						bool of2 = false;
-						lw.init(ph, L, m, P, PU, rt, upath2.data(), T, D, of2);
+						if (planar) lw.init<true>(ph, L, m, P, PU, rt, upath2.data(), T, D, of2);
+						else lw.init<false>(ph, L, m, P, PU, rt, upath2.data(), T, D, of2);
 						for (unsigned j = 0; j < Ec; ++j) {
 							unsigned depth = 0;
 							bool internal = false;
 							uint4 lux, lus;
 							lw.step_lean(j, lw.word_for(j), depth, internal, lux, lus, upath2.data(), T, r0);
 							const unsigned e = cpre[j];
-							const uint4 dn = depth == 0 ? r0 : fitch_block(dstack2[depth - 1], lus);
+							const uint4 dn = depth == 0 ? r0 : MB(dstack2[depth - 1], lus);
 							if (internal) dstack2[depth] = dn;
 							if (depth != prog_depth(want[j]) || internal != (prog_size(want[j]) > 1u) || lw.edge_at(j) != prog_edge(want[j])) {
 								printf("rep %u m %u P %u step %u: lean step gives depth %u internal %d edge %u, from scratch %08x\n", rep, m, P, j, depth, (int) internal, lw.edge_at(j), want[j]);
 								return 1;
 							}
-							if (!same(lux, cup[e]) || !same(dn, cdown[e])) { printf("rep %u m %u P %u step %u col %u: lean step: UP or DOWN set differs\n", rep, m, P, j, col); return 1; }
+							if (!same(lux, X(cup[e])) || !same(dn, X(cdown[e]))) { printf("rep %u m %u P %u step %u col %u: lean step: UP or DOWN set differs\n", rep, m, P, j, col); return 1; }
 						}
 					}
 				}

@@ -82,6 +82,8 @@ struct ChildWalk {
 	uint4 *gup;
 
 	// Decodes the insertion at position P of the parent and recomputes UP along the root path.
+	// PLANAR: the state sets (the parent's rows, row_new) are in planar form (fitch_dev.cuh); the walk itself never looks inside a set.
+	template <bool PLANAR = false>
 	XMP_HD unsigned init(const unsigned *ph, const Layout &L, unsigned m, unsigned P, const uint4 *parent_up,
 	                                         const uint4 &row_new, uint4 *upath, unsigned T, unsigned D, bool &overflow,
 	                                         uint4 *child_rows = nullptr) {
@@ -92,7 +94,7 @@ struct ChildWalk {
 		rt = row_new;
 		sp = make_splice(P, prog[P * 32u], E);
 		lim = 0;
-		uint4 u = fitch_block(rt, XMP_LDG(PU + P * rs));
+		uint4 u = merge_block<PLANAR>(rt, XMP_LDG(PU + P * rs));
 		gup = child_rows;
 		if (gup) gup[P * rs] = u;
 		else upath[0] = u;
@@ -105,7 +107,7 @@ struct ChildWalk {
 			cur = parent_pos(cur, other);
 			other = prog_sib(prog[cur * 32u]);
 			const uint4 off_next = depth > 1 ? XMP_LDG(PU + other * rs) : rt;
-			u = fitch_block(u, off);
+			u = merge_block<PLANAR>(u, off);
 			if (gup) gup[cur * rs] = u;
 			else if (k < D) upath[k * T] = u;
 			else overflow = true;

@@ -101,8 +101,9 @@ int launch_score_sets(xmp_ctx *ctx, const uint4 *d_sets, unsigned long long tree
 // Builds state sets for n_trees trees on m taxa whose topologies were uploaded to d_topo
 // ([tree][4][stride] bytes: par, kid0, kid1, preorder; byte `stride-1` of the par row = top).
 // rec_blocks = uint4 per tree record; MIDPOINT sets at 0 and, when store_all, UP sets at E*W.
+// planar_rows != nullptr: read those rows (the alignment in planar form) and write planar sets.
 int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
-                      uint4 *d_out, size_t rec_blocks, bool store_all, unsigned *d_tree_len);
+                      uint4 *d_out, size_t rec_blocks, bool store_all, unsigned *d_tree_len, const uint4 *planar_rows = nullptr);
 int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m,
                             unsigned taxon, unsigned *d_cost);
 void search_destroy(xmp_ctx *ctx);

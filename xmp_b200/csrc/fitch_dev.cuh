@@ -113,6 +113,18 @@ XMP_FHD unsigned cost_block_planar(const uint4 &a, const uint4 &b, unsigned bloc
 	return s;
 }
 
+// The same three operations in whichever form a kernel's template parameter selects.
+template <bool PLANAR>
+XMP_FHD uint4 merge_block(const uint4 &a, const uint4 &b) { return PLANAR ? fitch_block_planar(a, b) : fitch_block(a, b); }
+template <bool PLANAR>
+XMP_FHD unsigned score_block(const uint4 &a, const uint4 &b, unsigned block, const WeightPlanes &wp) {
+	return PLANAR ? cost_block_planar(a, b, block, wp) : cost_block(a, b, block, wp);
+}
+template <bool PLANAR>
+XMP_FHD unsigned score_block_w1(const uint4 &a, const uint4 &b) {
+	return PLANAR ? cost_block_planar_w1(a, b) : cost_word_w1(a.x, b.x) + cost_word_w1(a.y, b.y) + cost_word_w1(a.z, b.z) + cost_word_w1(a.w, b.w);
+}
+
 // Streaming 128-bit load: read once, do not keep in L1.
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
 	uint4 r;

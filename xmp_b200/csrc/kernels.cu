@@ -307,7 +307,9 @@ int launch_score_batch(xmp_ctx *ctx, const uint4 *d_sets, size_t n_pairs, unsign
 // State sets of whole trees from their topologies: one thread per (tree, 128-bit column).
 // UP sets in reverse pre-order, then DOWN and MIDPOINT in pre-order.
 // ---------------------------------------------------------------------------------------------
-template <int MAXE>
+// PLANAR: rows come in and sets go out in planar form (fitch_dev.cuh) -- a search run with XMP_SEARCH_PLANAR=1 builds its root and
+// its imported subtrees this way; the public entry points (xmp_cuda_build_midpoints) always use the packed form.
+template <int MAXE, bool PLANAR>
 __global__ void __launch_bounds__(128)
 k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp, const uint8_t *__restrict__ topo,
              unsigned topo_stride, unsigned n_trees, unsigned m, uint4 *__restrict__ out, unsigned long long rec_blocks,
@@ -327,12 +329,12 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 				up[e] = __ldg(rows + (size_t) edge_taxon(e) * n_blocks + col);
 			} else {
 				uint4 a = up[k0[e]], b = up[k1[e]];
-				len += cost_block(a, b, col, wp);
-				up[e] = fitch_block(a, b);
+				len += score_block<PLANAR>(a, b, col, wp);
+				up[e] = merge_block<PLANAR>(a, b);
 			}
 		}
 		const uint4 r0 = __ldg(rows + col);
-		len += cost_block(up[pre[0]], r0, col, wp);
+		len += score_block<PLANAR>(up[pre[0]], r0, col, wp);
 		uint4 *rec = out + tree * rec_blocks;
 		for (unsigned i = 0; i < E; ++i) {
 			unsigned e = pre[i], p = par[e];
@@ -341,10 +343,10 @@ k_build_sets(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlanes wp,
 				d = r0;
 			} else {
 				unsigned sib = (k0[p] == e) ? k1[p] : k0[p];
-				d = fitch_block(down[p], up[sib]);
+				d = merge_block<PLANAR>(down[p], up[sib]);
 			}
 			down[e] = d;
-			rec[(size_t) e * n_blocks + col] = fitch_block(up[e], d);
+			rec[(size_t) e * n_blocks + col] = merge_block<PLANAR>(up[e], d);
 			if (store_all) rec[((size_t) E + e) * n_blocks + col] = up[e];
 		}
 	}
@@ -518,15 +520,21 @@ int launch_score_trees_wide(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_s
 }
 
 int launch_build_sets(xmp_ctx *ctx, const uint8_t *d_topo, unsigned topo_stride, unsigned n_trees, unsigned m, uint4 *d_out,
-                      size_t rec_blocks, bool store_all, unsigned *d_tree_len) {
+                      size_t rec_blocks, bool store_all, unsigned *d_tree_len, const uint4 *planar_rows) {
 	if (n_trees == 0) return XMP_OK;
 	const unsigned E = 2 * m - 3;
 	const unsigned long long threads = (unsigned long long) n_trees * ctx->n_blocks;
 	const unsigned blocks = (unsigned) ((threads + 127) / 128);
 	if (d_tree_len) XMP_CUDA(cudaMemsetAsync(d_tree_len, 0, (size_t) n_trees * sizeof(unsigned), ctx->stream));
-#define XMP_BUILD(MAXE)                                                                                             \
-	k_build_sets<MAXE><<<blocks, 128, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo, topo_stride, n_trees, m, \
-	                                                    d_out, rec_blocks, store_all ? 1 : 0, d_tree_len, ctx->constant_weight)
+#define XMP_BUILD(MAXE)                                                                                                                  \
+	do {                                                                                                                                 \
+		if (planar_rows)                                                                                                                 \
+			k_build_sets<MAXE, true><<<blocks, 128, 0, ctx->stream>>>(planar_rows, ctx->n_blocks, ctx->wp, d_topo, topo_stride, n_trees, m,  \
+			                                                          d_out, rec_blocks, store_all ? 1 : 0, d_tree_len, ctx->constant_weight); \
+		else                                                                                                                             \
+			k_build_sets<MAXE, false><<<blocks, 128, 0, ctx->stream>>>(ctx->d_rows, ctx->n_blocks, ctx->wp, d_topo, topo_stride, n_trees, m, \
+			                                                           d_out, rec_blocks, store_all ? 1 : 0, d_tree_len, ctx->constant_weight); \
+	} while (0)
 	if (E <= 16) XMP_BUILD(16);
 	else if (E <= 32) XMP_BUILD(32);
 	else if (E <= 72) XMP_BUILD(72);

@@ -85,7 +85,7 @@ __device__ __forceinline__ unsigned path_hash(const unsigned *h, unsigned m, uns
 // Pairs are enumerated tile by tile, position by position, slot-minor: a warp reads whole 128-byte lines of
 // MIDPOINT rows, and the survivors of one tile (<= 8 parents) stay together in the survivor list, so that
 // the child kernels find their parents' data in L1.
-template <int G>
+template <int G, bool PLANAR>
 __global__ void __launch_bounds__(256)
 k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned long long n_nodes,
                const uint4 *__restrict__ taxon_row, WeightPlanes wp, unsigned rest, unsigned *bound_ptr, int last,
@@ -109,7 +109,7 @@ k_expand_score(PoolView pool, Layout L, unsigned m, unsigned long long first, un
 	__syncthreads();
 	if (valid) {
 		const uint4 *src = sets_of(pool, L, node) + ((size_t) pos << ts) * L.W;
-		for (unsigned b = sub; b < L.W; b += G) s += cost_block(src[b], __ldg(taxon_row + b), b, wp);
+		for (unsigned b = sub; b < L.W; b += G) s += score_block<PLANAR>(src[b], __ldg(taxon_row + b), b, wp);
 	}
 #pragma unroll
 	for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -227,6 +227,7 @@ k_select(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned
 // (depth_out collects it for the next level), not from the worst case m + 1, so that deep levels (20-36 taxa)
 // still fit four CTAs per SM.  (Compiling for six CTAs -- 80 registers -- was measured and is slower:
 // profiles/r01_search_tuning.md.)
+template <bool PLANAR>
 __global__ void __launch_bounds__(128)
 k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const uint4 *__restrict__ surv,
                  const unsigned *n_surv_ptr, unsigned s_begin, unsigned s_end, unsigned long long child_first,
@@ -257,7 +258,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 		unsigned *cprog = ch + L.off_prog * 32u;
 		const uint4 r0 = __ldg(rows + col);
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T, D, overflow);
+		const unsigned n_up = cw.init<PLANAR>(ph, L, m, P, PU, __ldg(rows + (size_t) m * W + col), upath, T, D, overflow);
 		// software-pipelined by one step: the UP sets of step j + 1 are requested before step j's arithmetic
 		// (two steps ahead was measured and gains nothing: profiles/r01_search_tuning.md)
 		unsigned wj, first_edge = 0;
@@ -271,13 +272,13 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 			if (j + 1 < Ec) cw.step(j + 1, pw1, wn, uxn, usn, upath, T, r0);
 			pw1 = pw2;
 			const unsigned d = prog_depth(wj);
-			const uint4 dn = d == 0 ? r0 : fitch_block(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
+			const uint4 dn = d == 0 ? r0 : merge_block<PLANAR>(dstack[(size_t) (d - 1 < D ? d - 1 : 0u) * T], us);   // d - 1 >= D: overflow is already flagged
 			if (prog_size(wj) > 1u) {
 				if (d < D) dstack[(size_t) d * T] = dn; else overflow = true;
 			}
 			my_depth = max(my_depth, d);
 			CU[(size_t) j * rs] = ux;
-			CM[(size_t) j * rs] = fitch_block(ux, dn);
+			CM[(size_t) j * rs] = merge_block<PLANAR>(ux, dn);
 			if (col == 0) {
 				cprog[j * 32u] = wj;
 				if (j == 0) first_edge = prog_edge(wj);
@@ -307,6 +308,7 @@ k_build_children(PoolView parent, PoolView child, Layout L, unsigned m, const ui
 // Eager variant: the child's MIDPOINT sets are not stored; each is scored against the taxon the child will
 // receive next, and the per-position costs go to the child's header.  A child's W columns sit in consecutive
 // threads of ONE CTA (whole children per CTA), their costs meet in shared memory.
+template <bool PLANAR>
 #ifdef XMP_EAGER_MIN_CTAS            // A/B knob (scripts/build_variant.sh): register target as CTAs of 128 threads per SM
 __global__ void __launch_bounds__(128, XMP_EAGER_MIN_CTAS)
 #else
@@ -352,7 +354,7 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 			unsigned *ch = hdr_of(child, L, cslot);
 			unsigned *cprog = ch + L.off_prog * 32u, *ccost = ch + L.off_cost * 32u;
 			ChildWalk cw;
-			const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow, CU);
+			const unsigned n_up = cw.init<PLANAR>(ph, L, m, P, PU, rt, upath, T, D, overflow, CU);
 			unsigned wj, first_edge = 0;
 			uint4 ux, us;
 			unsigned pw1 = cw.word_for(1);                  // Ec >= 5
@@ -367,16 +369,16 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 				pw1 = pw2;
 				const unsigned d = prog_depth(wj);
 				uint4 dn = r0;
-				if (d) dn = fitch_block(lds128(ds0 + (d - 1 < D ? d - 1 : 0u) * SB), us);   // d - 1 >= D: overflow is already flagged
+				if (d) dn = merge_block<PLANAR>(lds128(ds0 + (d - 1 < D ? d - 1 : 0u) * SB), us);   // d - 1 >= D: overflow is already flagged
 				if (prog_size(wj) > 1u) {
 					if (d < D) sts128(ds0 + d * SB, dn); else overflow = true;
 				}
 				my_depth = max(my_depth, d);
 				*cu_at = ux;
-				const uint4 mid = fitch_block(ux, dn);
+				const uint4 mid = merge_block<PLANAR>(ux, dn);
 				unsigned c;
-				if (w1) c = cost_word_w1(mid.x, rn.x) + cost_word_w1(mid.y, rn.y) + cost_word_w1(mid.z, rn.z) + cost_word_w1(mid.w, rn.w);
-				else c = cost_block(mid, rn, col, wp);
+				if (w1) c = score_block_w1<PLANAR>(mid, rn);
+				else c = score_block<PLANAR>(mid, rn, col, wp);
 				if (W == 1) *cost_at = c;
 				else if (c) atomicAdd(&acc[lc * Ec + j], c);
 				if (col == 0) {
@@ -423,7 +425,7 @@ k_build_children_eager(PoolView parent, PoolView child, Layout L, unsigned m, co
 // edge's MIDPOINT on the fly, score the last taxon on it (group-shuffle sum over the columns), apply the
 // acceptance test and emit complete trees.  This replaces k_build_children for the deepest pool and the
 // whole k_expand_score pass over it -- where almost all nodes of a search live.
-template <int G>
+template <int G, bool PLANAR>
 __global__ void __launch_bounds__(128)
 k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restrict__ surv, const unsigned *n_surv_ptr,
                     unsigned s_begin, unsigned s_end, const uint4 *__restrict__ rows, WeightPlanes wp, unsigned rest_last,
@@ -459,7 +461,7 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 		const unsigned *ph = hdr_of(parent, L, pnode);
 		const uint4 *PU = sets_of(parent, L, pnode) + (size_t) up_row0(L, E) * rs + col;
 		ChildWalk cw;
-		const unsigned n_up = cw.init(ph, L, m, P, PU, rt, upath, T, D, overflow);
+		const unsigned n_up = cw.init<PLANAR>(ph, L, m, P, PU, rt, upath, T, D, overflow);
 		// the bound is a hot word: one lane per warp reads it, the others get it by shuffle
 		unsigned bound = 0;
 		if (lane == 0) bound = *(volatile unsigned *) bound_ptr;
@@ -475,14 +477,14 @@ k_expand_last_fused(PoolView parent, Layout L, unsigned m, const uint4 *__restri
 			if (j + 1 < Ec) cw.step_lean(j + 1, pw1, depth_n, internal_n, uxn, usn, upath, T, r0);
 			pw1 = pw2;
 			uint4 dn = r0;
-			if (depth) dn = fitch_block(lds128(ds0 + (depth - 1 < D ? depth - 1 : 0u) * SB), us);   // depth - 1 >= D: overflow is already flagged
+			if (depth) dn = merge_block<PLANAR>(lds128(ds0 + (depth - 1 < D ? depth - 1 : 0u) * SB), us);   // depth - 1 >= D: overflow is already flagged
 			if (internal) {
 				if (depth < D) sts128(ds0 + depth * SB, dn); else overflow = true;
 			}
-			const uint4 mid = fitch_block(ux, dn);
+			const uint4 mid = merge_block<PLANAR>(ux, dn);
 			unsigned c;
-			if (w1) c = cost_word_w1(mid.x, rl.x) + cost_word_w1(mid.y, rl.y) + cost_word_w1(mid.z, rl.z) + cost_word_w1(mid.w, rl.w);
-			else c = cost_block(mid, rl, col, wp);
+			if (w1) c = score_block_w1<PLANAR>(mid, rl);
+			else c = score_block<PLANAR>(mid, rl, col, wp);
 			if (!col_ok) c = 0;
 #pragma unroll
 			for (int o = G / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -553,6 +555,7 @@ __global__ void k_scatter_sets(PoolView pool, Layout L, unsigned m, unsigned lon
 }
 
 // Eager layout: cost of inserting taxon m at every position of the imported nodes, from their staged MIDPOINT sets.
+template <bool PLANAR>
 __global__ void k_stage_costs(PoolView pool, Layout L, unsigned m, unsigned long long first, unsigned n_jobs,
                               const uint8_t *__restrict__ topo, unsigned topo_stride, const uint4 *__restrict__ src,
                               const uint4 *__restrict__ taxon_row, WeightPlanes wp) {
@@ -563,7 +566,7 @@ __global__ void k_stage_costs(PoolView pool, Layout L, unsigned m, unsigned long
 	const unsigned e = topo[(size_t) j * 4 * topo_stride + 3 * topo_stride + i];
 	const uint4 *mid = src + ((size_t) j * 2 * E + e) * W;
 	unsigned c = 0;
-	for (unsigned b = 0; b < W; ++b) c += cost_block(mid[b], __ldg(taxon_row + b), b, wp);
+	for (unsigned b = 0; b < W; ++b) c += score_block<PLANAR>(mid[b], __ldg(taxon_row + b), b, wp);
 	hdr_of(pool, L, first + j)[(L.off_cost + i) * 32u] = c;
 }
 
@@ -592,6 +595,12 @@ __global__ void k_filter_trees(const uint8_t *__restrict__ src, unsigned n_src, 
 }
 
 __global__ void k_lower_bound(unsigned *bound_ptr, unsigned value) { atomicMin(bound_ptr, value); }
+
+// The alignment rows in planar form (fitch_dev.cuh), for a search run with XMP_SEARCH_PLANAR=1.
+__global__ void k_rows_to_planar(const uint4 *__restrict__ in, uint4 *__restrict__ out, unsigned long long n) {
+	const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = to_planar(in[i]);
+}
 
 // The beam of the greedy dive: keeps the `keep` cheapest entries of a survivor list (by the length of the child tree,
 // surv[i].z), on the device -- one CTA, a histogram of lengths above the minimum, a threshold, a compaction.  Ties at
@@ -682,6 +691,12 @@ struct Search {
 	unsigned *d_maxdepth = nullptr, *d_overflow = nullptr;
 	xmp_search_stats st;
 	Scratch topo, pathbuf, stage;
+	// XMP_SEARCH_PLANAR=1 (an A/B switch, off by default): every state set of the search -- the rows below, the pools, the staged
+	// sets of imported subtrees -- is kept in planar form (fitch_dev.cuh).  The form is closed under merging and preserves costs
+	// (tests/child_walk_check.cu), and nothing but paths and lengths ever leaves a search, so results cannot depend on it.
+	bool planar = false;
+	const uint4 *rows = nullptr;          // the alignment rows the search's kernels read: ctx->d_rows, or their planar copy
+	Scratch prows;
 };
 
 // Scheduler knobs (defaults chosen on B200, see profiles/r01_search_tuning.md; overridable for tuning):
@@ -720,6 +735,7 @@ void search_destroy(xmp_ctx *ctx) {
 	S->topo.release();
 	S->pathbuf.release();
 	S->stage.release();
+	S->prows.release();
 	delete S;
 	ctx->search = nullptr;
 }
@@ -874,7 +890,8 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			XMP_CUDA(cudaMemcpyAsync(S->pathbuf.ptr, sel.data() + done * L.n, (size_t) part * L.n, cudaMemcpyHostToDevice, ctx->stream));
 			rc = S->stage.reserve((size_t) part * 2 * P.E * L.W * 16);
 			if (rc) return rc;
-			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, (uint4 *) S->stage.ptr, (size_t) 2 * P.E * L.W, true, S->d_len);
+			rc = launch_build_sets(ctx, (const uint8_t *) S->topo.ptr, stride, part, m, (uint4 *) S->stage.ptr, (size_t) 2 * P.E * L.W, true, S->d_len,
+			                       S->planar ? S->rows : nullptr);
 			if (rc) return rc;
 			{
 				const unsigned long long threads = (unsigned long long) part * E * L.W;
@@ -887,8 +904,12 @@ static int import_nodes(xmp_ctx *ctx, Search *S, const uint8_t *jobs, unsigned n
 			XMP_CUDA(cudaGetLastError());
 			if (S->eager) {
 				const unsigned long long threads = (unsigned long long) part * E;
-				k_stage_costs<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
-				                                                                         (const uint4 *) S->stage.ptr, ctx->d_rows + (size_t) m * L.W, ctx->wp);
+				if (S->planar)
+					k_stage_costs<true><<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
+					                                                                               (const uint4 *) S->stage.ptr, S->rows + (size_t) m * L.W, ctx->wp);
+				else
+					k_stage_costs<false><<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, tail, part, (const uint8_t *) S->topo.ptr, stride,
+					                                                                                (const uint4 *) S->stage.ptr, S->rows + (size_t) m * L.W, ctx->wp);
 				XMP_CUDA(cudaGetLastError());
 			}
 			XMP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -905,7 +926,7 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	const Layout &L = S->L;
 	Pool &P = S->pool[m];
 	const int last = (m + 1 == S->n);
-	const uint4 *row = ctx->d_rows + (size_t) m * L.W;
+	const uint4 *row = S->rows + (size_t) m * L.W;
 	const unsigned rest = ctx->rest_bound[m];
 	const unsigned sc = shard ? S->prm.shard_count : 1u, si = shard ? S->prm.shard_index : 0u;
 	// whole tiles of the pool's record layout are enumerated; slots outside the batch are masked in the kernel
@@ -922,10 +943,15 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 		S->st.launches += 1;
 		return XMP_OK;
 	}
-#define XMP_EXPAND(G)                                                                                                   \
-	k_expand_score<G><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
-	                                                                              S->d_bound, last, surv, nsurv, trees,             \
-	                                                                              S->d_ntrees, room, sc, si, S->d_peers)
+#define XMP_EXPAND_F(G, F)                                                                                                 \
+	k_expand_score<G, F><<<(unsigned) ((pairs * G + 255) / 256), 256, 0, ctx->stream>>>(P.view(), L, m, first, chunk, row, ctx->wp, rest, \
+	                                                                                 S->d_bound, last, surv, nsurv, trees,             \
+	                                                                                 S->d_ntrees, room, sc, si, S->d_peers)
+#define XMP_EXPAND(G)                    \
+	do {                                 \
+		if (S->planar) XMP_EXPAND_F(G, true); \
+		else XMP_EXPAND_F(G, false);     \
+	} while (0)
 	const unsigned W = L.W;
 	if (W > 16) XMP_EXPAND(32);
 	else if (W > 8) XMP_EXPAND(16);
@@ -934,6 +960,7 @@ static int launch_expand(xmp_ctx *ctx, Search *S, unsigned m, unsigned long long
 	else if (W > 1) XMP_EXPAND(2);
 	else XMP_EXPAND(1);
 #undef XMP_EXPAND
+#undef XMP_EXPAND_F
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -959,16 +986,28 @@ static int launch_children(xmp_ctx *ctx, Search *S, unsigned m, const uint4 *sur
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
 	if (S->eager) {
 		if (S->L.W > 1) smem += (size_t) (threads / S->L.W) * (2 * m - 1) * sizeof(unsigned);      // per-position costs of the CTA's children
-		XMP_CUDA(cudaFuncSetAttribute(k_build_children_eager, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-		k_build_children_eager<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-		                                                               ctx->d_rows, ctx->wp, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+		if (S->planar) {
+			XMP_CUDA(cudaFuncSetAttribute(k_build_children_eager<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_build_children_eager<true><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+			                                                                     S->rows, ctx->wp, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+		} else {
+			XMP_CUDA(cudaFuncSetAttribute(k_build_children_eager<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_build_children_eager<false><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+			                                                                      S->rows, ctx->wp, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+		}
 		XMP_CUDA(cudaGetLastError());
 		S->st.launches += 1;
 		return XMP_OK;
 	}
-	XMP_CUDA(cudaFuncSetAttribute(k_build_children, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	k_build_children<<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
-	                                                         ctx->d_rows, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+	if (S->planar) {
+		XMP_CUDA(cudaFuncSetAttribute(k_build_children<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_build_children<true><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+		                                                               S->rows, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+	} else {
+		XMP_CUDA(cudaFuncSetAttribute(k_build_children<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		k_build_children<false><<<blocks, threads, smem, ctx->stream>>>(P.view(), C.view(), S->L, m, surv, nsurv, s_begin, s_end, child_first % C.cap,
+		                                                                S->rows, S->d_merges, D, S->d_maxdepth + m + 1, S->d_overflow);
+	}
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -981,13 +1020,18 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	size_t smem = 0;
 	const unsigned threads = walk_threads(D, &smem);
 	const unsigned blocks = (unsigned) ctx->sm_count * 16;
-#define XMP_FUSED(G)                                                                                                          \
-	do {                                                                                                                      \
-		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
-		k_expand_last_fused<G><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
-		                                                            ctx->d_rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,     \
-		                                                            S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D, \
-		                                                            S->d_overflow, S->d_peers);                                   \
+#define XMP_FUSED_F(G, F)                                                                                                        \
+	do {                                                                                                                         \
+		XMP_CUDA(cudaFuncSetAttribute(k_expand_last_fused<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));          \
+		k_expand_last_fused<G, F><<<blocks, threads, smem, ctx->stream>>>(P.view(), L, m, surv, nsurv, s_begin, s_end,               \
+		                                                               S->rows, ctx->wp, ctx->rest_bound[m + 1], S->d_bound,         \
+		                                                               S->d_trees[S->cur], S->d_ntrees, S->trees_cap, S->d_merges, D, \
+		                                                               S->d_overflow, S->d_peers);                                   \
+	} while (0)
+#define XMP_FUSED(G)                         \
+	do {                                     \
+		if (S->planar) XMP_FUSED_F(G, true); \
+		else XMP_FUSED_F(G, false);          \
 	} while (0)
 	if (L.W == 1) XMP_FUSED(1);
 	else if (L.W == 2) XMP_FUSED(2);
@@ -996,6 +1040,7 @@ static int launch_fused(xmp_ctx *ctx, Search *S, unsigned m, unsigned s_begin, u
 	else if (L.W <= 16) XMP_FUSED(16);
 	else XMP_FUSED(32);
 #undef XMP_FUSED
+#undef XMP_FUSED_F
 	XMP_CUDA(cudaGetLastError());
 	S->st.launches += 1;
 	return XMP_OK;
@@ -1346,6 +1391,7 @@ static void init_knobs(xmp_ctx *ctx, Search *S) {
 	S->sweep = env_unsigned("XMP_SWEEP", 1) != 0;
 	S->sweep_fallback = env_unsigned("XMP_SWEEP_FALLBACK", 1);
 	S->sweep_levels = std::max(env_unsigned("XMP_SWEEP_LEVELS", 6), 1u);
+	S->planar = env_unsigned("XMP_SEARCH_PLANAR", 0) != 0;
 	for (unsigned m = 0; m < XMP_MAX_TAXA + 2; ++m) S->rate[m] = 1.0;
 	memset(&S->st, 0, sizeof S->st);
 }
@@ -1572,6 +1618,16 @@ extern "C" int xmp_cuda_search_begin(xmp_ctx *ctx, const xmp_search_params *para
 	auto fail = [&](int rc) { search_destroy(ctx); return rc; };
 	int rc = alloc_search(ctx, S, ctx->n_blocks);
 	if (rc) return fail(rc);
+	S->rows = ctx->d_rows;
+	if (S->planar) {
+		const unsigned long long nb = (unsigned long long) ctx->num_taxa * ctx->n_blocks;
+		rc = S->prows.reserve((size_t) nb * sizeof(uint4));
+		if (rc) return fail(rc);
+		k_rows_to_planar<<<(unsigned) ((nb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_rows, (uint4 *) S->prows.ptr, nb);
+		const cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return fail(cuda_failed(e, "k_rows_to_planar", __FILE__, __LINE__));
+		S->rows = (const uint4 *) S->prows.ptr;
+	}
 	S->book.trec = S->L.trec;
 	S->book.n = S->L.n;
 	S->book.max_trees = S->prm.max_trees;
