@@ -425,7 +425,7 @@ def run_reference_bandb(names, budget_s=120.0):
 REF_MPI_SAME_BOX = ["h4", "mh3", "its36", "h5", "Metazoan", "rbc14x759", "h1", "mh1", "mt-10"]
 
 
-def run_reference_bandb_mpi(names, workers, budget_s=90.0):
+def run_reference_bandb_mpi(names, workers, budget_s=60.0):
     """`xmpirun -n workers + 1 fastdnamp_ref_mpi <the golden's flags>` per dataset, one after the other (each run uses every
     core), until the time budget is spent.  Returns {name: {"s": its "Time to perform branch and bound search", "workers": W}}
     for the runs that reproduced the golden score and tree count.  Test infrastructure used as a reported CPU baseline only."""
