@@ -461,7 +461,7 @@ k_score_trees_wide(const uint4 *__restrict__ rows, unsigned n_blocks, WeightPlan
 			const uint4 w = lds128(at);
 			const uint4 a = lds128(me + w.x), b = lds128(me + w.y);
 			const uint4 d = PLANAR ? fitch_block_planar(a, b) : fitch_block(a, b);
-			sts128(me + w.w, d);
+			if (w.w != DUMMY * SB) sts128(me + w.w, d);               // a leaf's DOWN set is read by nobody: 8 of 13 stores at m = 8 (uniform per warp)
 			const uint4 ue = lds128(me + w.z);
 			const uint4 mid = PLANAR ? fitch_block_planar(ue, d) : fitch_block(ue, d);
 			unsigned c;
